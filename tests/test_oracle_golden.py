@@ -1,0 +1,91 @@
+"""Pins oracle/block_oracle.py (the CPU restatement) against outputs of the UNMODIFIED reference:
+committed golden vectors (tests/golden, made by oracle/make_golden.py) and, when /root/reference
+is present (build container only), the imported reference modules live."""
+import pytest
+import torch
+
+from oracle import block_oracle as bo
+from oracle.ref_loader import reference_available, load_reference_gnn
+from tests.util import nerr, run_oracle_block, upstream
+
+CASES = ["dense_train", "dense_eval", "dense_train_u0", "dense_train_T5", "dense_train_F16", "dense_train_F4",
+         "dense_unnormed", "permuted_train", "class_major_train", "shuffled_train", "sparse_train", "sparse_eval",
+         "duplicates_train"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_restatement_matches_reference_fp64(golden_block_cases, name):
+    case = golden_block_cases[name]
+    outs, gin, gparam, buffers = run_oracle_block(bo, case, torch.float64)
+    for k in outs:
+        assert nerr(outs[k], case["out_f64"][k]) < 1e-10, k
+    for k in gin:
+        assert nerr(gin[k], case["gin_f64"][k]) < 1e-8, k
+    assert set(gparam) == set(case["gparam_f64"])
+    scale = max(v.abs().max().item() for v in case["gparam_f64"].values())
+    for k, g in gparam.items():
+        ref = case["gparam_f64"][k]
+        # analytically-zero gradients (biases feeding a train-mode BN) are noise in the reference too
+        assert (g - ref).abs().max().item() <= 1e-8 * max(scale, ref.abs().max().item()), k
+    if case["training"] and case.get("normed", True):
+        for k, v in case["buffers_f64"].items():
+            if k.endswith("num_batches_tracked"):
+                assert int(buffers[k]) == int(v), k
+            else:
+                assert nerr(buffers[k], v) < 1e-10, k
+
+
+def test_double_norm_is_pinned(golden_block_cases):
+    """edge BatchNorm gets two running-stat updates per forward, node BatchNorms one."""
+    b = golden_block_cases["dense_train"]["buffers_f64"]
+    assert int(b["edge_model.norm.num_batches_tracked"]) == 2
+    assert int(b["s_model.norm.num_batches_tracked"]) == 1
+    assert int(b["t_model.norm.num_batches_tracked"]) == 1
+
+
+def test_gnn_shipped_weights_fp64(golden_gnn_case):
+    case = golden_gnn_case
+    ck_state = None
+    if reference_available():
+        ck_state = torch.load("/root/reference/params/model_gnn_0.pth", map_location="cpu",
+                              weights_only=False)["model_state"]
+    else:
+        pytest.skip("shipped checkpoint only exists in the build container")
+    sd = bo.cast_state(ck_state, torch.float64)
+    for training in (True, False):
+        x_s, x_t, x_e, u = bo.gnn_forward(sd, 3, case["edge_index"], case["x_s"], case["x_t"], case["x_e"], case["u"],
+                                          training=training, buffers={})
+        time = bo.edge_prediction(sd, x_e, scale=42 / 12)
+        gold = case[("train_" if training else "eval_") + "f64"]
+        assert nerr(x_e, gold["x_e"]) < 1e-9
+        assert nerr(x_s, gold["x_s"]) < 1e-9
+        assert nerr(x_t, gold["x_t"]) < 1e-9
+        assert nerr(u, gold["u"]) < 1e-9
+        assert nerr(time, gold["time"]) < 1e-9
+
+
+@pytest.mark.skipif(not reference_available(), reason="/root/reference only exists in the build container")
+def test_restatement_matches_live_reference():
+    ref = load_reference_gnn()
+    torch.manual_seed(5)
+    F, S, T = 10, 37, 12
+    sd = bo.random_block_state(F, seed=77, dtype=torch.float64)
+    blk = ref.Block(F).double()
+    blk.load_state_dict(sd, strict=True)
+    blk.train()
+    edge_index = bo.complete_bipartite(S, T)[:, torch.randperm(S * T)[: S * T // 2]]
+    x_s, x_t = torch.randn(S, F, dtype=torch.float64), torch.randn(T, F, dtype=torch.float64)
+    x_e, u = torch.randn(edge_index.shape[1], F, dtype=torch.float64), torch.randn(1, F, dtype=torch.float64)
+    _, r_s, r_t, r_e, r_u = blk((edge_index, x_s, x_t, x_e, u))
+    o_s, o_t, o_e, o_u = bo.block(sd, "", edge_index, x_s, x_t, x_e, u, training=True, buffers={})
+    for a, b in ((o_s, r_s), (o_t, r_t), (o_e, r_e), (o_u, r_u)):
+        assert nerr(a, b) < 1e-10
+
+
+def test_integer_time_definition():
+    time = torch.tensor([3.0, 5.0, 9.0, 2.9])
+    hours = torch.tensor([2.0, 6.0])
+    tgt = torch.tensor([0, 0, 1, 1])
+    visits, t_int = bo.integer_times(time, hours, tgt)
+    assert visits.tolist() == [2.0, 2.0, 2.0, 0.0]      # 1.5 -> 2 and 2.5 -> 2: round-half-even
+    assert t_int.tolist() == [4.0, 4.0, 12.0, 0.0]
