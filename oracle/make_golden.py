@@ -104,7 +104,8 @@ def run_gnn_case(ref, S, seed):
     x_e = 2.0 + 8.0 * torch.rand(S * T, F, generator=gen, dtype=torch.float64)
     u = torch.zeros(1, F, dtype=torch.float64)
     out = {"S": S, "T": T, "F": F, "edge_index": edge_index, "x_s": x_s, "x_t": x_t, "x_e": x_e, "u": u,
-           "class_info": class_info}
+           "class_info": class_info,
+           "state": {k: v.clone() for k, v in sd.items()}}      # shipped params/model_gnn_0.pth weights
     for training in (True, False):
         for dtype, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
             model = ref.GNN(Fdim=F, B=3, F_s=1, F_t=2, T=T).to(dtype)

@@ -1,0 +1,193 @@
+"""ctypes binding of libpfs_b200.so (include/pfs_b200.h).
+
+This is the whole Python<->CUDA boundary: plain pointers and sizes, one argument struct per
+module, the caller's CUDA stream.  The library is built in-tree by `build_library()` (called from
+`__graft_entry__.build()`); importing this module never compiles anything.  There is NO CPU
+fallback: if the shared library is missing, or a tensor is not a contiguous fp32 CUDA tensor, the
+call raises.
+"""
+import ctypes as ct
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libpfs_b200.so")
+HEADER = os.path.join(os.path.dirname(_HERE), "include", "pfs_b200.h")
+
+PFS_LAYOUT_DENSE = 0
+PFS_LAYOUT_CSR = 1
+PFS_TILE_EDGES = 256
+ABI_VERSION = 1
+
+_P = ct.c_void_p
+
+
+def _fields(spec):
+    out = []
+    for ctype, names in spec:
+        for n in names.split():
+            out.append((n, ctype))
+    return out
+
+
+class TopologyStruct(ct.Structure):
+    _fields_ = _fields([
+        (ct.c_int32, "layout G F S T E"),
+        (_P, "csr_rowptr csr_eid csr_src csr_tgt tile_fibre"),
+        (ct.c_int32, "ntiles"),
+        (_P, "csc_colptr csc_q"),
+    ])
+
+
+class EdgeArgs(ct.Structure):
+    _fields_ = _fields([
+        (TopologyStruct, "topo"),
+        (_P, "x_s x_t x_e u w1 b1 w2 b2 gamma beta running_mean running_var num_batches_tracked"),
+        (ct.c_int32, "training normed"),
+        (ct.c_float, "eps momentum"),
+        (_P, "x_e_out bn_save g_out g_x_s g_x_t g_x_e g_u g_w1 g_b1 g_w2 g_b2 g_gamma g_beta workspace"),
+        (ct.c_size_t, "workspace_bytes"),
+        (_P, "stream"),
+    ])
+
+
+class SourceArgs(ct.Structure):
+    _fields_ = _fields([
+        (TopologyStruct, "topo"),
+        (_P, "x_s x_t x_e u w1 b1 w2 b2 w3 b3 w4 b4 gamma beta running_mean running_var num_batches_tracked"),
+        (ct.c_int32, "training normed"),
+        (ct.c_float, "eps momentum"),
+        (_P, "x_s_out moments hidden y_pre bn_save g_out g_x_s g_x_t g_x_e g_u "
+             "g_w1 g_b1 g_w2 g_b2 g_w3 g_b3 g_w4 g_b4 g_gamma g_beta workspace"),
+        (ct.c_size_t, "workspace_bytes"),
+        (_P, "stream"),
+    ])
+
+
+class TargetArgs(ct.Structure):
+    _fields_ = _fields([
+        (TopologyStruct, "topo"),
+        (_P, "x_s x_t x_e u w1 b1 w2 b2 w3 b3 w4 b4 gamma beta running_mean running_var num_batches_tracked"),
+        (ct.c_int32, "training normed"),
+        (ct.c_float, "eps momentum"),
+        (_P, "x_t_out act_sum y_pre bn_save g_out g_x_s g_x_t g_x_e g_u "
+             "g_w1 g_b1 g_w2 g_b2 g_w3 g_b3 g_w4 g_b4 g_gamma g_beta workspace"),
+        (ct.c_size_t, "workspace_bytes"),
+        (_P, "stream"),
+    ])
+
+
+class GlobalArgs(ct.Structure):
+    _fields_ = _fields([
+        (ct.c_int32, "G F S T"),
+        (_P, "x_s x_t u w1 b1 w2 b2 rms_weight"),
+        (ct.c_int32, "normed"),
+        (ct.c_float, "rms_eps"),
+        (_P, "u_out g_out g_x_s g_x_t g_u g_w1 g_b1 g_w2 g_b2 g_rms_weight workspace"),
+        (ct.c_size_t, "workspace_bytes"),
+        (_P, "stream"),
+    ])
+
+
+class HeadArgs(ct.Structure):
+    _fields_ = _fields([
+        (TopologyStruct, "topo"),
+        (_P, "x_e w1 b1 w2 b2"),
+        (ct.c_float, "scale"),
+        (_P, "class_hours edge_tgt time visits time_int g_time g_x_e g_w1 g_b1 g_w2 g_b2 workspace"),
+        (ct.c_size_t, "workspace_bytes"),
+        (_P, "stream"),
+    ])
+
+
+# every symbol include/pfs_b200.h declares: name -> (restype, argtypes)
+_I64, _I32 = ct.c_int64, ct.c_int32
+SYMBOLS = {
+    "pfs_abi_version": (ct.c_int, []),
+    "pfs_last_error": (ct.c_char_p, []),
+    "pfs_supports_fdim": (ct.c_int, [_I32]),
+    "pfs_sizeof_topology": (ct.c_size_t, []),
+    "pfs_sizeof_edge_args": (ct.c_size_t, []),
+    "pfs_sizeof_source_args": (ct.c_size_t, []),
+    "pfs_sizeof_target_args": (ct.c_size_t, []),
+    "pfs_sizeof_global_args": (ct.c_size_t, []),
+    "pfs_sizeof_head_args": (ct.c_size_t, []),
+    "pfs_workspace_bytes": (ct.c_size_t, [ct.POINTER(TopologyStruct)]),
+    "pfs_detect_dense": (ct.c_int, [_P, _I64, _I32, _I32, _P, _P]),
+    "pfs_build_topology_temp_bytes": (ct.c_size_t, [_I64, _I32, _I32]),
+    "pfs_build_topology": (ct.c_int, [_P, _I64, _I32, _I32] + [_P] * 9 + [_P, ct.c_size_t, _P]),
+    "pfs_edge_fwd": (ct.c_int, [ct.POINTER(EdgeArgs)]),
+    "pfs_edge_bwd": (ct.c_int, [ct.POINTER(EdgeArgs)]),
+    "pfs_source_fwd": (ct.c_int, [ct.POINTER(SourceArgs)]),
+    "pfs_source_bwd": (ct.c_int, [ct.POINTER(SourceArgs)]),
+    "pfs_target_fwd": (ct.c_int, [ct.POINTER(TargetArgs)]),
+    "pfs_target_bwd": (ct.c_int, [ct.POINTER(TargetArgs)]),
+    "pfs_global_fwd": (ct.c_int, [ct.POINTER(GlobalArgs)]),
+    "pfs_global_bwd": (ct.c_int, [ct.POINTER(GlobalArgs)]),
+    "pfs_time_head_fwd": (ct.c_int, [ct.POINTER(HeadArgs)]),
+    "pfs_time_head_bwd": (ct.c_int, [ct.POINTER(HeadArgs)]),
+}
+_SIZEOF_CHECKS = {
+    "pfs_sizeof_topology": TopologyStruct, "pfs_sizeof_edge_args": EdgeArgs, "pfs_sizeof_source_args": SourceArgs,
+    "pfs_sizeof_target_args": TargetArgs, "pfs_sizeof_global_args": GlobalArgs, "pfs_sizeof_head_args": HeadArgs,
+}
+
+
+class PfsError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def nvcc_command(out_path=LIB_PATH):
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    return [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
+            "-Xcompiler", "-fPIC", "-o", out_path, os.path.join(CSRC, "api.cu")]
+
+
+def build_library(force=False, verbose=False):
+    """Compile csrc/*.cu into csrc/libpfs_b200.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))] + [HEADER]
+    if not force and os.path.exists(LIB_PATH) and \
+            os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(s) for s in srcs):
+        return LIB_PATH
+    cmd = nvcc_command()
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.run(cmd, check=True, cwd=CSRC)
+    return LIB_PATH
+
+
+def load_library():
+    """dlopen the in-tree library, declare every prototype and verify the struct layouts."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PfsError("libpfs_b200.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                       "there is no CPU fallback for the message-passing layer")
+    lib = ct.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in SYMBOLS.items():
+        fn = getattr(lib, name)      # AttributeError if the library lacks a declared symbol
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if lib.pfs_abi_version() != ABI_VERSION:
+        raise PfsError("libpfs_b200.so ABI version %d != binding %d" % (lib.pfs_abi_version(), ABI_VERSION))
+    for fn, struct in _SIZEOF_CHECKS.items():
+        if getattr(lib, fn)() != ct.sizeof(struct):
+            raise PfsError("%s: C sizeof %d != ctypes %d" % (fn, getattr(lib, fn)(), ct.sizeof(struct)))
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load_library().pfs_last_error()
+        raise PfsError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()

@@ -1,0 +1,863 @@
+// api.cu -- extern "C" entry points of libpfs_b200.so (see include/pfs_b200.h).
+// Host-side orchestration only: argument checks, workspace carving, kernel launches on the
+// caller's stream.  No torch types, no synchronisation, no host allocation in the hot calls.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "edge_model.cuh"
+#include "node_ops.cuh"
+#include "source_model.cuh"
+#include "target_model.cuh"
+
+using namespace pfs;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define PFS_CUDA(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess) return fail(PFS_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+    } while (0)
+#define PFS_LAUNCH_CHECK(name)                                                                       \
+    do {                                                                                            \
+        cudaError_t e__ = cudaGetLastError();                                                       \
+        if (e__ != cudaSuccess) return fail(PFS_ERR_CUDA, "launch %s: %s", name, cudaGetErrorString(e__)); \
+    } while (0)
+#define PFS_REQUIRE(cond, msg)                                  \
+    do {                                                        \
+        if (!(cond)) return fail(PFS_ERR_ARG, "%s (%s)", msg, #cond); \
+    } while (0)
+#define PFS_TRY(expr)            \
+    do {                         \
+        int rc__ = (expr);       \
+        if (rc__ != PFS_OK) return rc__; \
+    } while (0)
+
+constexpr int kMaxCtas = 1024;
+
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return kNumSM;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = kNumSM;
+    }
+    return n;
+}
+
+// persistent grid: resident CTAs of this kernel on the whole device, capped by the work items
+template <class Kern>
+int persistent_grid(Kern kern, size_t smem, long long items) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    long long g = (long long)per_sm * num_sms();
+    if (g > kMaxCtas) g = kMaxCtas;
+    if (g > items) g = items;
+    return (int)(g < 1 ? 1 : g);
+}
+
+template <class Kern>
+int allow_smem(Kern kern, size_t smem) {
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(PFS_ERR_CUDA, "cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
+    }
+    return PFS_OK;
+}
+
+struct Bump {
+    char* p;
+    size_t left;
+    bool ok = true;
+    Bump(void* base, size_t bytes) : p((char*)base), left(bytes) {
+        const size_t mis = (size_t)((uintptr_t)p & 255);
+        if (mis) {
+            const size_t adv = 256 - mis;
+            if (adv > left) { ok = false; left = 0; } else { p += adv; left -= adv; }
+        }
+    }
+    float* f(size_t n) {
+        const size_t bytes = ((n * sizeof(float) + 255) / 256) * 256;
+        if (!ok || bytes > left) { ok = false; return nullptr; }
+        float* r = (float*)p;
+        p += bytes;
+        left -= bytes;
+        return r;
+    }
+};
+
+int dense_fpt(int T) { return T > 0 ? kTile / T : 0; }
+int dense_ntiles(int S, int T) {
+    const int fpt = dense_fpt(T);
+    return fpt > 0 ? (S + fpt - 1) / fpt : 0;
+}
+int node_ntiles(int S) { return (S + kNodeRows - 1) / kNodeRows; }
+
+int make_topo(const pfs_topology& t, Topo& o) {
+    PFS_REQUIRE(t.G >= 1 && t.S >= 1 && t.T >= 1 && t.E >= 0 && t.F >= 2, "bad topology sizes");
+    o.layout = t.layout; o.G = t.G; o.F = t.F; o.S = t.S; o.T = t.T; o.E = t.E;
+    o.rowptr = t.csr_rowptr; o.eid = t.csr_eid; o.csrc = t.csr_src; o.ctgt = t.csr_tgt;
+    o.tile_fibre = t.tile_fibre; o.colptr = t.csc_colptr; o.cscq = t.csc_q;
+    if (t.layout == PFS_LAYOUT_DENSE) {
+        if ((long long)t.S * t.T != t.E) return fail(PFS_ERR_ARG, "dense layout needs E == S*T");
+        o.fpt = dense_fpt(t.T);
+        if (o.fpt < 1)
+            return fail(PFS_ERR_UNSUPPORTED, "dense layout with T=%d > %d classes per fibre is not supported by this build",
+                        t.T, kTile);
+        o.ntiles = dense_ntiles(t.S, t.T);
+    } else if (t.layout == PFS_LAYOUT_CSR) {
+        PFS_REQUIRE(t.csr_rowptr && t.csr_src && t.csr_tgt && t.tile_fibre && t.csc_colptr && t.csc_q && t.ntiles >= 1,
+                    "CSR layout needs the arrays of pfs_build_topology");
+        o.fpt = 0;
+        o.ntiles = t.ntiles;
+    } else {
+        return fail(PFS_ERR_ARG, "unknown layout %d", t.layout);
+    }
+    return PFS_OK;
+}
+
+bool fdim_supported(int F) { return F == 4 || F == 8 || F == 10 || F == 16; }
+
+#define PFS_DISPATCH_F(Fv, CALL)                                   \
+    switch (Fv) {                                                  \
+        case 4: { constexpr int kF = 4; CALL; } break;            \
+        case 8: { constexpr int kF = 8; CALL; } break;            \
+        case 10: { constexpr int kF = 10; CALL; } break;          \
+        case 16: { constexpr int kF = 16; CALL; } break;          \
+        default: return fail(PFS_ERR_UNSUPPORTED, "Fdim=%d has no compiled kernels (built: 4, 8, 10, 16)", Fv); \
+    }
+
+// ---- small launch helpers ---------------------------------------------------------------
+template <int K, int J>
+int node_linear(const float* x, int rows, int G, const float* W, int ldw, int koff, const float* bias,
+                const float* addvec, float* out, cudaStream_t st) {
+    const long long N = (long long)rows * G;
+    if (N == 0) return PFS_OK;
+    long long blocks = (N + kThreads - 1) / kThreads;
+    if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
+    k_node_linear<K, J><<<(int)blocks, kThreads, 0, st>>>(x, rows, G, W, ldw, koff, bias, addvec, out);
+    PFS_LAUNCH_CHECK("k_node_linear");
+    return PFS_OK;
+}
+template <int K, int J>
+int node_linear_bwd(const float* d, long long N, const float* W, int ldw, int koff, float* dx, cudaStream_t st) {
+    if (N == 0) return PFS_OK;
+    long long blocks = (N + kThreads - 1) / kThreads;
+    if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
+    k_node_linear_bwd<K, J, false><<<(int)blocks, kThreads, 0, st>>>(d, N, W, ldw, koff, dx);
+    PFS_LAUNCH_CHECK("k_node_linear_bwd");
+    return PFS_OK;
+}
+int reduce_partials(const float* partial, int ncta, int pstride, int poff, int n, int cols, float* out, int ldo,
+                    int coff, cudaStream_t st) {
+    k_reduce_partials<<<(n + 127) / 128, 128, 0, st>>>(partial, ncta, pstride, poff, n, cols, out, ldo, coff);
+    PFS_LAUNCH_CHECK("k_reduce_partials");
+    return PFS_OK;
+}
+int colsum_all(const float* x, long long N, int ld, int off, int J, float* out, cudaStream_t st) {
+    k_colsum_all<<<(J + 31) / 32, dim3(32, 8), 0, st>>>(x, N, ld, off, J, out);
+    PFS_LAUNCH_CHECK("k_colsum_all");
+    return PFS_OK;
+}
+int colsum_graph(const float* x, int rows, int J, int G, float* out, cudaStream_t st) {
+    k_colsum_graph<<<dim3((J + 31) / 32, G), dim3(32, 8), 0, st>>>(x, rows, J, out);
+    PFS_LAUNCH_CHECK("k_colsum_graph");
+    return PFS_OK;
+}
+int outer_graphs(const float* a, const float* b, int G, int J, int K, float* out, int ldo, int koff, cudaStream_t st) {
+    k_outer_graphs<<<(J * K + 127) / 128, 128, 0, st>>>(a, b, G, J, K, out, ldo, koff);
+    PFS_LAUNCH_CHECK("k_outer_graphs");
+    return PFS_OK;
+}
+// dW[:, coff:coff+K] = D^T X and (optionally) db = column sums of D, over N rows
+template <int J, int K, int TJ, int TK>
+int outer_rows(const float* D, const float* X, long long N, float* scratch_partial, float* dW, int ldo, int coff,
+               float* db, cudaStream_t st) {
+    constexpr size_t smem = outer_rows_smem<J, K, TJ, TK>();
+    auto kern = k_outer_rows<J, K, TJ, TK>;
+    PFS_TRY(allow_smem(kern, smem));
+    const long long tiles = (N + kTile - 1) / kTile;
+    const int grid = persistent_grid(kern, smem, tiles);
+    constexpr int pstride = J * K + J;
+    kern<<<grid, kThreads, smem, st>>>(D, X, N, scratch_partial, pstride);
+    PFS_LAUNCH_CHECK("k_outer_rows");
+    PFS_TRY(reduce_partials(scratch_partial, grid, pstride, 0, J * K, K, dW, ldo, coff, st));
+    if (db) PFS_TRY(reduce_partials(scratch_partial, grid, pstride, J * K, J, J, db, J, 0, st));
+    return PFS_OK;
+}
+// class-side sums: dense -> second stage over per-tile partials; CSR -> class-sorted segment sums
+int class_sums(const Topo& tp, const float* part_or_rows, int J, float* out, cudaStream_t st) {
+    if (tp.layout == PFS_LAYOUT_DENSE) {
+        const int TJ = tp.T * J;
+        k_class_reduce<<<dim3((TJ + 127) / 128, tp.G), 128, 0, st>>>(part_or_rows, tp.ntiles, TJ, out);
+        PFS_LAUNCH_CHECK("k_class_reduce");
+    } else {
+        k_csc_segment_sum<<<dim3((tp.T + 3) / 4, tp.G), 128, 0, st>>>(part_or_rows, tp.colptr, tp.cscq, tp.E, tp.T, J, out);
+        PFS_LAUNCH_CHECK("k_csc_segment_sum");
+    }
+    return PFS_OK;
+}
+size_t class_stage_floats(const Topo& tp, int J) {
+    return tp.layout == PFS_LAYOUT_DENSE ? (size_t)tp.G * tp.ntiles * tp.T * J : (size_t)tp.G * tp.E * J;
+}
+int bn_forward_tail(int F, int G, long long rows, const float* partial, int ntiles, int twice, int training,
+                    const float* gamma, const float* beta, float* rm, float* rv, long long* nbt, float eps,
+                    float momentum, float* save, cudaStream_t st) {
+    const int n = G * F;
+    if (training) {
+        if (rows <= 1) return fail(PFS_ERR_ARG, "Expected more than 1 value per channel when training");
+        k_bn_finalize<<<(n + 127) / 128, 128, 0, st>>>(partial, ntiles, bn_partial_stride(F), F, G, gamma, beta, eps,
+                                                        twice, save);
+        PFS_LAUNCH_CHECK("k_bn_finalize");
+        if (rm && rv) {
+            k_bn_running<<<1, 64, 0, st>>>(save, F, G, rows, gamma, beta, eps, momentum, twice, rm, rv, nbt);
+            PFS_LAUNCH_CHECK("k_bn_running");
+        }
+    } else {
+        PFS_REQUIRE(rm && rv, "eval-mode BatchNorm needs running_mean / running_var");
+        k_bn_eval_coeffs<<<(n + 127) / 128, 128, 0, st>>>(rm, rv, F, G, gamma, beta, eps, twice, save);
+        PFS_LAUNCH_CHECK("k_bn_eval_coeffs");
+    }
+    return PFS_OK;
+}
+int affine_rows(const float* in, const float* save, int F, long long rows, int G, float* out, cudaStream_t st) {
+    const long long total = rows * F * G;
+    if (total == 0) return PFS_OK;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
+    k_affine_rows<<<(int)blocks, 256, 0, st>>>(in, save, F, rows * F, G, out);
+    PFS_LAUNCH_CHECK("k_affine_rows");
+    return PFS_OK;
+}
+
+// ==========================================================================================
+// EdgeModel
+// ==========================================================================================
+template <int F>
+int edge_tables(const pfs_edge_args& a, const Topo& tp, float* uvec, float* Ps, float* Pt, cudaStream_t st) {
+    constexpr int H = 4 * F;
+    PFS_TRY((node_linear<F, H>(a.u, 1, tp.G, a.w1, H, 3 * F, a.b1, nullptr, uvec, st)));
+    PFS_TRY((node_linear<F, H>(a.x_t, tp.T, tp.G, a.w1, H, F, nullptr, uvec, Pt, st)));
+    PFS_TRY((node_linear<F, H>(a.x_s, tp.S, tp.G, a.w1, H, 0, nullptr, nullptr, Ps, st)));
+    return PFS_OK;
+}
+
+template <int F>
+int edge_fwd_impl(const pfs_edge_args& a, const Topo& tp) {
+    constexpr int H = 4 * F;
+    cudaStream_t st = (cudaStream_t)a.stream;
+    const int total = tp.ntiles * tp.G;
+    Bump ws(a.workspace, a.workspace_bytes);
+    float* uvec = ws.f((size_t)tp.G * H);
+    float* Ps = ws.f((size_t)tp.G * tp.S * H);
+    float* Pt = ws.f((size_t)tp.G * tp.T * H);
+    float* part = ws.f((size_t)total * bn_partial_stride(F));
+    if (!ws.ok) return fail(PFS_ERR_WORKSPACE, "edge_fwd: workspace too small (%zu B)", a.workspace_bytes);
+    PFS_TRY(edge_tables<F>(a, tp, uvec, Ps, Pt, st));
+    const bool stats = a.normed && a.training;
+    EdgeFwdParams p{tp, a.x_e, Ps, Pt, a.w1, a.w2, a.b2, a.x_e_out, stats ? part : nullptr};
+    const int grid = persistent_grid(k_edge_fwd<F>, 0, total);
+    k_edge_fwd<F><<<grid, kThreads, 0, st>>>(p);
+    PFS_LAUNCH_CHECK("k_edge_fwd");
+    if (a.normed) {
+        PFS_REQUIRE(a.gamma && a.beta && a.bn_save, "normed edge model needs gamma, beta, bn_save");
+        PFS_TRY(bn_forward_tail(F, tp.G, tp.E, part, tp.ntiles, 1, a.training, a.gamma, a.beta, a.running_mean,
+                                a.running_var, (long long*)a.num_batches_tracked, a.eps, a.momentum, a.bn_save, st));
+        PFS_TRY(affine_rows(a.x_e_out, a.bn_save, F, tp.E, tp.G, a.x_e_out, st));
+    }
+    return PFS_OK;
+}
+
+template <int F>
+int edge_bwd_impl(const pfs_edge_args& a, const Topo& tp) {
+    constexpr int H = 4 * F;
+    cudaStream_t st = (cudaStream_t)a.stream;
+    const int total = tp.ntiles * tp.G;
+    const int mode = !a.normed ? 0 : (a.training ? 1 : 2);
+    using SM = EdgeBwdSmem<F>;
+    auto kern = k_edge_bwd<F>;
+    PFS_TRY(allow_smem(kern, SM::bytes));
+    const int grid = persistent_grid(kern, SM::bytes, total);
+    constexpr int pstride = 2 * H * F + F;
+    Bump ws(a.workspace, a.workspace_bytes);
+    float* uvec = ws.f((size_t)tp.G * H);
+    float* Ps = ws.f((size_t)tp.G * tp.S * H);
+    float* Pt = ws.f((size_t)tp.G * tp.T * H);
+    float* coef = ws.f((size_t)tp.G * 6 * F);
+    float* statp = ws.f((size_t)total * 2 * F);
+    float* dgb = ws.f((size_t)tp.G * 2 * F);
+    float* dPs = ws.f((size_t)tp.G * tp.S * H);
+    float* stage = ws.f(class_stage_floats(tp, H));
+    float* dPt = ws.f((size_t)tp.G * tp.T * H);
+    float* tot = ws.f((size_t)tp.G * H);
+    float* wpart = ws.f((size_t)grid * pstride);
+    float* opart = ws.f((size_t)kMaxCtas * (H * F + H));
+    if (!ws.ok) return fail(PFS_ERR_WORKSPACE, "edge_bwd: workspace too small (%zu B)", a.workspace_bytes);
+    PFS_TRY(edge_tables<F>(a, tp, uvec, Ps, Pt, st));
+    const int n = tp.G * F;
+    k_edge_bn_bwd_coef<<<(n + 127) / 128, 128, 0, st>>>(0, mode, F, tp.G, tp.ntiles, tp.E, a.bn_save, a.gamma, a.beta,
+                                                         a.running_mean, a.running_var, a.eps, statp, coef, dgb);
+    PFS_LAUNCH_CHECK("k_edge_bn_bwd_coef/0");
+    if (mode != 0) {
+        EdgeBnStatParams sp{tp, a.x_e_out, a.g_out, coef, statp};
+        const int g2 = persistent_grid(k_edge_bn_bwd_stats<F>, 0, total);
+        k_edge_bn_bwd_stats<F><<<g2, kThreads, 0, st>>>(sp);
+        PFS_LAUNCH_CHECK("k_edge_bn_bwd_stats");
+        k_edge_bn_bwd_coef<<<(n + 127) / 128, 128, 0, st>>>(1, mode, F, tp.G, tp.ntiles, tp.E, a.bn_save, a.gamma,
+                                                             a.beta, a.running_mean, a.running_var, a.eps, statp, coef,
+                                                             dgb);
+        PFS_LAUNCH_CHECK("k_edge_bn_bwd_coef/1");
+        PFS_TRY(colsum_all(dgb, tp.G, 2 * F, 0, F, a.g_gamma, st));
+        PFS_TRY(colsum_all(dgb, tp.G, 2 * F, F, F, a.g_beta, st));
+    }
+    const bool dense = tp.layout == PFS_LAYOUT_DENSE;
+    EdgeBwdParams p{tp, a.x_e, a.x_e_out, a.g_out, Ps, Pt, a.w1, a.w2, coef, a.g_x_e, dPs,
+                    dense ? stage : nullptr, dense ? nullptr : stage, wpart, pstride};
+    kern<<<grid, kThreads, SM::bytes, st>>>(p);
+    PFS_LAUNCH_CHECK("k_edge_bwd");
+    PFS_TRY(reduce_partials(wpart, grid, pstride, 0, H * F, F, a.g_w1, H, 2 * F, st));
+    PFS_TRY(reduce_partials(wpart, grid, pstride, H * F, F * H, H, a.g_w2, H, 0, st));
+    PFS_TRY(reduce_partials(wpart, grid, pstride, 2 * H * F, F, F, a.g_b2, F, 0, st));
+    PFS_TRY(class_sums(tp, stage, H, dPt, st));
+    PFS_TRY((node_linear_bwd<F, H>(dPs, (long long)tp.G * tp.S, a.w1, H, 0, a.g_x_s, st)));
+    PFS_TRY((node_linear_bwd<F, H>(dPt, (long long)tp.G * tp.T, a.w1, H, F, a.g_x_t, st)));
+    PFS_TRY((outer_rows<H, F, 8, F / 2>(dPs, a.x_s, (long long)tp.G * tp.S, opart, a.g_w1, H, 0, nullptr, st)));
+    PFS_TRY((outer_rows<H, F, 8, F / 2>(dPt, a.x_t, (long long)tp.G * tp.T, opart, a.g_w1, H, F, nullptr, st)));
+    PFS_TRY(colsum_graph(dPt, tp.T, H, tp.G, tot, st));
+    PFS_TRY(colsum_all(tot, tp.G, H, 0, H, a.g_b1, st));
+    PFS_TRY(outer_graphs(tot, a.u, tp.G, H, F, a.g_w1, H, 3 * F, st));
+    PFS_TRY((node_linear_bwd<F, H>(tot, tp.G, a.w1, H, 3 * F, a.g_u, st)));
+    return PFS_OK;
+}
+
+// ==========================================================================================
+// SModel
+// ==========================================================================================
+template <int F>
+int source_fwd_impl(const pfs_source_args& a, const Topo& tp) {
+    constexpr int M = 2 * F;
+    cudaStream_t st = (cudaStream_t)a.stream;
+    const int total = tp.ntiles * tp.G;
+    const int ntn = node_ntiles(tp.S);
+    Bump ws(a.workspace, a.workspace_bytes);
+    float* Qt = ws.f((size_t)tp.G * tp.T * M);
+    float* partn = ws.f((size_t)tp.G * ntn * bn_partial_stride(F));
+    if (!ws.ok) return fail(PFS_ERR_WORKSPACE, "source_fwd: workspace too small (%zu B)", a.workspace_bytes);
+    PFS_TRY((node_linear<F, M>(a.x_t, tp.T, tp.G, a.w1, M, 0, a.b1, nullptr, Qt, st)));
+    {
+        SourceEdgeFwdParams p{tp, a.x_e, Qt, a.w1, a.w2, a.b2, a.moments};
+        const int grid = persistent_grid(k_source_edge_fwd<F>, 0, total);
+        k_source_edge_fwd<F><<<grid, kThreads, 0, st>>>(p);
+        PFS_LAUNCH_CHECK("k_source_edge_fwd");
+    }
+    {
+        using SM = SourceNodeFwdSmem<F>;
+        auto kern = k_source_node_fwd<F>;
+        PFS_TRY(allow_smem(kern, SM::bytes));
+        const bool stats = a.normed && a.training;
+        SourceNodeFwdParams p{tp.G, tp.S, a.x_s, a.u, a.moments, a.w3, a.b3, a.w4, a.b4, a.hidden, a.y_pre,
+                              stats ? partn : nullptr, ntn};
+        const int grid = persistent_grid(kern, SM::bytes, (long long)ntn * tp.G);
+        kern<<<grid, kThreads, SM::bytes, st>>>(p);
+        PFS_LAUNCH_CHECK("k_source_node_fwd");
+    }
+    if (a.normed) {
+        PFS_REQUIRE(a.gamma && a.beta && a.bn_save, "normed source model needs gamma, beta, bn_save");
+        PFS_TRY(bn_forward_tail(F, tp.G, tp.S, partn, ntn, 0, a.training, a.gamma, a.beta, a.running_mean,
+                                a.running_var, (long long*)a.num_batches_tracked, a.eps, a.momentum, a.bn_save, st));
+        PFS_TRY(affine_rows(a.y_pre, a.bn_save, F, tp.S, tp.G, a.x_s_out, st));
+    } else {
+        PFS_CUDA(cudaMemcpyAsync(a.x_s_out, a.y_pre, sizeof(float) * (size_t)tp.G * tp.S * F, cudaMemcpyDeviceToDevice, st));
+    }
+    return PFS_OK;
+}
+
+template <int F>
+int source_bwd_impl(const pfs_source_args& a, const Topo& tp) {
+    constexpr int M = 2 * F, J = 10 * F, K9 = 9 * F;
+    cudaStream_t st = (cudaStream_t)a.stream;
+    const int total = tp.ntiles * tp.G;
+    const int ntn = node_ntiles(tp.S);
+    const int mode = !a.normed ? 0 : (a.training ? 1 : 2);
+    using SMN = SourceNodeBwdSmem<F>;
+    using SME = SourceEdgeBwdSmem<F>;
+    auto kn = k_source_node_bwd<F>;
+    auto ke = k_source_edge_bwd<F>;
+    PFS_TRY(allow_smem(kn, SMN::bytes));
+    PFS_TRY(allow_smem(ke, SME::bytes));
+    const int gridn = persistent_grid(kn, SMN::bytes, (long long)ntn * tp.G);
+    const int gride = persistent_grid(ke, SME::bytes, total);
+    constexpr int pstride_n = J * K9 + F * J + F;
+    constexpr int pstride_e = M * F + M * M + M;
+    Bump ws(a.workspace, a.workspace_bytes);
+    float* Qt = ws.f((size_t)tp.G * tp.T * M);
+    float* bnstat = ws.f((size_t)tp.G * 2 * F);
+    float* coefA = ws.f((size_t)tp.G * tp.S * 4 * M);
+    float* tot3p = ws.f((size_t)tp.G * ntn * J);
+    float* tot3 = ws.f((size_t)tp.G * J);
+    float* wpn = ws.f((size_t)gridn * pstride_n);
+    float* stage = ws.f(class_stage_floats(tp, M));
+    float* dQt = ws.f((size_t)tp.G * tp.T * M);
+    float* wpe = ws.f((size_t)gride * pstride_e);
+    float* opart = ws.f((size_t)kMaxCtas * (M * F + M));
+    if (!ws.ok) return fail(PFS_ERR_WORKSPACE, "source_bwd: workspace too small (%zu B)", a.workspace_bytes);
+    if (mode != 0) {
+        k_bn_bwd_stats_rows<<<tp.G, kThreads, sizeof(float) * kWarps * 2 * F, st>>>(a.g_out, a.y_pre, a.bn_save, tp.S, F,
+                                                                                    a.eps, bnstat);
+        PFS_LAUNCH_CHECK("k_bn_bwd_stats_rows");
+        PFS_TRY(colsum_all(bnstat, tp.G, 2 * F, F, F, a.g_gamma, st));
+        PFS_TRY(colsum_all(bnstat, tp.G, 2 * F, 0, F, a.g_beta, st));
+    }
+    {
+        SourceNodeBwdParams p{tp.G, tp.S, ntn, mode, a.eps, a.x_s, a.moments, a.hidden, a.y_pre, a.g_out, a.bn_save,
+                              bnstat, a.w3, a.w4, a.g_x_s, coefA, tot3p, wpn, pstride_n};
+        kn<<<gridn, kThreads, SMN::bytes, st>>>(p);
+        PFS_LAUNCH_CHECK("k_source_node_bwd");
+    }
+    PFS_TRY(reduce_partials(wpn, gridn, pstride_n, 0, J * K9, K9, a.g_w3, J, 0, st));
+    PFS_TRY(reduce_partials(wpn, gridn, pstride_n, J * K9, F * J, J, a.g_w4, J, 0, st));
+    PFS_TRY(reduce_partials(wpn, gridn, pstride_n, J * K9 + F * J, F, F, a.g_b4, F, 0, st));
+    k_class_reduce<<<dim3((J + 127) / 128, tp.G), 128, 0, st>>>(tot3p, ntn, J, tot3);
+    PFS_LAUNCH_CHECK("k_class_reduce(tot3)");
+    PFS_TRY(colsum_all(tot3, tp.G, J, 0, J, a.g_b3, st));
+    PFS_TRY(outer_graphs(tot3, a.u, tp.G, J, F, a.g_w3, J, K9, st));
+    PFS_TRY((node_linear_bwd<F, J>(tot3, tp.G, a.w3, J, K9, a.g_u, st)));
+    PFS_TRY((node_linear<F, M>(a.x_t, tp.T, tp.G, a.w1, M, 0, a.b1, nullptr, Qt, st)));
+    {
+        const bool dense = tp.layout == PFS_LAYOUT_DENSE;
+        SourceEdgeBwdParams p{tp, a.x_e, Qt, a.w1, a.w2, a.b2, a.moments, coefA, a.g_x_e,
+                              dense ? stage : nullptr, dense ? nullptr : stage, wpe, pstride_e};
+        ke<<<gride, kThreads, SME::bytes, st>>>(p);
+        PFS_LAUNCH_CHECK("k_source_edge_bwd");
+    }
+    PFS_TRY(reduce_partials(wpe, gride, pstride_e, 0, M * F, F, a.g_w1, M, F, st));
+    PFS_TRY(reduce_partials(wpe, gride, pstride_e, M * F, M * M, M, a.g_w2, M, 0, st));
+    PFS_TRY(reduce_partials(wpe, gride, pstride_e, M * F + M * M, M, M, a.g_b2, M, 0, st));
+    PFS_TRY(class_sums(tp, stage, M, dQt, st));
+    PFS_TRY((node_linear_bwd<F, M>(dQt, (long long)tp.G * tp.T, a.w1, M, 0, a.g_x_t, st)));
+    PFS_TRY((outer_rows<M, F, F / 2, F / 2>(dQt, a.x_t, (long long)tp.G * tp.T, opart, a.g_w1, M, 0, a.g_b1, st)));
+    return PFS_OK;
+}
+
+// ==========================================================================================
+// TModel
+// ==========================================================================================
+TargetTailParams make_tail(const pfs_target_args& a, const Topo& tp) {
+    TargetTailParams p{};
+    p.G = tp.G; p.T = tp.T; p.F = tp.F;
+    p.mode = !a.normed ? 0 : (a.training ? 1 : 2);
+    p.eps = a.eps;
+    p.x_t = a.x_t; p.u = a.u; p.act_sum = a.act_sum;
+    p.colptr = tp.layout == PFS_LAYOUT_DENSE ? nullptr : tp.colptr;
+    p.dense_count = tp.S;
+    p.w2 = a.w2; p.b2 = a.b2; p.w3 = a.w3; p.b3 = a.b3; p.w4 = a.w4; p.b4 = a.b4;
+    p.gamma = a.gamma; p.beta = a.beta; p.rm = a.running_mean; p.rv = a.running_var;
+    p.y_pre = a.y_pre; p.x_t_out = a.x_t_out; p.bn_save = a.bn_save;
+    p.gout = a.g_out; p.g_x_t = a.g_x_t; p.g_u = a.g_u;
+    return p;
+}
+
+template <int F>
+int target_fwd_impl(const pfs_target_args& a, const Topo& tp) {
+    constexpr int M = 2 * F;
+    cudaStream_t st = (cudaStream_t)a.stream;
+    const int total = tp.ntiles * tp.G;
+    Bump ws(a.workspace, a.workspace_bytes);
+    float* Rs = ws.f((size_t)tp.G * tp.S * M);
+    float* stage = ws.f(class_stage_floats(tp, M));
+    if (!ws.ok) return fail(PFS_ERR_WORKSPACE, "target_fwd: workspace too small (%zu B)", a.workspace_bytes);
+    if (a.normed) PFS_REQUIRE(a.gamma && a.beta && a.bn_save, "normed target model needs gamma, beta, bn_save");
+    if (a.normed && a.training && tp.T <= 1)
+        return fail(PFS_ERR_ARG, "Expected more than 1 value per channel when training");
+    if (a.normed && !a.training) PFS_REQUIRE(a.running_mean && a.running_var, "eval-mode BatchNorm needs running buffers");
+    PFS_TRY((node_linear<F, M>(a.x_s, tp.S, tp.G, a.w1, M, 0, a.b1, nullptr, Rs, st)));
+    {
+        const bool dense = tp.layout == PFS_LAYOUT_DENSE;
+        TargetEdgeFwdParams p{tp, a.x_e, Rs, a.w1, dense ? stage : nullptr, dense ? nullptr : stage};
+        const int grid = persistent_grid(k_target_edge_fwd<F>, 0, total);
+        k_target_edge_fwd<F><<<grid, kThreads, 0, st>>>(p);
+        PFS_LAUNCH_CHECK("k_target_edge_fwd");
+    }
+    PFS_TRY(class_sums(tp, stage, M, a.act_sum, st));
+    {
+        TargetTailParams p = make_tail(a, tp);
+        const size_t smem = sizeof(float) * ((size_t)tp.T * 8 * F + 4 * F);
+        if (smem > 200 * 1024) return fail(PFS_ERR_UNSUPPORTED, "target tail: T*F too large for one CTA (%zu B)", smem);
+        PFS_TRY(allow_smem(k_target_tail_fwd, smem));
+        k_target_tail_fwd<<<tp.G, kThreads, smem, st>>>(p);
+        PFS_LAUNCH_CHECK("k_target_tail_fwd");
+    }
+    if (a.normed && a.training && a.running_mean && a.running_var) {
+        k_bn_running<<<1, 64, 0, st>>>(a.bn_save, F, tp.G, tp.T, a.gamma, a.beta, a.eps, a.momentum, 0, a.running_mean,
+                                       a.running_var, (long long*)a.num_batches_tracked);
+        PFS_LAUNCH_CHECK("k_bn_running");
+    }
+    return PFS_OK;
+}
+
+template <int F>
+int target_bwd_impl(const pfs_target_args& a, const Topo& tp) {
+    constexpr int M = 2 * F, H = 4 * F;
+    cudaStream_t st = (cudaStream_t)a.stream;
+    const int total = tp.ntiles * tp.G;
+    using SM = TargetEdgeBwdSmem<F>;
+    auto ke = k_target_edge_bwd<F>;
+    PFS_TRY(allow_smem(ke, SM::bytes));
+    const int gride = persistent_grid(ke, SM::bytes, total);
+    constexpr int pstride_e = M * F;
+    constexpr int ptail = tail_partial_floats(F);
+    Bump ws(a.workspace, a.workspace_bytes);
+    float* Rs = ws.f((size_t)tp.G * tp.S * M);
+    float* dasum = ws.f((size_t)tp.G * tp.T * M);
+    float* gpart = ws.f((size_t)tp.G * ptail);
+    float* dRs = ws.f((size_t)tp.G * tp.S * M);
+    float* wpe = ws.f((size_t)gride * pstride_e);
+    float* opart = ws.f((size_t)kMaxCtas * (M * F + M));
+    if (!ws.ok) return fail(PFS_ERR_WORKSPACE, "target_bwd: workspace too small (%zu B)", a.workspace_bytes);
+    {
+        TargetTailParams p = make_tail(a, tp);
+        p.dasum = dasum;
+        p.gpartial = gpart;
+        const size_t smem = sizeof(float) * ((size_t)tp.T * 12 * F + 6 * F);
+        if (smem > 200 * 1024) return fail(PFS_ERR_UNSUPPORTED, "target tail: T*F too large for one CTA (%zu B)", smem);
+        PFS_TRY(allow_smem(k_target_tail_bwd, smem));
+        k_target_tail_bwd<<<tp.G, kThreads, smem, st>>>(p);
+        PFS_LAUNCH_CHECK("k_target_tail_bwd");
+    }
+    PFS_TRY(reduce_partials(gpart, tp.G, ptail, tail_off_w2(F), M * M, M, a.g_w2, M, 0, st));
+    PFS_TRY(reduce_partials(gpart, tp.G, ptail, tail_off_b2(F), M, M, a.g_b2, M, 0, st));
+    PFS_TRY(reduce_partials(gpart, tp.G, ptail, tail_off_w3(F), H * H, H, a.g_w3, H, 0, st));
+    PFS_TRY(reduce_partials(gpart, tp.G, ptail, tail_off_b3(F), H, H, a.g_b3, H, 0, st));
+    PFS_TRY(reduce_partials(gpart, tp.G, ptail, tail_off_w4(F), F * H, H, a.g_w4, H, 0, st));
+    PFS_TRY(reduce_partials(gpart, tp.G, ptail, tail_off_b4(F), F, F, a.g_b4, F, 0, st));
+    if (a.normed) {
+        PFS_TRY(reduce_partials(gpart, tp.G, ptail, tail_off_gamma(F), F, F, a.g_gamma, F, 0, st));
+        PFS_TRY(reduce_partials(gpart, tp.G, ptail, tail_off_beta(F), F, F, a.g_beta, F, 0, st));
+    }
+    PFS_TRY((node_linear<F, M>(a.x_s, tp.S, tp.G, a.w1, M, 0, a.b1, nullptr, Rs, st)));
+    {
+        TargetEdgeBwdParams p{tp, a.x_e, Rs, a.w1, dasum, a.g_x_e, dRs, wpe, pstride_e};
+        ke<<<gride, kThreads, SM::bytes, st>>>(p);
+        PFS_LAUNCH_CHECK("k_target_edge_bwd");
+    }
+    PFS_TRY(reduce_partials(wpe, gride, pstride_e, 0, M * F, F, a.g_w1, M, F, st));
+    PFS_TRY((node_linear_bwd<F, M>(dRs, (long long)tp.G * tp.S, a.w1, M, 0, a.g_x_s, st)));
+    PFS_TRY((outer_rows<M, F, F / 2, F / 2>(dRs, a.x_s, (long long)tp.G * tp.S, opart, a.g_w1, M, 0, a.g_b1, st)));
+    return PFS_OK;
+}
+
+// ==========================================================================================
+// time head
+// ==========================================================================================
+template <int F>
+int head_impl(const pfs_head_args& a, const Topo& tp, bool backward) {
+    cudaStream_t st = (cudaStream_t)a.stream;
+    const long long N = (long long)tp.G * tp.E;
+    constexpr int pstride = F * F + 2 * F + 1;
+    HeadParams p{tp, a.x_e, a.w1, a.b1, a.w2, a.b2, a.scale, a.class_hours, (const long long*)a.edge_tgt,
+                 a.time, a.visits, a.time_int, a.g_time, a.g_x_e, nullptr, pstride};
+    if (!backward) {
+        if (tp.layout != PFS_LAYOUT_DENSE && a.class_hours) PFS_REQUIRE(a.edge_tgt, "CSR layout head needs edge_tgt");
+        long long blocks = (N + kThreads - 1) / kThreads;
+        if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
+        if (blocks < 1) blocks = 1;
+        k_head_fwd<F><<<(int)blocks, kThreads, 0, st>>>(p);
+        PFS_LAUNCH_CHECK("k_head_fwd");
+        return PFS_OK;
+    }
+    const long long tiles = (N + kTile - 1) / kTile;
+    const int grid = persistent_grid(k_head_bwd<F>, 0, tiles);
+    Bump ws(a.workspace, a.workspace_bytes);
+    float* wpart = ws.f((size_t)grid * pstride);
+    if (!ws.ok) return fail(PFS_ERR_WORKSPACE, "head_bwd: workspace too small (%zu B)", a.workspace_bytes);
+    p.wpartial = wpart;
+    k_head_bwd<F><<<grid, kThreads, 0, st>>>(p);
+    PFS_LAUNCH_CHECK("k_head_bwd");
+    PFS_TRY(reduce_partials(wpart, grid, pstride, 0, F * F, F, a.g_w1, F, 0, st));
+    PFS_TRY(reduce_partials(wpart, grid, pstride, F * F, F, F, a.g_b1, F, 0, st));
+    PFS_TRY(reduce_partials(wpart, grid, pstride, F * F + F, F, F, a.g_w2, F, 0, st));
+    PFS_TRY(reduce_partials(wpart, grid, pstride, F * F + 2 * F, 1, 1, a.g_b2, 1, 0, st));
+    return PFS_OK;
+}
+
+// ==========================================================================================
+// topology kernels
+// ==========================================================================================
+__global__ void k_set_flag(int* flag, int v) { *flag = v; }
+__global__ void k_detect_dense(const long long* ei, long long E, int T, int* flag) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    if (ei[e] != e / T || ei[E + e] != e % T) *flag = 0;   // benign race: every writer stores 0
+}
+__global__ void k_split_edges(const long long* ei, long long E, int* src, int* eid) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    src[e] = (int)ei[e];
+    eid[e] = (int)e;
+}
+__global__ void k_gather_tgt(const long long* ei, long long E, const int* eid, int* tgt, int* q) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= E) return;
+    tgt[i] = (int)ei[E + eid[i]];
+    q[i] = (int)i;
+}
+// ptr[s] = number of sorted keys < s  (lower bound), s in [0, n]
+__global__ void k_lower_bounds(const int* keys, int E, int n, int* ptr) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > n) return;
+    int lo = 0, hi = E;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (keys[mid] < s) lo = mid + 1; else hi = mid;
+    }
+    ptr[s] = lo;
+}
+// greedy packing of whole fibres into tiles of <= kTile edges (sequential, one-time per topology)
+__global__ void k_pack_tiles(const int* rowptr, int S, int* tile_fibre, int* ntiles, int* max_degree) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    int nt = 0, cur = 0, maxd = 0;
+    tile_fibre[0] = 0;
+    for (int f = 0; f < S; ++f) {
+        const int d = rowptr[f + 1] - rowptr[f];
+        maxd = d > maxd ? d : maxd;
+        if (cur + d > kTile && cur > 0) {
+            tile_fibre[++nt] = f;
+            cur = 0;
+        }
+        cur += d;
+    }
+    tile_fibre[++nt] = S;
+    *ntiles = nt;
+    *max_degree = maxd;
+}
+
+size_t sort_temp_bytes(long long E) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const int*)nullptr, (int*)nullptr, (const int*)nullptr,
+                                    (int*)nullptr, (int)E);
+    return ((bytes + 255) / 256) * 256;
+}
+
+}  // namespace
+
+// ==========================================================================================
+// extern "C"
+// ==========================================================================================
+extern "C" {
+
+int pfs_abi_version(void) { return PFS_ABI_VERSION; }
+const char* pfs_last_error(void) { return g_err; }
+int pfs_supports_fdim(int32_t F) { return fdim_supported(F) ? 1 : 0; }
+size_t pfs_sizeof_topology(void) { return sizeof(pfs_topology); }
+size_t pfs_sizeof_edge_args(void) { return sizeof(pfs_edge_args); }
+size_t pfs_sizeof_source_args(void) { return sizeof(pfs_source_args); }
+size_t pfs_sizeof_target_args(void) { return sizeof(pfs_target_args); }
+size_t pfs_sizeof_global_args(void) { return sizeof(pfs_global_args); }
+size_t pfs_sizeof_head_args(void) { return sizeof(pfs_head_args); }
+
+size_t pfs_workspace_bytes(const pfs_topology* t) {
+    if (!t) return 0;
+    const size_t G = t->G, S = t->S, T = t->T, E = t->E, F = t->F;
+    const size_t ntiles = t->layout == PFS_LAYOUT_DENSE ? (size_t)dense_ntiles(t->S, t->T) : (size_t)t->ntiles;
+    const size_t ntn = node_ntiles(t->S);
+    size_t fl = 0;
+    fl += G * S * 16 * F;                               // node tables, fibre sums, moment coefficients
+    fl += G * T * 16 * F;
+    fl += G * ntiles * (T * 4 * F + 4 * F + 8);         // per-tile class partials and BatchNorm partials
+    fl += G * ntn * (12 * F + 8);
+    if (t->layout != PFS_LAYOUT_DENSE) fl += G * E * 4 * F;
+    fl += (size_t)kMaxCtas * (100 * F * F + 32 * F + 64) * 2;   // per-CTA weight-gradient partials
+    fl += G * (36 * F * F + 128 * F);
+    fl += 4096;
+    return fl * sizeof(float) + 64 * 256;
+}
+
+int pfs_detect_dense(const int64_t* edge_index, int64_t E, int32_t S, int32_t T, int32_t* flag_dev, void* stream) {
+    PFS_REQUIRE(edge_index && flag_dev && S >= 1 && T >= 1, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool maybe = (long long)S * T == E && E > 0;
+    k_set_flag<<<1, 1, 0, st>>>(flag_dev, maybe ? 1 : 0);
+    PFS_LAUNCH_CHECK("k_set_flag");
+    if (maybe) {
+        k_detect_dense<<<(unsigned)((E + 255) / 256), 256, 0, st>>>((const long long*)edge_index, E, T, flag_dev);
+        PFS_LAUNCH_CHECK("k_detect_dense");
+    }
+    return PFS_OK;
+}
+
+size_t pfs_build_topology_temp_bytes(int64_t E, int32_t S, int32_t T) {
+    (void)S; (void)T;
+    const size_t arr = (((size_t)E * sizeof(int) + 255) / 256) * 256;
+    return 4 * arr + sort_temp_bytes(E) + 1024;
+}
+
+int pfs_build_topology(const int64_t* edge_index, int64_t E, int32_t S, int32_t T, int32_t* csr_rowptr,
+                       int32_t* csr_eid, int32_t* csr_src, int32_t* csr_tgt, int32_t* csc_colptr, int32_t* csc_q,
+                       int32_t* tile_fibre, int32_t* ntiles_dev, int32_t* max_degree_dev, void* temp,
+                       size_t temp_bytes, void* stream) {
+    PFS_REQUIRE(edge_index && csr_rowptr && csr_eid && csr_src && csr_tgt && csc_colptr && csc_q && tile_fibre &&
+                    ntiles_dev && max_degree_dev && temp, "null pointer");
+    PFS_REQUIRE(E >= 1 && E < (1ll << 31) && S >= 1 && T >= 1, "bad sizes");
+    if (temp_bytes < pfs_build_topology_temp_bytes(E, S, T)) return fail(PFS_ERR_WORKSPACE, "topology temp too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t arr = (((size_t)E * sizeof(int) + 255) / 256) * 256;
+    char* base = (char*)temp;
+    int* k_in = (int*)base;
+    int* v_in = (int*)(base + arr);
+    int* k_tmp = (int*)(base + 2 * arr);
+    int* v_tmp = (int*)(base + 3 * arr);
+    void* cub_tmp = base + 4 * arr;
+    size_t cub_bytes = sort_temp_bytes(E);
+    const unsigned blocks = (unsigned)((E + 255) / 256);
+    const long long* ei = (const long long*)edge_index;
+    // fibre-sorted (CSR) order: stable LSD radix sort of (src, edge id)
+    k_split_edges<<<blocks, 256, 0, st>>>(ei, E, k_in, v_in);
+    PFS_LAUNCH_CHECK("k_split_edges");
+    PFS_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, k_in, csr_src, v_in, csr_eid, (int)E, 0, 32, st));
+    k_gather_tgt<<<blocks, 256, 0, st>>>(ei, E, csr_eid, csr_tgt, v_tmp);
+    PFS_LAUNCH_CHECK("k_gather_tgt");
+    k_lower_bounds<<<(S + 1 + 255) / 256, 256, 0, st>>>(csr_src, (int)E, S, csr_rowptr);
+    PFS_LAUNCH_CHECK("k_lower_bounds(src)");
+    // class-sorted (CSC) order of the CSR positions
+    PFS_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, csr_tgt, k_tmp, v_tmp, csc_q, (int)E, 0, 32, st));
+    k_lower_bounds<<<(T + 1 + 255) / 256, 256, 0, st>>>(k_tmp, (int)E, T, csc_colptr);
+    PFS_LAUNCH_CHECK("k_lower_bounds(tgt)");
+    k_pack_tiles<<<1, 1, 0, st>>>(csr_rowptr, S, tile_fibre, ntiles_dev, max_degree_dev);
+    PFS_LAUNCH_CHECK("k_pack_tiles");
+    return PFS_OK;
+}
+
+int pfs_edge_fwd(const pfs_edge_args* a) {
+    PFS_REQUIRE(a && a->x_s && a->x_t && a->x_e && a->u && a->w1 && a->b1 && a->w2 && a->b2 && a->x_e_out && a->workspace,
+                "null pointer");
+    Topo tp;
+    PFS_TRY(make_topo(a->topo, tp));
+    PFS_DISPATCH_F(tp.F, return edge_fwd_impl<kF>(*a, tp));
+    return PFS_OK;
+}
+int pfs_edge_bwd(const pfs_edge_args* a) {
+    PFS_REQUIRE(a && a->x_s && a->x_t && a->x_e && a->u && a->w1 && a->b1 && a->w2 && a->x_e_out && a->g_out &&
+                    a->g_x_s && a->g_x_t && a->g_x_e && a->g_u && a->g_w1 && a->g_b1 && a->g_w2 && a->g_b2 && a->workspace,
+                "null pointer");
+    if (a->normed) PFS_REQUIRE(a->gamma && a->beta && a->bn_save && a->g_gamma && a->g_beta, "normed backward needs norm tensors");
+    Topo tp;
+    PFS_TRY(make_topo(a->topo, tp));
+    PFS_DISPATCH_F(tp.F, return edge_bwd_impl<kF>(*a, tp));
+    return PFS_OK;
+}
+int pfs_source_fwd(const pfs_source_args* a) {
+    PFS_REQUIRE(a && a->x_s && a->x_t && a->x_e && a->u && a->w1 && a->b1 && a->w2 && a->b2 && a->w3 && a->b3 && a->w4 &&
+                    a->b4 && a->x_s_out && a->moments && a->hidden && a->y_pre && a->workspace, "null pointer");
+    Topo tp;
+    PFS_TRY(make_topo(a->topo, tp));
+    PFS_DISPATCH_F(tp.F, return source_fwd_impl<kF>(*a, tp));
+    return PFS_OK;
+}
+int pfs_source_bwd(const pfs_source_args* a) {
+    PFS_REQUIRE(a && a->x_s && a->x_t && a->x_e && a->u && a->w1 && a->b1 && a->w2 && a->b2 && a->w3 && a->w4 &&
+                    a->moments && a->hidden && a->y_pre && a->g_out && a->g_x_s && a->g_x_t && a->g_x_e && a->g_u &&
+                    a->g_w1 && a->g_b1 && a->g_w2 && a->g_b2 && a->g_w3 && a->g_b3 && a->g_w4 && a->g_b4 && a->workspace,
+                "null pointer");
+    if (a->normed) PFS_REQUIRE(a->gamma && a->bn_save && a->g_gamma && a->g_beta, "normed backward needs norm tensors");
+    Topo tp;
+    PFS_TRY(make_topo(a->topo, tp));
+    PFS_DISPATCH_F(tp.F, return source_bwd_impl<kF>(*a, tp));
+    return PFS_OK;
+}
+int pfs_target_fwd(const pfs_target_args* a) {
+    PFS_REQUIRE(a && a->x_s && a->x_t && a->x_e && a->u && a->w1 && a->b1 && a->w2 && a->b2 && a->w3 && a->b3 && a->w4 &&
+                    a->b4 && a->x_t_out && a->act_sum && a->y_pre && a->workspace, "null pointer");
+    Topo tp;
+    PFS_TRY(make_topo(a->topo, tp));
+    PFS_DISPATCH_F(tp.F, return target_fwd_impl<kF>(*a, tp));
+    return PFS_OK;
+}
+int pfs_target_bwd(const pfs_target_args* a) {
+    PFS_REQUIRE(a && a->x_s && a->x_t && a->x_e && a->u && a->w1 && a->b1 && a->w2 && a->b2 && a->w3 && a->b3 && a->w4 &&
+                    a->act_sum && a->y_pre && a->g_out && a->g_x_s && a->g_x_t && a->g_x_e && a->g_u && a->g_w1 &&
+                    a->g_b1 && a->g_w2 && a->g_b2 && a->g_w3 && a->g_b3 && a->g_w4 && a->g_b4 && a->workspace,
+                "null pointer");
+    if (a->normed) PFS_REQUIRE(a->gamma && a->bn_save && a->g_gamma && a->g_beta, "normed backward needs norm tensors");
+    Topo tp;
+    PFS_TRY(make_topo(a->topo, tp));
+    PFS_DISPATCH_F(tp.F, return target_bwd_impl<kF>(*a, tp));
+    return PFS_OK;
+}
+
+static int global_common(const pfs_global_args* a, GlobalParams& p) {
+    PFS_REQUIRE(a && a->x_s && a->x_t && a->u && a->w1 && a->b1 && a->w2 && a->b2, "null pointer");
+    PFS_REQUIRE(a->G >= 1 && a->F >= 2 && a->S >= 1 && a->T >= 1 && 3 * a->F <= kThreads, "bad sizes");
+    if (a->normed) PFS_REQUIRE(a->rms_weight, "normed global model needs norm.weight");
+    p = GlobalParams{};
+    p.G = a->G; p.F = a->F; p.S = a->S; p.T = a->T; p.normed = a->normed; p.rms_eps = a->rms_eps;
+    p.x_s = a->x_s; p.x_t = a->x_t; p.u = a->u;
+    p.w1 = a->w1; p.b1 = a->b1; p.w2 = a->w2; p.b2 = a->b2; p.rms_w = a->rms_weight;
+    p.u_out = a->u_out; p.gout = a->g_out; p.g_x_s = a->g_x_s; p.g_x_t = a->g_x_t; p.g_u = a->g_u;
+    return PFS_OK;
+}
+int pfs_global_fwd(const pfs_global_args* a) {
+    GlobalParams p;
+    PFS_TRY(global_common(a, p));
+    PFS_REQUIRE(a->u_out, "null pointer");
+    const size_t smem = sizeof(float) * (22 * (size_t)a->F + 2);
+    k_global_fwd<<<a->G, kThreads, smem, (cudaStream_t)a->stream>>>(p);
+    PFS_LAUNCH_CHECK("k_global_fwd");
+    return PFS_OK;
+}
+int pfs_global_bwd(const pfs_global_args* a) {
+    GlobalParams p;
+    PFS_TRY(global_common(a, p));
+    PFS_REQUIRE(a->g_out && a->g_x_s && a->g_x_t && a->g_u && a->g_w1 && a->g_b1 && a->g_w2 && a->g_b2 && a->workspace,
+                "null pointer");
+    cudaStream_t st = (cudaStream_t)a->stream;
+    const int F = a->F, K = 3 * F, pg = global_partial_floats(F);
+    Bump ws(a->workspace, a->workspace_bytes);
+    float* gpart = ws.f((size_t)a->G * pg);
+    if (!ws.ok) return fail(PFS_ERR_WORKSPACE, "global_bwd: workspace too small");
+    p.gpartial = gpart;
+    const size_t smem = sizeof(float) * (22 * (size_t)F + 2);
+    k_global_bwd<<<a->G, kThreads, smem, st>>>(p);
+    PFS_LAUNCH_CHECK("k_global_bwd");
+    PFS_TRY(reduce_partials(gpart, a->G, pg, glob_off_w1(F), K * K, K, a->g_w1, K, 0, st));
+    PFS_TRY(reduce_partials(gpart, a->G, pg, glob_off_b1(F), K, K, a->g_b1, K, 0, st));
+    PFS_TRY(reduce_partials(gpart, a->G, pg, glob_off_w2(F), F * K, K, a->g_w2, K, 0, st));
+    PFS_TRY(reduce_partials(gpart, a->G, pg, glob_off_b2(F), F, F, a->g_b2, F, 0, st));
+    if (a->normed) {
+        PFS_REQUIRE(a->g_rms_weight, "null pointer");
+        PFS_TRY(reduce_partials(gpart, a->G, pg, glob_off_rms(F), F, F, a->g_rms_weight, F, 0, st));
+    }
+    return PFS_OK;
+}
+
+int pfs_time_head_fwd(const pfs_head_args* a) {
+    PFS_REQUIRE(a && a->x_e && a->w1 && a->b1 && a->w2 && a->b2 && a->time, "null pointer");
+    Topo tp;
+    PFS_TRY(make_topo(a->topo, tp));
+    PFS_DISPATCH_F(tp.F, return head_impl<kF>(*a, tp, false));
+    return PFS_OK;
+}
+int pfs_time_head_bwd(const pfs_head_args* a) {
+    PFS_REQUIRE(a && a->x_e && a->w1 && a->b1 && a->w2 && a->b2 && a->g_time && a->g_x_e && a->g_w1 && a->g_b1 &&
+                    a->g_w2 && a->g_b2 && a->workspace, "null pointer");
+    Topo tp;
+    PFS_TRY(make_topo(a->topo, tp));
+    PFS_DISPATCH_F(tp.F, return head_impl<kF>(*a, tp, true));
+    return PFS_OK;
+}
+
+}  // extern "C"

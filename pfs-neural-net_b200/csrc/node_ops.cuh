@@ -1,0 +1,339 @@
+// node_ops.cuh -- node-level (per fibre / per class / per graph) kernels shared by the modules:
+// small linear maps over node rows (the per-node tables of the first-layer split), their
+// backward, BatchNorm finalisation / running-stat updates, and the fixed-order reductions of
+// per-CTA partials.  All templated on compile-time widths; instantiated from api.cu.
+#pragma once
+#include "common.cuh"
+
+namespace pfs {
+
+// ------------------------------------------------------------------------------------------
+// out[n][j] = bias[j] + addvec[g][j] + sum_k W[j][koff + k] * x[n][k]      (n = g * rows + r)
+// thread-per-row, weights broadcast from shared memory.
+// ------------------------------------------------------------------------------------------
+template <int K, int J>
+__global__ void __launch_bounds__(kThreads) k_node_linear(const float* __restrict__ x, int rows_per_graph, int G,
+                                                           const float* __restrict__ W, int ldw, int koff,
+                                                           const float* __restrict__ bias,
+                                                           const float* __restrict__ addvec,
+                                                           float* __restrict__ out) {
+    __shared__ __align__(16) float Wt[K * J];
+    __shared__ float bs[J];
+    load_w_inmajor<K, J>(Wt, W, ldw, koff);
+    for (int i = threadIdx.x; i < J; i += blockDim.x) bs[i] = bias ? __ldg(bias + i) : 0.f;
+    __syncthreads();
+    const long long N = (long long)rows_per_graph * G;
+    for (long long n = (long long)blockIdx.x * kThreads + threadIdx.x; n < N; n += (long long)gridDim.x * kThreads) {
+        float xr[K], y[J];
+        load_row<K>(x + n * K, xr);
+#pragma unroll
+        for (int j = 0; j < J; ++j) y[j] = bs[j];
+        if (addvec) {
+            const int g = (int)(n / rows_per_graph);
+            add_row<J>(addvec + (size_t)g * J, y);
+        }
+        dense_acc<K, J>(Wt, xr, y);
+        store_row<J>(out + n * J, y);
+    }
+}
+
+// dx[n][k] (+)= sum_j W[j][koff + k] * d[n][j]     (backward of the map above w.r.t. x)
+template <int K, int J, bool ACCUM>
+__global__ void __launch_bounds__(kThreads) k_node_linear_bwd(const float* __restrict__ d, long long N,
+                                                               const float* __restrict__ W, int ldw, int koff,
+                                                               float* __restrict__ dx) {
+    __shared__ __align__(16) float Wo[J * K];  // Wo[j*K + k]: "input" index j, "output" index k
+    load_w_outmajor<K, J>(Wo, W, ldw, koff);
+    __syncthreads();
+    for (long long n = (long long)blockIdx.x * kThreads + threadIdx.x; n < N; n += (long long)gridDim.x * kThreads) {
+        float dr[J], y[K];
+        load_row<J>(d + n * J, dr);
+        if (ACCUM) load_row<K>(dx + n * K, y);
+        else {
+#pragma unroll
+            for (int k = 0; k < K; ++k) y[k] = 0.f;
+        }
+        dense_acc<J, K>(Wo, dr, y);
+        store_row<K>(dx + n * K, y);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// dW[j][k] partial = sum over a CTA's rows of D[n][j] * X[n][k]; bias partial = column sums of D.
+// Persistent CTAs over row tiles of kTile rows; partial p of CTA c at out[c * pstride + ...].
+// Layout inside a CTA partial: [J*K] weights (row-major j, k) then [J] column sums.
+// ------------------------------------------------------------------------------------------
+template <int J, int K, int TJ, int TK>
+__global__ void __launch_bounds__(kThreads) k_outer_rows(const float* __restrict__ D, const float* __restrict__ X,
+                                                          long long N, float* __restrict__ partial, int pstride) {
+    constexpr int LDD = J + 2, LDX = K + 2;
+    using Acc = OuterAcc<J, K, TJ, TK>;
+    constexpr int kTileFloats = kTile * (LDD + LDX);
+    constexpr int kScratch = Acc::kScratchFloats;
+    extern __shared__ __align__(16) float sm[];
+    float* Ds = sm;
+    float* Xs = sm + kTile * LDD;
+    static_assert(kScratch >= 0 && kTileFloats >= 0, "");
+    Acc acc;
+    acc.init();
+    float colsum = 0.f;  // thread j < J accumulates column j
+    const long long ntile = (N + kTile - 1) / kTile;
+    for (long long tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+        const long long n0 = tile * kTile;
+        const int rows = (int)min((long long)kTile, N - n0);
+        for (int i = threadIdx.x; i < rows * J; i += kThreads) {
+            const int r = i / J, j = i - r * J;
+            Ds[r * LDD + j] = __ldg(D + (n0 + r) * J + j);
+        }
+        for (int i = threadIdx.x; i < rows * K; i += kThreads) {
+            const int r = i / K, k = i - r * K;
+            Xs[r * LDX + k] = __ldg(X + (n0 + r) * K + k);
+        }
+        __syncthreads();
+        acc.accumulate(Ds, LDD, Xs, LDX, rows);
+        if (threadIdx.x < J) {
+            float s = 0.f;
+            for (int r = 0; r < rows; ++r) s += Ds[r * LDD + threadIdx.x];
+            colsum += s;
+        }
+        __syncthreads();
+    }
+    float* out = partial + (size_t)blockIdx.x * pstride;
+    acc.flush(sm, out, K, 0);
+    if (threadIdx.x < J) out[J * K + threadIdx.x] = colsum;
+}
+template <int J, int K, int TJ, int TK>
+constexpr size_t outer_rows_smem() {
+    constexpr int LDD = J + 2, LDX = K + 2;
+    constexpr int a = kTile * (LDD + LDX);
+    constexpr int b = OuterAcc<J, K, TJ, TK>::kScratchFloats;
+    return sizeof(float) * (a > b ? a : b);
+}
+
+// out[i] = sum_c partial[c * pstride + poff + i] for i < n  (fixed order over the CTAs);
+// 2-D destination: out[(i / cols) * ldo + coff + (i % cols)].
+__global__ void k_reduce_partials(const float* __restrict__ partial, int ncta, int pstride, int poff, int n, int cols,
+                                  float* __restrict__ out, int ldo, int coff) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float s = 0.f;
+    for (int c = 0; c < ncta; ++c) s += partial[(size_t)c * pstride + poff + i];
+    out[(i / cols) * ldo + coff + (i % cols)] = s;
+}
+
+// colsum over rows and graphs: out[j] = sum_n x[n][j] (single CTA per 32 columns; fixed order)
+__global__ void k_colsum_all(const float* __restrict__ x, long long N, int ld, int off, int J,
+                             float* __restrict__ out) {
+    // blockDim = (32 columns, 8 row lanes); column j of the result is x[:, off + j] of a [N, ld] matrix
+    __shared__ float red[8][33];
+    const int j = blockIdx.x * 32 + threadIdx.x;
+    float s = 0.f;
+    if (j < J)
+        for (long long n = threadIdx.y; n < N; n += 8) s += x[n * ld + off + j];
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && j < J) {
+        float t = 0.f;
+        for (int r = 0; r < 8; ++r) t += red[r][threadIdx.x];
+        out[j] = t;
+    }
+}
+
+// per-graph column sums: out[g][j] = sum_r x[g][r][j]
+__global__ void k_colsum_graph(const float* __restrict__ x, int rows, int J, float* __restrict__ out) {
+    __shared__ float red[8][33];
+    const int g = blockIdx.y;
+    const int j = blockIdx.x * 32 + threadIdx.x;
+    float s = 0.f;
+    if (j < J)
+        for (int r = threadIdx.y; r < rows; r += 8) s += x[((size_t)g * rows + r) * J + j];
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && j < J) {
+        float t = 0.f;
+        for (int r = 0; r < 8; ++r) t += red[r][threadIdx.x];
+        out[(size_t)g * J + j] = t;
+    }
+}
+
+// out[j][koff + k] = sum_g a[g][j] * b[g][k]      (the `u` columns of a first-layer weight gradient)
+__global__ void k_outer_graphs(const float* __restrict__ a, const float* __restrict__ b, int G, int J, int K,
+                               float* __restrict__ out, int ldo, int koff) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= J * K) return;
+    const int j = i / K, k = i - j * K;
+    float s = 0.f;
+    for (int g = 0; g < G; ++g) s += a[(size_t)g * J + j] * b[(size_t)g * K + k];
+    out[j * ldo + koff + k] = s;
+}
+
+// ------------------------------------------------------------------------------------------
+// class-side reduction of per-tile partial sums: out[g][i][j] = sum_lt part[g][lt][i][j]
+// ------------------------------------------------------------------------------------------
+__global__ void k_class_reduce(const float* __restrict__ part, int ntiles, int TJ, float* __restrict__ out) {
+    const int g = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= TJ) return;
+    const float* p = part + (size_t)g * ntiles * TJ + i;
+    float s = 0.f;
+    for (int t = 0; t < ntiles; ++t) s += p[(size_t)t * TJ];
+    out[(size_t)g * TJ + i] = s;
+}
+
+// general layout: out[g][c][j] = sum over the class's edges (class-sorted order) of rows[g][q][j]
+__global__ void k_csc_segment_sum(const float* __restrict__ rows, const int* __restrict__ colptr,
+                                  const int* __restrict__ cscq, int E, int T, int J, float* __restrict__ out) {
+    // one warp per (graph, class): lanes stride over features, fixed edge order
+    const int g = blockIdx.y;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= T) return;
+    const int lane = threadIdx.x & 31;
+    const int a = colptr[c], b = colptr[c + 1];
+    for (int j = lane; j < J; j += 32) {
+        float s = 0.f;
+        for (int k = a; k < b; ++k) s += rows[((size_t)g * E + cscq[k]) * J + j];
+        out[((size_t)g * T + c) * J + j] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// BatchNorm: combine tile partials (Chan, fp64, fixed order), closed-form coefficients
+//   save[g][0][f] = mean, save[g][1][f] = biased variance, save[g][2][f] = scale, save[g][3][f] = shift
+//   twice == 1: the edge model's double application (reference src/gnn.py:82,101):
+//       scale = gamma^2 r1 r2, shift = beta - scale * mean, r2 = rsqrt(gamma^2 var r1^2 + eps)
+// ------------------------------------------------------------------------------------------
+__global__ void k_bn_finalize(const float* __restrict__ partial, int ntiles, int pstride, int F, int G,
+                              const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int twice,
+                              float* __restrict__ save) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= G * F) return;
+    const int g = i / F, f = i - g * F;
+    const float* p = partial + (size_t)g * ntiles * pstride;
+    double n = 0.0, mean = 0.0, m2 = 0.0;
+    for (int t = 0; t < ntiles; ++t) {
+        const double nb = p[(size_t)t * pstride + 2 * F];
+        if (nb <= 0.0) continue;
+        const double mb = p[(size_t)t * pstride + f], sb = p[(size_t)t * pstride + F + f];
+        const double tot = n + nb, delta = mb - mean;
+        mean += delta * (nb / tot);
+        m2 += sb + delta * delta * (n * nb / tot);
+        n = tot;
+    }
+    const double var = n > 0 ? m2 / n : 0.0;
+    const double gm = gamma[f], bt = beta[f];
+    const double r1 = 1.0 / sqrt(var + (double)eps);
+    double scale, shift;
+    if (twice) {
+        const double var2 = gm * gm * var * r1 * r1;
+        const double r2 = 1.0 / sqrt(var2 + (double)eps);
+        scale = gm * gm * r1 * r2;
+    } else {
+        scale = gm * r1;
+    }
+    shift = bt - scale * mean;
+    float* s = save + (size_t)g * 4 * F;
+    s[f] = (float)mean;
+    s[F + f] = (float)var;
+    s[2 * F + f] = (float)scale;
+    s[3 * F + f] = (float)shift;
+}
+
+// eval mode: coefficients from the running buffers (same for every graph)
+__global__ void k_bn_eval_coeffs(const float* __restrict__ rm, const float* __restrict__ rv, int F, int G,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int twice,
+                                 float* __restrict__ save) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= G * F) return;
+    const int g = i / F, f = i - g * F;
+    const double a = (double)gamma[f] / sqrt((double)rv[f] + (double)eps);
+    const double m = rm[f], bt = beta[f];
+    double scale, shift;
+    if (twice) {  // y2 = a (a (z - m) + bt - m) + bt
+        scale = a * a;
+        shift = a * (bt - m - a * m) + bt;
+    } else {
+        scale = a;
+        shift = bt - a * m;
+    }
+    float* s = save + (size_t)g * 4 * F;
+    s[f] = (float)m;
+    s[F + f] = rv[f];
+    s[2 * F + f] = (float)scale;
+    s[3 * F + f] = (float)shift;
+}
+
+// running buffers, graph after graph (what G sequential reference forwards would leave behind)
+__global__ void k_bn_running(const float* __restrict__ save, int F, int G, long long n_rows,
+                             const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                             float momentum, int twice, float* __restrict__ rm, float* __restrict__ rv,
+                             long long* __restrict__ nbt) {
+    const int f = threadIdx.x;
+    if (f < F) {
+        double m = rm[f], v = rv[f];
+        const double mom = momentum, unb = (double)n_rows / (double)(n_rows - 1);
+        for (int g = 0; g < G; ++g) {
+            const double mean = save[(size_t)g * 4 * F + f], var = save[(size_t)g * 4 * F + F + f];
+            m = (1.0 - mom) * m + mom * mean;
+            v = (1.0 - mom) * v + mom * var * unb;
+            if (twice) {  // second application sees mean beta and variance gamma^2 var / (var + eps)
+                const double gm = gamma[f];
+                const double var2 = gm * gm * var / (var + (double)eps);
+                m = (1.0 - mom) * m + mom * (double)beta[f];
+                v = (1.0 - mom) * v + mom * var2 * unb;
+            }
+        }
+        rm[f] = (float)m;
+        rv[f] = (float)v;
+    }
+    if (f == 0 && nbt) *nbt += (long long)G * (twice ? 2 : 1);
+}
+
+// out[g][r][f] = in[g][r][f] * scale[g][f] + shift[g][f]   (in place allowed)
+__global__ void k_affine_rows(const float* __restrict__ in, const float* __restrict__ save, int F, long long rows_f,
+                              int G, float* __restrict__ out) {
+    // rows_f = rows_per_graph * F (elements per graph)
+    const long long total = rows_f * G;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(i / rows_f);
+        const int f = (int)((i - (long long)g * rows_f) % F);
+        const float* s = save + (size_t)g * 4 * F;
+        out[i] = fmaf(in[i], s[2 * F + f], s[3 * F + f]);
+    }
+}
+
+// BatchNorm backward statistics over node rows: per graph sum_r g and sum_r g * xhat,
+// xhat = (y - mean) * rsqrt(var + eps).  One CTA per graph (rows <= a few thousand per graph).
+// out[g][0][f] = sum g, out[g][1][f] = sum g * xhat
+__global__ void k_bn_bwd_stats_rows(const float* __restrict__ gout, const float* __restrict__ y,
+                                    const float* __restrict__ save, int rows, int F, float eps,
+                                    float* __restrict__ out) {
+    extern __shared__ float red[];  // [nwarp][2F]
+    const int g = blockIdx.x;
+    const int nw = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* s = save + (size_t)g * 4 * F;
+    for (int f = 0; f < F; ++f) {
+        const float mean = s[f], r = rsqrtf(s[F + f] + eps);
+        float a = 0.f, b = 0.f;
+        for (int rr = threadIdx.x; rr < rows; rr += blockDim.x) {
+            const size_t idx = ((size_t)g * rows + rr) * F + f;
+            const float gv = gout[idx];
+            a += gv;
+            b += gv * ((y[idx] - mean) * r);
+        }
+        a = warp_sum(a);
+        b = warp_sum(b);
+        if (lane == 0) {
+            red[w * 2 * F + f] = a;
+            red[w * 2 * F + F + f] = b;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * F) {
+        float t = 0.f;
+        for (int i = 0; i < nw; ++i) t += red[i * 2 * F + threadIdx.x];
+        out[(size_t)g * 2 * F + threadIdx.x] = t;
+    }
+}
+
+}  // namespace pfs
