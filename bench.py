@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py -- edges/sec, forward+backward, per GNN layer (`Block`) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[2], "C3"): a batch of 256 synthetic complete bipartite graphs of
+2394 fibres x 12 classes (28 728 edges each), Fdim 10, fp32, train mode; one step = one `Block`
+forward + backward w.r.t. all four outputs (upstream gradients linspace(0.5, 1.5)), every parameter
+gets a gradient.  configs[1] (ONE such graph) needs ~1 us of HBM time, below a kernel-launch latency,
+so the throughput configuration is the 256-graph batch; the single graph is a
+parity-test case (tests/test_gpu_parity.py::test_full_size_graph_c2).
+
+N > 1 (launched by torchrun, one rank per GPU): data parallel over graph batches, 256 graphs PER
+GPU (weak scaling), weights replicated, one NCCL all-reduce of the flat gradient bucket per step.
+
+Printed JSON line: see the keys at the bottom.  `value` = edges of all ranks / device time (CUDA
+events, max over ranks, inputs resident in HBM); `e2e` = the same through the nn.Module API with
+pinned HOST inputs copied in every step and the loss read back; `roofline` = dominant kernel,
+algorithmic bytes / CUDA-event duration against the measured HBM copy bandwidth (the binding
+ceiling of these small-width MLPs is the FP32 FMA pipe, reported beside it in `fma`);
+`cpu_baseline` = the oracle port of the reference path on this box's host cores.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "edges_per_sec_fwd_bwd_per_gnn_layer"
+UNIT = "edges/s"
+
+# algorithmic bytes each kernel must move, in units of F*4 bytes (one fp32 feature row):
+# per edge (E) and per fibre (S); DESIGN.md section 6 derives them from SURVEY.md section 8(d).
+KERNEL_ROWS = {
+    "k_edge_fwd": (2, 0), "k_edge_bwd": (3, 0), "k_edge_bn_bwd_stats": (2, 0), "k_affine_rows": (2, 0),
+    "k_source_edge_fwd": (1, 10), "k_source_edge_bwd": (2, 18), "k_target_edge_fwd": (1, 2),
+    "k_target_edge_bwd": (2, 2), "k_source_node_fwd": (0, 22), "k_source_node_bwd": (0, 32),
+}
+# executed multiply-accumulates per edge / per fibre, forward + backward, in units of F^2
+MAC_PER_EDGE_F2 = 60
+MAC_PER_FIBRE_F2 = 318
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--graphs", type=int, default=256, help="graphs per GPU")
+    ap.add_argument("--fibres", type=int, default=2394)
+    ap.add_argument("--classes", type=int, default=12)
+    ap.add_argument("--fdim", type=int, default=10)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget of the cpu_baseline sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(p.get("sm_max_mhz", 1965.0))
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi fields through NVML) running during the timed region
+# ---------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index, period=0.05):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                    self.nv, "nvmlDeviceGetCurrentClocksEventReasons") else self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU reference arm: the oracle port of the reference path on the host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_graph_step(bo, state, ei, ins, ups):
+    params = {k: v.clone().requires_grad_(True) for k, v in state.items() if v.is_floating_point() and "running" not in k}
+    full = dict(state)
+    full.update(params)
+    xs = [t.clone().requires_grad_(True) for t in ins]
+    outs = bo.block(full, "", ei, *xs, training=True, buffers={})
+    torch.autograd.backward(list(outs), [u for u in ups])
+
+
+def cpu_reference(args, seconds, steps=None, warmup=1):
+    """Times the oracle port (kind 'port': the unmodified reference cannot travel to the GPU box, it needs
+    /root/reference + torch_scatter) on the host cores, reference-style threading (src/train.py:15-19).
+    Returns (edges_per_s, description)."""
+    from oracle import block_oracle as bo
+    ncores = os.cpu_count() or 1
+    torch.set_num_threads(ncores)
+    F, S, T = args.fdim, args.fibres, args.classes
+    E = S * T
+    state = bo.random_block_state(F, seed=0)
+    ei = bo.complete_bipartite(S, T)
+    g = torch.Generator().manual_seed(1234)
+    ins = [torch.randn(S, F, generator=g), torch.randn(T, F, generator=g), torch.randn(E, F, generator=g),
+           torch.randn(1, F, generator=g)]
+    ups = [torch.linspace(0.5, 1.5, t.numel()).reshape(t.shape) for t in
+           (ins[0], ins[1], ins[2], ins[3])]
+    for _ in range(warmup):
+        cpu_reference_graph_step(bo, state, ei, ins, ups)
+    times = []
+    t_begin = time.perf_counter()
+    while True:
+        t0 = time.perf_counter()
+        cpu_reference_graph_step(bo, state, ei, ins, ups)
+        times.append(time.perf_counter() - t0)
+        if steps is not None:
+            if len(times) >= steps:
+                break
+        elif time.perf_counter() - t_begin >= seconds and len(times) >= 3:
+            break
+    total = sum(times)
+    return E * len(times) / total, ncores, "%d of the %d graphs (%dx%d, Fdim %d, fp32), one after the other, %.1f s" % (
+        len(times), args.graphs, S, T, F, total), total / len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_step_graphs = 8
+    w_graphs = max(1, args.warmup)
+    t0 = time.perf_counter()
+    eps, ncores, sample, sec_per_graph = cpu_reference(args, seconds=0, steps=per_step_graphs * args.steps, warmup=w_graphs)
+    ms_per_step = sec_per_graph * per_step_graphs * 1e3
+    line = {
+        "impl": "reference", "metric": METRIC, "value": eps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C3: 256 x complete bipartite 2394x12, Fdim 10, Block fwd+bwd (each CPU step = a bounded "
+                               "sample of %d graphs)" % per_step_graphs,
+                   "graphs_per_gpu": args.graphs, "fibres": args.fibres, "classes": args.classes, "fdim": args.fdim},
+        "cpu_baseline": {"value": eps, "unit": UNIT, "cores": ncores, "kind": "port", "sample": sample},
+        "e2e": {"value": eps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# the B200 arm
+# ---------------------------------------------------------------------------------------------
+def build_block(F, dev):
+    from pfs_neural_net_b200 import gnn
+    torch.manual_seed(0)
+    blk = gnn.Block(F)
+    g = torch.Generator().manual_seed(1)
+    for m in blk.modules():
+        if isinstance(m, torch.nn.BatchNorm1d):     # non-trivial affine so the double norm matters
+            m.weight.data = 0.5 + torch.rand(m.weight.shape, generator=g)
+            m.bias.data = 2 * torch.rand(m.bias.shape, generator=g) - 1
+    return blk.to(dev).train()
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from pfs_neural_net_b200 import _abi, dp
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the message-passing layer has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _abi.load_library()
+    G, S, T, F = args.graphs, args.fibres, args.classes, args.fdim
+    E = S * T
+    blk = build_block(F, dev)
+    bucket = dp.GradBucket(blk.parameters())
+    if world > 1:
+        dp.broadcast_parameters(blk)
+    ei = torch.cartesian_prod(torch.arange(S), torch.arange(T)).T.contiguous().to(dev)   # reference src/train.py:94
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    shapes = [(G, S, F), (G, T, F), (G, E, F), (G, 1, F)]
+    ins = [torch.randn(s, generator=gen, device=dev) for s in shapes]
+    ups = [torch.linspace(0.5, 1.5, s[1] * s[2], device=dev).reshape(1, s[1], s[2]).expand(s).contiguous() for s in shapes]
+
+    def step(xs):
+        for p in blk.parameters():
+            p.grad = None
+        xs = [x.requires_grad_(True) for x in xs]
+        _, o_s, o_t, o_e, o_u = blk((ei, xs[0], xs[1], xs[2], xs[3]))
+        torch.autograd.backward([o_s, o_t, o_e, o_u], ups)
+        bucket.all_reduce()
+        return o_u
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = lib.pfs_launch_count()
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        launches = lib.pfs_launch_count() - n0
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms, launches
+
+    detached = [x.detach() for x in ins]
+    for _ in range(max(args.warmup, 3)):
+        step([x.detach() for x in detached])
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms, launches = timed(lambda: step([x.detach() for x in detached]), args.steps)
+    clocks = sampler.stop()
+    ms_per_step = ms / args.steps
+    edges_total = float(E) * G * world
+    value = edges_total / (ms_per_step * 1e-3)
+
+    # ---- per-kernel durations (CUDA events on the launch stream), same steps --------------------
+    hbm_gbs, peak_src, sm_max = measured_peaks()
+    roofline, kernels = None, None
+    if not args.no_profile:
+        lib.pfs_profile_enable(1)
+        torch.cuda.synchronize(dev)
+        for _ in range(args.steps):
+            step([x.detach() for x in detached])
+        torch.cuda.synchronize(dev)
+        rep = _abi.profile_report()
+        lib.pfs_profile_enable(0)
+        tot = sum(v[1] for v in rep.values())
+        kernels = {k: {"launches": v[0], "ms_per_step": v[1] / args.steps, "share": v[1] / tot}
+                   for k, v in sorted(rep.items(), key=lambda kv: -kv[1][1])[:12]}
+        cand = [k for k in rep if k in KERNEL_ROWS]
+        if cand:
+            top = max(cand, key=lambda k: rep[k][1])
+            n, tms = rep[top]
+            per_e, per_s = KERNEL_ROWS[top]
+            bytes_per_launch = 4.0 * F * (per_e * E + per_s * S) * G
+            dur_s = tms / n * 1e-3
+            achieved = bytes_per_launch / dur_s / 1e9
+            roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s",
+                        "frac": achieved / hbm_gbs, "traffic": None, "peak_source": peak_src,
+                        "avg_launch_ms": tms / n, "algorithmic_bytes_per_launch": bytes_per_launch,
+                        "share_of_step": tms / tot, "binding": "fp32_fma (see fma)"}
+    step_bytes = (5.0 * F * 4 * E + 6.0 * (S + T) * F * 4) * G
+    flops = 2.0 * F * F * (MAC_PER_EDGE_F2 * E + MAC_PER_FIBRE_F2 * S) * G
+    clk = (clocks.get("sm_mhz") or sm_max)
+    fma_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+    fma = {"executed_tflops": flops / (ms_per_step * 1e-3) / 1e12, "peak_tflops_at_max_clock": fma_peak,
+           "frac": flops / (ms_per_step * 1e-3) / 1e12 / fma_peak,
+           "frac_at_measured_clock": flops / (ms_per_step * 1e-3) / 1e12 / (148 * 128 * 2 * clk * 1e6 / 1e12)}
+    step_roofline = {"bound": "hbm", "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9, "peak": hbm_gbs,
+                     "unit": "GB/s", "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_gbs,
+                     "algorithmic_bytes_per_step": step_bytes}
+
+    # ---- end to end: pinned host inputs in, loss out, every step ------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        host = [x.detach().cpu().pin_memory() for x in ins]
+        dbuf = [torch.empty_like(x) for x in detached]
+        h2d = sum(h.numel() * h.element_size() for h in host)
+
+        def e2e_step():
+            for d, h in zip(dbuf, host):
+                d.copy_(h, non_blocking=True)
+            for p in blk.parameters():
+                p.grad = None
+            xs = [d.detach().requires_grad_(True) for d in dbuf]
+            _, o_s, o_t, o_e, o_u = blk((ei, xs[0], xs[1], xs[2], xs[3]))
+            loss = (o_s * ups[0]).sum() + (o_t * ups[1]).sum() + (o_e * ups[2]).sum() + (o_u * ups[3]).sum()
+            loss.backward()
+            bucket.all_reduce()
+            return float(loss.item())       # device -> host read of the step's result
+
+        for _ in range(2):
+            e2e_step()
+        ms_e, _ = timed(e2e_step, max(3, args.steps // 2))
+        ms_e /= max(3, args.steps // 2)
+        e2e = {"value": edges_total / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+               "ms_per_step": ms_e}
+
+    # ---- CPU baseline (rank 0, N = 1) ------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        eps, ncores, sample, _ = cpu_reference(args, seconds=args.cpu_seconds)
+        cpu = {"value": eps, "unit": UNIT, "cores": ncores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C3: %d x complete bipartite %dx%d per GPU, Fdim %d, one Block fwd+bwd, train mode"
+                                   % (G, S, T, F),
+                       "graphs_per_gpu": G, "global_graphs": G * world, "fibres": S, "classes": T, "fdim": F,
+                       "edges_per_step": edges_total, "parallelism": "dp%d" % world,
+                       "l2": "inputs larger than L2 (x_e %.0f MB per step)" % (G * E * F * 4 / 1e6)},
+            "roofline": roofline, "step_roofline": step_roofline, "fma": fma, "kernels": kernels,
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -83,6 +83,14 @@ size_t pfs_sizeof_target_args(void);
 size_t pfs_sizeof_global_args(void);
 size_t pfs_sizeof_head_args(void);
 
+/* Launch accounting and optional per-kernel timing (used by bench.py; not part of the reference
+ * surface).  pfs_launch_count: kernels launched by this library so far.  pfs_profile_enable(1)
+ * starts recording a CUDA event after every kernel on its launch stream; pfs_profile_report waits
+ * for them and writes one line "kernel launches total_ms" per kernel (returns bytes written). */
+long long pfs_launch_count(void);
+int pfs_profile_enable(int on);
+int pfs_profile_report(char* buf, size_t buflen);
+
 /* Workspace (bytes) sufficient for any forward/backward call on this topology. */
 size_t pfs_workspace_bytes(const pfs_topology* topo);
 

@@ -113,6 +113,9 @@ SYMBOLS = {
     "pfs_sizeof_target_args": (ct.c_size_t, []),
     "pfs_sizeof_global_args": (ct.c_size_t, []),
     "pfs_sizeof_head_args": (ct.c_size_t, []),
+    "pfs_launch_count": (ct.c_longlong, []),
+    "pfs_profile_enable": (ct.c_int, [ct.c_int]),
+    "pfs_profile_report": (ct.c_int, [ct.c_char_p, ct.c_size_t]),
     "pfs_workspace_bytes": (ct.c_size_t, [ct.POINTER(TopologyStruct)]),
     "pfs_detect_dense": (ct.c_int, [_P, _I64, _I32, _I32, _P, _P]),
     "pfs_build_topology_temp_bytes": (ct.c_size_t, [_I64, _I32, _I32]),
@@ -186,6 +189,19 @@ def check(rc, what):
     if rc != 0:
         msg = load_library().pfs_last_error()
         raise PfsError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def profile_report():
+    """{kernel: (launches, total_ms)} recorded since pfs_profile_enable(1); synchronises."""
+    lib = load_library()
+    buf = ct.create_string_buffer(1 << 16)
+    n = lib.pfs_profile_report(buf, len(buf))
+    out = {}
+    if n > 0:
+        for line in buf.value.decode().splitlines():
+            name, cnt, ms = line.rsplit(" ", 2)
+            out[name] = (int(cnt), float(ms))
+    return out
 
 
 def ptr(t):

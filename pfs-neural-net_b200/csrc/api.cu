@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -32,10 +33,40 @@ int fail(int code, const char* fmt, ...) {
         cudaError_t e__ = (expr);                                                                   \
         if (e__ != cudaSuccess) return fail(PFS_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
     } while (0)
+// ---- launch accounting / optional per-kernel timing ------------------------------------------
+// Every kernel launch goes through PFS_LAUNCH_CHECK(name) with the launch stream `st` in scope.
+// The launch counter is always on.  With profiling enabled (pfs_profile_enable(1), used by
+// bench.py) an event is recorded on the launch stream after every kernel and at the start of
+// every entry point; a kernel's duration is the gap between its event and the previous one on
+// that stream, which for back-to-back launches on one stream is its execution time.
+struct ProfMark {
+    const char* name;   // nullptr = start-of-call marker
+    cudaEvent_t ev;
+};
+long long g_launches = 0;
+bool g_prof_on = false;
+std::vector<ProfMark> g_marks;
+std::vector<cudaEvent_t> g_event_pool;
+size_t g_events_used = 0;
+
+void prof_mark(const char* name, cudaStream_t st) {
+    if (name) ++g_launches;
+    if (!g_prof_on) return;
+    if (g_events_used == g_event_pool.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        g_event_pool.push_back(e);
+    }
+    cudaEvent_t e = g_event_pool[g_events_used++];
+    if (cudaEventRecord(e, st) != cudaSuccess) return;
+    g_marks.push_back({name, e});
+}
+
 #define PFS_LAUNCH_CHECK(name)                                                                       \
     do {                                                                                            \
         cudaError_t e__ = cudaGetLastError();                                                       \
         if (e__ != cudaSuccess) return fail(PFS_ERR_CUDA, "launch %s: %s", name, cudaGetErrorString(e__)); \
+        prof_mark(name, st);                                                                        \
     } while (0)
 #define PFS_REQUIRE(cond, msg)                                  \
     do {                                                        \
@@ -106,7 +137,7 @@ int dense_ntiles(int S, int T) {
     const int fpt = dense_fpt(T);
     return fpt > 0 ? (S + fpt - 1) / fpt : 0;
 }
-int node_ntiles(int S) { return (S + kNodeRows - 1) / kNodeRows; }
+template <int F> int node_ntiles(int S) { return (S + node_rows<F>() - 1) / node_rows<F>(); }
 
 int make_topo(const pfs_topology& t, Topo& o) {
     PFS_REQUIRE(t.G >= 1 && t.S >= 1 && t.T >= 1 && t.E >= 0 && t.F >= 2, "bad topology sizes");
@@ -261,6 +292,7 @@ template <int F>
 int edge_fwd_impl(const pfs_edge_args& a, const Topo& tp) {
     constexpr int H = 4 * F;
     cudaStream_t st = (cudaStream_t)a.stream;
+    prof_mark(nullptr, st);
     const int total = tp.ntiles * tp.G;
     Bump ws(a.workspace, a.workspace_bytes);
     float* uvec = ws.f((size_t)tp.G * H);
@@ -287,6 +319,7 @@ template <int F>
 int edge_bwd_impl(const pfs_edge_args& a, const Topo& tp) {
     constexpr int H = 4 * F;
     cudaStream_t st = (cudaStream_t)a.stream;
+    prof_mark(nullptr, st);
     const int total = tp.ntiles * tp.G;
     const int mode = !a.normed ? 0 : (a.training ? 1 : 2);
     using SM = EdgeBwdSmem<F>;
@@ -352,8 +385,9 @@ template <int F>
 int source_fwd_impl(const pfs_source_args& a, const Topo& tp) {
     constexpr int M = 2 * F;
     cudaStream_t st = (cudaStream_t)a.stream;
+    prof_mark(nullptr, st);
     const int total = tp.ntiles * tp.G;
-    const int ntn = node_ntiles(tp.S);
+    const int ntn = node_ntiles<F>(tp.S);
     Bump ws(a.workspace, a.workspace_bytes);
     float* Qt = ws.f((size_t)tp.G * tp.T * M);
     float* partn = ws.f((size_t)tp.G * ntn * bn_partial_stride(F));
@@ -391,8 +425,9 @@ template <int F>
 int source_bwd_impl(const pfs_source_args& a, const Topo& tp) {
     constexpr int M = 2 * F, J = 10 * F, K9 = 9 * F;
     cudaStream_t st = (cudaStream_t)a.stream;
+    prof_mark(nullptr, st);
     const int total = tp.ntiles * tp.G;
-    const int ntn = node_ntiles(tp.S);
+    const int ntn = node_ntiles<F>(tp.S);
     const int mode = !a.normed ? 0 : (a.training ? 1 : 2);
     using SMN = SourceNodeBwdSmem<F>;
     using SME = SourceEdgeBwdSmem<F>;
@@ -476,6 +511,7 @@ template <int F>
 int target_fwd_impl(const pfs_target_args& a, const Topo& tp) {
     constexpr int M = 2 * F;
     cudaStream_t st = (cudaStream_t)a.stream;
+    prof_mark(nullptr, st);
     const int total = tp.ntiles * tp.G;
     Bump ws(a.workspace, a.workspace_bytes);
     float* Rs = ws.f((size_t)tp.G * tp.S * M);
@@ -514,6 +550,7 @@ template <int F>
 int target_bwd_impl(const pfs_target_args& a, const Topo& tp) {
     constexpr int M = 2 * F, H = 4 * F;
     cudaStream_t st = (cudaStream_t)a.stream;
+    prof_mark(nullptr, st);
     const int total = tp.ntiles * tp.G;
     using SM = TargetEdgeBwdSmem<F>;
     auto ke = k_target_edge_bwd<F>;
@@ -567,6 +604,7 @@ int target_bwd_impl(const pfs_target_args& a, const Topo& tp) {
 template <int F>
 int head_impl(const pfs_head_args& a, const Topo& tp, bool backward) {
     cudaStream_t st = (cudaStream_t)a.stream;
+    prof_mark(nullptr, st);
     const long long N = (long long)tp.G * tp.E;
     constexpr int pstride = F * F + 2 * F + 1;
     HeadParams p{tp, a.x_e, a.w1, a.b1, a.w2, a.b2, a.scale, a.class_hours, (const long long*)a.edge_tgt,
@@ -670,11 +708,46 @@ size_t pfs_sizeof_target_args(void) { return sizeof(pfs_target_args); }
 size_t pfs_sizeof_global_args(void) { return sizeof(pfs_global_args); }
 size_t pfs_sizeof_head_args(void) { return sizeof(pfs_head_args); }
 
+long long pfs_launch_count(void) { return g_launches; }
+int pfs_profile_enable(int on) {
+    g_prof_on = on != 0;
+    g_marks.clear();
+    g_events_used = 0;
+    return PFS_OK;
+}
+// Text report "name launches total_ms\n" per kernel, summed over everything recorded since
+// pfs_profile_enable(1).  Waits for the recorded events (call it outside the timed region).
+int pfs_profile_report(char* buf, size_t buflen) {
+    if (!buf || buflen == 0) return fail(PFS_ERR_ARG, "null buffer");
+    struct Row { const char* name; long long n; double ms; };
+    std::vector<Row> rows;
+    for (size_t i = 1; i < g_marks.size(); ++i) {
+        if (!g_marks[i].name) continue;
+        float ms = 0.f;
+        if (cudaEventSynchronize(g_marks[i].ev) != cudaSuccess) continue;
+        if (cudaEventElapsedTime(&ms, g_marks[i - 1].ev, g_marks[i].ev) != cudaSuccess) continue;
+        bool found = false;
+        for (auto& r : rows)
+            if (strcmp(r.name, g_marks[i].name) == 0) { r.n++; r.ms += ms; found = true; break; }
+        if (!found) rows.push_back({g_marks[i].name, 1, ms});
+    }
+    size_t off = 0;
+    for (auto& r : rows) {
+        int w = snprintf(buf + off, buflen - off, "%s %lld %.6f\n", r.name, r.n, r.ms);
+        if (w < 0 || (size_t)w >= buflen - off) break;
+        off += (size_t)w;
+    }
+    buf[off < buflen ? off : buflen - 1] = 0;
+    g_marks.clear();
+    g_events_used = 0;
+    return (int)off;
+}
+
 size_t pfs_workspace_bytes(const pfs_topology* t) {
     if (!t) return 0;
     const size_t G = t->G, S = t->S, T = t->T, E = t->E, F = t->F;
     const size_t ntiles = t->layout == PFS_LAYOUT_DENSE ? (size_t)dense_ntiles(t->S, t->T) : (size_t)t->ntiles;
-    const size_t ntn = node_ntiles(t->S);
+    const size_t ntn = ((size_t)t->S + 49) / 50;   // smallest node tile of any Fdim
     size_t fl = 0;
     fl += G * S * 16 * F;                               // node tables, fibre sums, moment coefficients
     fl += G * T * 16 * F;
@@ -814,8 +887,10 @@ int pfs_global_fwd(const pfs_global_args* a) {
     GlobalParams p;
     PFS_TRY(global_common(a, p));
     PFS_REQUIRE(a->u_out, "null pointer");
+    cudaStream_t st = (cudaStream_t)a->stream;
+    prof_mark(nullptr, st);
     const size_t smem = sizeof(float) * (22 * (size_t)a->F + 2);
-    k_global_fwd<<<a->G, kThreads, smem, (cudaStream_t)a->stream>>>(p);
+    k_global_fwd<<<a->G, kThreads, smem, st>>>(p);
     PFS_LAUNCH_CHECK("k_global_fwd");
     return PFS_OK;
 }
@@ -825,6 +900,7 @@ int pfs_global_bwd(const pfs_global_args* a) {
     PFS_REQUIRE(a->g_out && a->g_x_s && a->g_x_t && a->g_u && a->g_w1 && a->g_b1 && a->g_w2 && a->g_b2 && a->workspace,
                 "null pointer");
     cudaStream_t st = (cudaStream_t)a->stream;
+    prof_mark(nullptr, st);
     const int F = a->F, K = 3 * F, pg = global_partial_floats(F);
     Bump ws(a->workspace, a->workspace_bytes);
     float* gpart = ws.f((size_t)a->G * pg);

@@ -95,11 +95,11 @@ __global__ void __launch_bounds__(kThreads) k_source_edge_fwd(const SourceEdgeFw
 }
 
 // ------------------------------------------------------------------------------------------
-// node pass geometry: a tile of kNodeRows fibres, thread = (row pair, output chunk of 2F)
+// node pass geometry: a tile of node_rows<F>() fibres, thread = (row pair, output chunk of 2F)
 // ------------------------------------------------------------------------------------------
 constexpr int kNodeChunks = 5;                               // 10F outputs = 5 chunks of 2F
-constexpr int kNodePairs = kThreads / kNodeChunks;           // 51 row pairs
-constexpr int kNodeRows = 2 * kNodePairs;                    // 102 fibres per node tile
+template <int F> __host__ __device__ constexpr int node_pairs() { return F <= 10 ? kThreads / kNodeChunks : 25; }  // row pairs (shared memory bound for wide F)
+template <int F> __host__ __device__ constexpr int node_rows() { return 2 * node_pairs<F>(); }                          // fibres per node tile
 
 // hcat row (without the u columns): [x_s | mean | std | skew | kurt], finalised from raw moments
 // exactly as reference src/gnn.py:141-151.  Writes HC[r][0..9F) for the rows of one tile.
@@ -142,8 +142,8 @@ template <int F>
 struct SourceNodeFwdSmem {
     static constexpr int K9 = 9 * F, J = 10 * F;
     static constexpr int LDH = K9 + 1, LDA = J + 1;
-    static constexpr int kBuf = kNodeRows * LDA;   // HC, then reused for A3 (LDA >= LDH)
-    static constexpr int kFloats = K9 * J + J * F + kBuf + J + F + kNodeRows * F;
+    static constexpr int kBuf = node_rows<F>() * LDA;   // HC, then reused for A3 (LDA >= LDH)
+    static constexpr int kFloats = K9 * J + J * F + kBuf + J + F + node_rows<F>() * F;
     static constexpr size_t bytes = sizeof(float) * kFloats;
 };
 
@@ -166,8 +166,8 @@ __global__ void __launch_bounds__(kThreads) k_source_node_fwd(const SourceNodeFw
     const int rp = threadIdx.x / kNodeChunks, ch = threadIdx.x - rp * kNodeChunks;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
         const int g = tile / p.ntiles, lt = tile - g * p.ntiles;
-        const int f0 = lt * kNodeRows;
-        const int rows = min(kNodeRows, p.S - f0);
+        const int f0 = lt * node_rows<F>();
+        const int rows = min(node_rows<F>(), p.S - f0);
         const size_t row0 = (size_t)g * p.S + f0;
         build_hcat<F>(p.x_s, p.moments, row0, rows, BUF, LDH);
         for (int j = threadIdx.x; j < J; j += kThreads) {
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(kThreads) k_source_node_fwd(const SourceNodeFw
         __syncthreads();
         float a0[C], a1[C];
         const int r0 = 2 * rp, r1 = 2 * rp + 1;
-        const bool live = rp < kNodePairs && r0 < rows;
+        const bool live = rp < node_pairs<F>() && r0 < rows;
         if (live) {
             const float* h0 = BUF + r0 * LDH;
             const float* h1 = BUF + (r1 < rows ? r1 : r0) * LDH;
@@ -270,7 +270,17 @@ template <int F>
 struct SourceNodeBwdSmem {
     static constexpr int K9 = 9 * F, J = 10 * F;
     static constexpr int LDH = K9 + 1, LDA = J + 1, LDY = F + 1;
-    static constexpr int kFloats = J * K9 + F * J + kNodeRows * (LDH + 2 * LDA + LDY);
+    // dW3 on threads [0, 224), dW4 on the last warp (F <= 14); F = 16 shares the first warp
+    static_assert(F * F <= kThreads && 2 * F <= 32, "node kernels support Fdim <= 16");
+    static constexpr int kNT3 = (F * F <= 224) ? 224 : kThreads;
+    static constexpr int kT04 = (F * F <= 224) ? 224 : 0;
+    using AccW3 = OuterAcc<J, K9, 10, 9, 0, kNT3>;
+    using AccW4 = OuterAcc<F, J, F / 2, 10, kT04, 32>;
+    static constexpr int kRows = node_rows<F>() * (LDH + 2 * LDA + LDY);
+    static constexpr int kScr = AccW3::kScratchFloats > AccW4::kScratchFloats ? AccW3::kScratchFloats : AccW4::kScratchFloats;
+    // the row buffers double as the cross-group scratch of the weight-gradient flush
+    static constexpr int kRegion = kRows > kScr ? kRows : kScr;
+    static constexpr int kFloats = J * K9 + F * J + kRegion;
     static constexpr size_t bytes = sizeof(float) * kFloats;
 };
 
@@ -282,18 +292,14 @@ __global__ void __launch_bounds__(kThreads) k_source_node_bwd(const SourceNodeBw
     float* W3o = sm;                      // [j<10F][k<9F]  (w3 rows, first 9F columns)
     float* W4o = W3o + J * K9;            // [f<F][j<10F]   (w4 as stored)
     float* HC = W4o + F * J;              // [rows][LDH]  hcat, later dhcat
-    float* A3 = HC + kNodeRows * LDH;     // [rows][LDA]
-    float* DH3 = A3 + kNodeRows * LDA;    // [rows][LDA]
-    float* DY = DH3 + kNodeRows * LDA;    // [rows][LDY]
+    float* A3 = HC + node_rows<F>() * LDH;     // [rows][LDA]
+    float* DH3 = A3 + node_rows<F>() * LDA;    // [rows][LDA]
+    float* DY = DH3 + node_rows<F>() * LDA;    // [rows][LDY]
     load_w_outmajor<K9, J>(W3o, p.w3, J, 0);
     load_w_outmajor<J, F>(W4o, p.w4, J, 0);
     __syncthreads();
-    // dW3 on threads [0, 224), dW4 on the last warp (F <= 14); F = 16 shares the first warp
-    static_assert(F * F <= kThreads && 2 * F <= 32, "node kernels support Fdim <= 16");
-    constexpr int kNT3 = (F * F <= 224) ? 224 : kThreads;
-    constexpr int kT04 = (F * F <= 224) ? 224 : 0;
-    using AccW3 = OuterAcc<J, K9, 10, 9, 0, kNT3>;
-    using AccW4 = OuterAcc<F, J, F / 2, 10, kT04, 32>;
+    using AccW3 = typename SM::AccW3;
+    using AccW4 = typename SM::AccW4;
     AccW3 accw3;
     AccW4 accw4;
     accw3.init();
@@ -303,8 +309,8 @@ __global__ void __launch_bounds__(kThreads) k_source_node_bwd(const SourceNodeBw
     const int rp = threadIdx.x / kNodeChunks, ch = threadIdx.x - rp * kNodeChunks;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
         const int g = tile / p.ntiles, lt = tile - g * p.ntiles;
-        const int f0 = lt * kNodeRows;
-        const int rows = min(kNodeRows, p.S - f0);
+        const int f0 = lt * node_rows<F>();
+        const int rows = min(node_rows<F>(), p.S - f0);
         const size_t row0 = (size_t)g * p.S + f0;
         build_hcat<F>(p.x_s, p.moments, row0, rows, HC, LDH);
         // dy = BatchNorm backward of the upstream gradient
@@ -332,7 +338,7 @@ __global__ void __launch_bounds__(kThreads) k_source_node_bwd(const SourceNodeBw
         // dh3 = (dy . W4) * lrelu'(h3), two rows x one chunk per thread
         {
             const int r0 = 2 * rp, r1 = 2 * rp + 1;
-            if (rp < kNodePairs && r0 < rows) {
+            if (rp < node_pairs<F>() && r0 < rows) {
                 const bool two = r1 < rows;
                 float a0[C], a1[C], d0[C], d1[C];
                 load_row<C>(p.hidden + (row0 + r0) * J + ch * C, a0);

@@ -338,7 +338,11 @@ struct TargetEdgeBwdParams {
 template <int F>
 struct TargetEdgeBwdSmem {
     static constexpr int M = 2 * F, LDM = M + 4, LDF = F + 2;
-    static constexpr int kFloats = 2 * F * M + kTile * (LDM + LDF);
+    using AccW1 = OuterAcc<M, F, F / 2, F / 2>;
+    static constexpr int kTiles = kTile * (LDM + LDF);
+    // the tile region doubles as the cross-group scratch of the weight-gradient flush
+    static constexpr int kRegion = kTiles > AccW1::kScratchFloats ? kTiles : AccW1::kScratchFloats;
+    static constexpr int kFloats = 2 * F * M + kRegion;
     static constexpr size_t bytes = sizeof(float) * kFloats;
 };
 
@@ -354,7 +358,7 @@ __global__ void __launch_bounds__(kThreads) k_target_edge_bwd(const TargetEdgeBw
     load_w_inmajor<F, M>(W1t, p.w1, M, F);
     load_w_outmajor<F, M>(W1o, p.w1, M, F);
     __syncthreads();
-    using AccW1 = OuterAcc<M, F, F / 2, F / 2>;
+    using AccW1 = typename SM::AccW1;
     AccW1 accw1;
     accw1.init();
     const Topo& tp = p.tp;
@@ -628,14 +632,17 @@ __global__ void __launch_bounds__(kThreads) k_head_bwd(const HeadParams p) {
     __shared__ __align__(16) float W1t[F * F];
     __shared__ __align__(16) float W1o[F * F];
     __shared__ float b1s[F], w2s[F];
-    __shared__ float DH[kTile * LDF];
-    __shared__ float XE[kTile * LDF];
+    using AccW1 = OuterAcc<F, F, F / 2, F / 2, 0, 128>;
+    // one region: the two staging tiles, reused as the flush scratch and the final reduction buffer
+    constexpr int kRegion = (2 * kTile * LDF > AccW1::kScratchFloats) ? 2 * kTile * LDF : AccW1::kScratchFloats;
+    __shared__ float REGION[kRegion];
+    float* DH = REGION;
+    float* XE = REGION + kTile * LDF;
     load_w_inmajor<F, F>(W1t, p.w1, F, 0);
     load_w_outmajor<F, F>(W1o, p.w1, F, 0);
     load_vec<F>(b1s, p.b1);
     load_vec<F>(w2s, p.w2);
     __syncthreads();
-    using AccW1 = OuterAcc<F, F, F / 2, F / 2>;
     AccW1 acc;
     acc.init();
     float dw2[F], db1[F], db2 = 0.f;
