@@ -104,7 +104,7 @@ int persistent_grid(Kern kern, size_t smem, long long items) {
 
 template <class Kern>
 int allow_smem(Kern kern, size_t smem) {
-    if (smem > 48 * 1024) {
+    if (smem > 8 * 1024) {   // static + dynamic may cross the 48 KB default even when dynamic alone does not
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(PFS_ERR_CUDA, "cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
     }
@@ -160,6 +160,35 @@ int make_topo(const pfs_topology& t, Topo& o) {
         return fail(PFS_ERR_ARG, "unknown layout %d", t.layout);
     }
     return PFS_OK;
+}
+
+// weights -> __constant__ memory on the launch stream (common.cuh: c_w)
+int upload_weights(const PackList& pl, int nfloats, float* staging, cudaStream_t st) {
+    if (nfloats > kConstFloats) return fail(PFS_ERR_UNSUPPORTED, "weights (%d floats) exceed the constant bank", nfloats);
+    k_pack_weights<<<8, 256, 0, st>>>(pl, staging);
+    PFS_LAUNCH_CHECK("k_pack_weights");
+    PFS_CUDA(cudaMemcpyToSymbolAsync(c_w, staging, sizeof(float) * (size_t)nfloats, 0, cudaMemcpyDeviceToDevice, st));
+    return PFS_OK;
+}
+
+// staging geometry of the edge kernels (common.cuh: TileStage)
+int max_fibres_per_tile(const Topo& tp) {
+    const int m = tp.layout == PFS_LAYOUT_DENSE ? tp.fpt : kTile;
+    return m < tp.S ? m : tp.S;
+}
+bool stage_class_table(const Topo& tp, int row_floats) {   // both buffers of the class table <= 32 KB
+    return (size_t)tp.T * (row_floats + 4) * sizeof(float) * 2 <= 32 * 1024;
+}
+
+// staging depth that fits: 2 buffers when the kernel's shared memory stays under the per-CTA limit
+constexpr size_t kSmemLimit = 220 * 1024;
+template <class SizeFn>
+int pick_nbuf(SizeFn bytes_for, size_t& smem) {
+    for (int nbuf = 2; nbuf >= 1; --nbuf) {
+        smem = bytes_for(nbuf);
+        if (smem <= kSmemLimit) return nbuf;
+    }
+    return 0;
 }
 
 bool fdim_supported(int F) { return F == 4 || F == 8 || F == 10 || F == 16; }
@@ -248,15 +277,21 @@ size_t class_stage_floats(const Topo& tp, int J) {
 }
 int bn_forward_tail(int F, int G, long long rows, const float* partial, int ntiles, int twice, int training,
                     const float* gamma, const float* beta, float* rm, float* rv, long long* nbt, float eps,
-                    float momentum, float* save, cudaStream_t st) {
+                    float momentum, float* save, cudaStream_t st, int rec_ncta = 0, int rec_nrec = 0) {
     const int n = G * F;
     if (training) {
         if (rows <= 1) return fail(PFS_ERR_ARG, "Expected more than 1 value per channel when training");
-        k_bn_finalize<<<(n + 127) / 128, 128, 0, st>>>(partial, ntiles, bn_partial_stride(F), F, G, gamma, beta, eps,
-                                                        twice, save);
-        PFS_LAUNCH_CHECK("k_bn_finalize");
+        if (rec_ncta > 0) {
+            k_bn_finalize_rec<<<(n + 127) / 128, 128, 0, st>>>(partial, rec_ncta, rec_nrec, ntiles, F, G, gamma, beta,
+                                                                eps, twice, save);
+            PFS_LAUNCH_CHECK("k_bn_finalize_rec");
+        } else {
+            k_bn_finalize<<<(n + 127) / 128, 128, 0, st>>>(partial, ntiles, bn_partial_stride(F), F, G, gamma, beta,
+                                                            eps, twice, save);
+            PFS_LAUNCH_CHECK("k_bn_finalize");
+        }
         if (rm && rv) {
-            k_bn_running<<<1, 64, 0, st>>>(save, F, G, rows, gamma, beta, eps, momentum, twice, rm, rv, nbt);
+            k_bn_running<<<F, 32, 0, st>>>(save, F, G, rows, gamma, beta, eps, momentum, twice, rm, rv, nbt);
             PFS_LAUNCH_CHECK("k_bn_running");
         }
     } else {
@@ -267,11 +302,13 @@ int bn_forward_tail(int F, int G, long long rows, const float* partial, int ntil
     return PFS_OK;
 }
 int affine_rows(const float* in, const float* save, int F, long long rows, int G, float* out, cudaStream_t st) {
-    const long long total = rows * F * G;
-    if (total == 0) return PFS_OK;
-    long long blocks = (total + 255) / 256;
-    if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
-    k_affine_rows<<<(int)blocks, 256, 0, st>>>(in, save, F, rows * F, G, out);
+    const long long per_graph = rows * F / 2;
+    if (per_graph == 0) return PFS_OK;
+    long long blocks = (per_graph + 255) / 256;
+    const long long cap = (16LL * num_sms() + G - 1) / G;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    k_affine_rows<<<dim3((unsigned)blocks, G), 256, 0, st>>>(in, save, F, rows * F, G, out);
     PFS_LAUNCH_CHECK("k_affine_rows");
     return PFS_OK;
 }
@@ -294,22 +331,39 @@ int edge_fwd_impl(const pfs_edge_args& a, const Topo& tp) {
     cudaStream_t st = (cudaStream_t)a.stream;
     prof_mark(nullptr, st);
     const int total = tp.ntiles * tp.G;
+    const int max_fib = max_fibres_per_tile(tp);
+    const bool sc = stage_class_table(tp, H);
+    size_t smem = 0;
+    const int nbuf = pick_nbuf([&](int nb) { return sizeof(float) * TileStage<F, 1, H, H>::floats(max_fib, tp.T, sc, nb); }, smem);
+    if (!nbuf) return fail(PFS_ERR_UNSUPPORTED, "edge_fwd: tile staging does not fit shared memory");
+    PFS_TRY(allow_smem(k_edge_fwd<F>, smem));
+    const int grid = persistent_grid(k_edge_fwd<F>, smem, total);
+    const int nrec = chunk_records(grid, total, tp.ntiles);
     Bump ws(a.workspace, a.workspace_bytes);
     float* uvec = ws.f((size_t)tp.G * H);
     float* Ps = ws.f((size_t)tp.G * tp.S * H);
     float* Pt = ws.f((size_t)tp.G * tp.T * H);
-    float* part = ws.f((size_t)total * bn_partial_stride(F));
+    float* part = ws.f((size_t)grid * nrec * bn_partial_stride(F));
+    float* wstage = ws.f(kConstFloats);
     if (!ws.ok) return fail(PFS_ERR_WORKSPACE, "edge_fwd: workspace too small (%zu B)", a.workspace_bytes);
     PFS_TRY(edge_tables<F>(a, tp, uvec, Ps, Pt, st));
+    {
+        PackList pl{};
+        pl.it[0] = PackItem{a.w1, H, 2 * F, F, H, 1, 0};            // W1_e input-major [F][H]
+        pl.it[1] = PackItem{a.w2, H, 0, H, F, 1, F * H};            // W2 input-major [H][F]
+        pl.it[2] = PackItem{a.b2, 1, 0, 1, F, 0, 2 * F * H};        // b2
+        pl.n = 3;
+        PFS_TRY(upload_weights(pl, 2 * F * H + F, wstage, st));
+    }
     const bool stats = a.normed && a.training;
-    EdgeFwdParams p{tp, a.x_e, Ps, Pt, a.w1, a.w2, a.b2, a.x_e_out, stats ? part : nullptr};
-    const int grid = persistent_grid(k_edge_fwd<F>, 0, total);
-    k_edge_fwd<F><<<grid, kThreads, 0, st>>>(p);
+    EdgeFwdParams p{tp, a.x_e, Ps, Pt, a.w1, a.w2, a.b2, a.x_e_out, stats ? part : nullptr, max_fib, sc ? 1 : 0, nrec, nbuf};
+    k_edge_fwd<F><<<grid, kThreads, smem, st>>>(p);
     PFS_LAUNCH_CHECK("k_edge_fwd");
     if (a.normed) {
         PFS_REQUIRE(a.gamma && a.beta && a.bn_save, "normed edge model needs gamma, beta, bn_save");
         PFS_TRY(bn_forward_tail(F, tp.G, tp.E, part, tp.ntiles, 1, a.training, a.gamma, a.beta, a.running_mean,
-                                a.running_var, (long long*)a.num_batches_tracked, a.eps, a.momentum, a.bn_save, st));
+                                a.running_var, (long long*)a.num_batches_tracked, a.eps, a.momentum, a.bn_save, st,
+                                grid, nrec));
         PFS_TRY(affine_rows(a.x_e_out, a.bn_save, F, tp.E, tp.G, a.x_e_out, st));
     }
     return PFS_OK;
@@ -324,8 +378,13 @@ int edge_bwd_impl(const pfs_edge_args& a, const Topo& tp) {
     const int mode = !a.normed ? 0 : (a.training ? 1 : 2);
     using SM = EdgeBwdSmem<F>;
     auto kern = k_edge_bwd<F>;
-    PFS_TRY(allow_smem(kern, SM::bytes));
-    const int grid = persistent_grid(kern, SM::bytes, total);
+    const int max_fib = max_fibres_per_tile(tp);
+    const bool sc = stage_class_table(tp, H);
+    size_t smem_bwd = 0;
+    const int nbuf = pick_nbuf([&](int nb) { return SM::bytes(max_fib, tp.T, sc, nb); }, smem_bwd);
+    if (!nbuf) return fail(PFS_ERR_UNSUPPORTED, "edge_bwd: tile staging does not fit shared memory");
+    PFS_TRY(allow_smem(kern, smem_bwd));
+    const int grid = persistent_grid(kern, smem_bwd, total);
     constexpr int pstride = 2 * H * F + F;
     Bump ws(a.workspace, a.workspace_bytes);
     float* uvec = ws.f((size_t)tp.G * H);
@@ -340,8 +399,18 @@ int edge_bwd_impl(const pfs_edge_args& a, const Topo& tp) {
     float* tot = ws.f((size_t)tp.G * H);
     float* wpart = ws.f((size_t)grid * pstride);
     float* opart = ws.f((size_t)kMaxCtas * (H * F + H));
+    float* wstage = ws.f(kConstFloats);
     if (!ws.ok) return fail(PFS_ERR_WORKSPACE, "edge_bwd: workspace too small (%zu B)", a.workspace_bytes);
     PFS_TRY(edge_tables<F>(a, tp, uvec, Ps, Pt, st));
+    {
+        using CW = EdgeBwdConst<F>;
+        PackList pl{};
+        pl.it[0] = PackItem{a.w1, H, 2 * F, F, H, 1, CW::kW1t};     // W1_e input-major [F][H]
+        pl.it[1] = PackItem{a.w2, H, 0, H, F, 0, CW::kW2o};         // W2 as stored [F][H]
+        pl.it[2] = PackItem{a.w1, H, 2 * F, F, H, 0, CW::kW1o};     // W1_e as stored [H][F]
+        pl.n = 3;
+        PFS_TRY(upload_weights(pl, CW::kFloats, wstage, st));
+    }
     const int n = tp.G * F;
     k_edge_bn_bwd_coef<<<(n + 127) / 128, 128, 0, st>>>(0, mode, F, tp.G, tp.ntiles, tp.E, a.bn_save, a.gamma, a.beta,
                                                          a.running_mean, a.running_var, a.eps, statp, coef, dgb);
@@ -359,9 +428,9 @@ int edge_bwd_impl(const pfs_edge_args& a, const Topo& tp) {
         PFS_TRY(colsum_all(dgb, tp.G, 2 * F, F, F, a.g_beta, st));
     }
     const bool dense = tp.layout == PFS_LAYOUT_DENSE;
-    EdgeBwdParams p{tp, a.x_e, a.x_e_out, a.g_out, Ps, Pt, a.w1, a.w2, coef, a.g_x_e, dPs,
-                    dense ? stage : nullptr, dense ? nullptr : stage, wpart, pstride};
-    kern<<<grid, kThreads, SM::bytes, st>>>(p);
+    EdgeBwdParams p{tp, a.x_e, a.x_e_out, a.g_out, Ps, Pt, coef, a.g_x_e, dPs,
+                    dense ? stage : nullptr, dense ? nullptr : stage, wpart, pstride, max_fib, sc ? 1 : 0, nbuf};
+    kern<<<grid, kThreads, smem_bwd, st>>>(p);
     PFS_LAUNCH_CHECK("k_edge_bwd");
     PFS_TRY(reduce_partials(wpart, grid, pstride, 0, H * F, F, a.g_w1, H, 2 * F, st));
     PFS_TRY(reduce_partials(wpart, grid, pstride, H * F, F * H, H, a.g_w2, H, 0, st));
@@ -485,7 +554,7 @@ int source_bwd_impl(const pfs_source_args& a, const Topo& tp) {
     PFS_TRY(reduce_partials(wpe, gride, pstride_e, M * F + M * M, M, M, a.g_b2, M, 0, st));
     PFS_TRY(class_sums(tp, stage, M, dQt, st));
     PFS_TRY((node_linear_bwd<F, M>(dQt, (long long)tp.G * tp.T, a.w1, M, 0, a.g_x_t, st)));
-    PFS_TRY((outer_rows<M, F, F / 2, F / 2>(dQt, a.x_t, (long long)tp.G * tp.T, opart, a.g_w1, M, 0, a.g_b1, st)));
+    PFS_TRY((outer_rows<M, F, 4, F / 2>(dQt, a.x_t, (long long)tp.G * tp.T, opart, a.g_w1, M, 0, a.g_b1, st)));
     return PFS_OK;
 }
 
@@ -539,7 +608,7 @@ int target_fwd_impl(const pfs_target_args& a, const Topo& tp) {
         PFS_LAUNCH_CHECK("k_target_tail_fwd");
     }
     if (a.normed && a.training && a.running_mean && a.running_var) {
-        k_bn_running<<<1, 64, 0, st>>>(a.bn_save, F, tp.G, tp.T, a.gamma, a.beta, a.eps, a.momentum, 0, a.running_mean,
+        k_bn_running<<<F, 32, 0, st>>>(a.bn_save, F, tp.G, tp.T, a.gamma, a.beta, a.eps, a.momentum, 0, a.running_mean,
                                        a.running_var, (long long*)a.num_batches_tracked);
         PFS_LAUNCH_CHECK("k_bn_running");
     }
@@ -594,7 +663,7 @@ int target_bwd_impl(const pfs_target_args& a, const Topo& tp) {
     }
     PFS_TRY(reduce_partials(wpe, gride, pstride_e, 0, M * F, F, a.g_w1, M, F, st));
     PFS_TRY((node_linear_bwd<F, M>(dRs, (long long)tp.G * tp.S, a.w1, M, 0, a.g_x_s, st)));
-    PFS_TRY((outer_rows<M, F, F / 2, F / 2>(dRs, a.x_s, (long long)tp.G * tp.S, opart, a.g_w1, M, 0, a.g_b1, st)));
+    PFS_TRY((outer_rows<M, F, 4, F / 2>(dRs, a.x_s, (long long)tp.G * tp.S, opart, a.g_w1, M, 0, a.g_b1, st)));
     return PFS_OK;
 }
 
@@ -668,16 +737,18 @@ __global__ void k_lower_bounds(const int* keys, int E, int n, int* ptr) {
 // greedy packing of whole fibres into tiles of <= kTile edges (sequential, one-time per topology)
 __global__ void k_pack_tiles(const int* rowptr, int S, int* tile_fibre, int* ntiles, int* max_degree) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    int nt = 0, cur = 0, maxd = 0;
+    int nt = 0, cur = 0, nf = 0, maxd = 0;   // a tile holds <= kTile edges AND <= kTile fibres
     tile_fibre[0] = 0;
     for (int f = 0; f < S; ++f) {
         const int d = rowptr[f + 1] - rowptr[f];
         maxd = d > maxd ? d : maxd;
-        if (cur + d > kTile && cur > 0) {
+        if ((cur + d > kTile && cur > 0) || nf >= kTile) {
             tile_fibre[++nt] = f;
             cur = 0;
+            nf = 0;
         }
         cur += d;
+        ++nf;
     }
     tile_fibre[++nt] = S;
     *ntiles = nt;
@@ -755,6 +826,7 @@ size_t pfs_workspace_bytes(const pfs_topology* t) {
     fl += G * ntn * (12 * F + 8);
     if (t->layout != PFS_LAYOUT_DENSE) fl += G * E * 4 * F;
     fl += (size_t)kMaxCtas * (100 * F * F + 32 * F + 64) * 2;   // per-CTA weight-gradient partials
+    fl += 2 * kConstFloats;                                       // weight staging for the constant bank
     fl += G * (36 * F * F + 128 * F);
     fl += 4096;
     return fl * sizeof(float) + 64 * 256;

@@ -22,7 +22,7 @@ constexpr float kSlopeVar = 0.01f;  // F.leaky_relu default on the variance (ref
 constexpr float kStdEps = 1e-6f;    // reference src/gnn.py:142,149
 constexpr int kNumSM = 148;
 
-__device__ __forceinline__ float lrelu(float x) { return x > 0.f ? x : kSlope * x; }
+__device__ __forceinline__ float lrelu(float x) { return fmaxf(x, kSlope * x); }   // slope < 1
 __device__ __forceinline__ float dlrelu(float x) { return x > 0.f ? 1.f : kSlope; }
 
 // ------------------------------------------------------------------------------------------
@@ -178,30 +178,226 @@ __device__ __forceinline__ void load_vec(float* dst, const float* __restrict__ v
 }
 
 // y[j] += sum_k Wt[k * J + j] * x[k]; Wt in shared memory (every lane reads the same address:
-// one broadcast wavefront per LDS.128), x and y in registers.
+// one broadcast wavefront per LDS.128), x and y in registers.  The multiply-adds are issued as
+// packed FFMA2 (fma.rn.f32x2, sm_100+): two output features per instruction, x[k] broadcast.
 template <int K, int J>
 __device__ __forceinline__ void dense_acc(const float* Wt, const float (&x)[K], float (&y)[J]) {
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        const float xk = x[k];
+        const float2 xx = make_float2(x[k], x[k]);
         if constexpr (J % 4 == 0) {
             const float4* w = reinterpret_cast<const float4*>(Wt + k * J);
 #pragma unroll
             for (int j = 0; j < J / 4; ++j) {
                 const float4 v = w[j];
-                y[4 * j] = fmaf(v.x, xk, y[4 * j]);
-                y[4 * j + 1] = fmaf(v.y, xk, y[4 * j + 1]);
-                y[4 * j + 2] = fmaf(v.z, xk, y[4 * j + 2]);
-                y[4 * j + 3] = fmaf(v.w, xk, y[4 * j + 3]);
+                const float2 a = __ffma2_rn(make_float2(v.x, v.y), xx, make_float2(y[4 * j], y[4 * j + 1]));
+                const float2 b = __ffma2_rn(make_float2(v.z, v.w), xx, make_float2(y[4 * j + 2], y[4 * j + 3]));
+                y[4 * j] = a.x; y[4 * j + 1] = a.y; y[4 * j + 2] = b.x; y[4 * j + 3] = b.y;
             }
         } else {
             const float2* w = reinterpret_cast<const float2*>(Wt + k * J);
 #pragma unroll
             for (int j = 0; j < J / 2; ++j) {
-                const float2 v = w[j];
-                y[2 * j] = fmaf(v.x, xk, y[2 * j]);
-                y[2 * j + 1] = fmaf(v.y, xk, y[2 * j + 1]);
+                const float2 a = __ffma2_rn(w[j], xx, make_float2(y[2 * j], y[2 * j + 1]));
+                y[2 * j] = a.x; y[2 * j + 1] = a.y;
             }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// asynchronous staging of a tile's inputs (global -> shared, double-buffered): the loads of tile
+// i+1 are in flight while tile i is computed, so DRAM/L2 latency never sits in front of the FMAs.
+// cp.async (LDGSTS) in 8-byte chunks handles every alignment the rows can have (F is even) and
+// row gathers; contiguous 16-byte aligned slabs use 16-byte chunks.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async8(float* smem, const float* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async16(float* smem, const float* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// flat copy of `nfloats` floats (even count; both pointers 8-byte aligned)
+__device__ __forceinline__ void stage_flat(float* dst, const float* __restrict__ src, int nfloats) {
+    const bool a16 = ((((uintptr_t)src) | ((uintptr_t)dst)) & 15) == 0;
+    if (a16) {
+        const int n4 = nfloats >> 2;
+        for (int i = threadIdx.x; i < n4; i += kThreads) cp_async16(dst + 4 * i, src + 4 * i);
+        for (int i = (n4 << 2) + 2 * threadIdx.x; i < nfloats; i += 2 * kThreads) cp_async8(dst + i, src + i);
+    } else {
+        const int n2 = nfloats >> 1;
+        for (int i = threadIdx.x; i < n2; i += kThreads) cp_async8(dst + 2 * i, src + 2 * i);
+    }
+}
+// rows of ROW floats: dst[r * LD + c] = src[rowidx(r) * ROW + c]  (gather by an index array, or
+// consecutive rows starting at row0 when idx == nullptr)
+template <int ROW, int LD, int SRC_LD = ROW>
+__device__ __forceinline__ void stage_rows(float* dst, const float* __restrict__ src, long long row0,
+                                           const int* __restrict__ idx, int nrows) {
+    if (idx == nullptr && LD == ROW && SRC_LD == ROW) {
+        stage_flat(dst, src + row0 * ROW, nrows * ROW);
+        return;
+    }
+    constexpr int C = ROW / 2;
+    for (int i = threadIdx.x; i < nrows * C; i += kThreads) {
+        const int r = i / C, c = i - r * C;
+        const long long row = idx ? (row0 + idx[r]) : (row0 + r);
+        cp_async8(dst + r * LD + 2 * c, src + row * SRC_LD + 2 * c);
+    }
+}
+
+// Double-buffered inputs of one tile: NE per-edge tensors (rows of F floats, in CSR order), one
+// per-fibre table (rows of PF floats, the tile's fibres are consecutive) and one per-class table
+// (rows of PC floats, padded to PC + 4 in shared memory against bank conflicts; staged only
+// when it is small enough, else read through L1).  All threads of the CTA call issue().
+template <int F, int NE, int PF, int PC>
+struct TileStage {
+    static constexpr int PCP = PC + 4;
+    float* base;
+    int per, max_fib;
+    bool with_class, dbl;
+    // nbuf = 2: double-buffered (tile i+1 in flight while tile i is computed); 1: load-then-compute
+    __host__ __device__ static size_t floats(int max_fib, int T, bool with_class, int nbuf = 2) {
+        return nbuf * ((size_t)NE * kTile * F + (size_t)max_fib * PF + (with_class ? (size_t)T * PCP : 0));
+    }
+    __device__ __forceinline__ void init(float* dyn, int max_fib_, int T, bool with_class_, int nbuf = 2) {
+        base = dyn;
+        max_fib = max_fib_;
+        with_class = with_class_;
+        dbl = nbuf == 2;
+        per = NE * kTile * F + max_fib * PF + (with_class ? T * PCP : 0);
+    }
+    // pipeline step at the top of the loop body for `tile` (buffer parity b): returns the buffer
+    // holding this tile once the following __syncthreads() has passed
+    template <class GetTile>
+    __device__ __forceinline__ int step(const Topo& tp, int tile, int t_end, int b, const float* const* esrc,
+                                        const float* fsrc, const float* csrc, GetTile get) const {
+        if (dbl) {
+            if (tile + 1 < t_end) issue(tp, get(tile + 1), b ^ 1, esrc, fsrc, csrc);
+            cp_async_commit();
+            cp_async_wait<1>();
+            return b;
+        }
+        issue(tp, get(tile), 0, esrc, fsrc, csrc);
+        cp_async_commit();
+        cp_async_wait<0>();
+        return 0;
+    }
+    // before the loop: first tile of a double-buffered pipeline
+    template <class GetTile>
+    __device__ __forceinline__ void prologue(const Topo& tp, int t_begin, int t_end, const float* const* esrc,
+                                             const float* fsrc, const float* csrc, GetTile get) const {
+        if (dbl) {
+            if (t_begin < t_end) issue(tp, get(t_begin), 0, esrc, fsrc, csrc);
+            cp_async_commit();
+        }
+    }
+    __device__ __forceinline__ float* edge(int b, int i) const { return base + b * per + i * kTile * F; }
+    __device__ __forceinline__ float* fib(int b) const { return base + b * per + NE * kTile * F; }
+    __device__ __forceinline__ float* cls(int b) const { return fib(b) + max_fib * PF; }
+    // enqueue the copies of tile t into buffer b (no commit: the caller may add more, then commits)
+    __device__ __forceinline__ void issue(const Topo& tp, const Tile& t, int b, const float* const* esrc,
+                                          const float* fsrc, const float* csrc) const {
+        const int* idx = (tp.layout != PFS_LAYOUT_DENSE && tp.eid) ? tp.eid + t.q0 : nullptr;
+        const long long row0 = idx ? 0 : t.q0;
+#pragma unroll
+        for (int i = 0; i < NE; ++i)
+            stage_rows<F, F>(edge(b, i), esrc[i] + (size_t)t.g * tp.E * F, row0, idx, t.ne);
+        if constexpr (PF > 0) stage_rows<PF, PF>(fib(b), fsrc + (size_t)t.g * tp.S * PF, t.fibre0, nullptr, t.nfib);
+        if constexpr (PC > 0) {
+            if (with_class) stage_rows<PC, PCP>(cls(b), csrc + (size_t)t.g * tp.T * PC, 0, nullptr, tp.T);
+        }
+    }
+};
+
+// rows out of shared memory (same vector widths as load_row, no read-only-cache hint)
+template <int N>
+__device__ __forceinline__ void lds_row(const float* p, float (&x)[N]) {
+    if constexpr (N % 4 == 0) {
+        const float4* q = reinterpret_cast<const float4*>(p);
+#pragma unroll
+        for (int i = 0; i < N / 4; ++i) {
+            const float4 v = q[i];
+            x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+        }
+    } else {
+        const float2* q = reinterpret_cast<const float2*>(p);
+#pragma unroll
+        for (int i = 0; i < N / 2; ++i) {
+            const float2 v = q[i];
+            x[2 * i] = v.x; x[2 * i + 1] = v.y;
+        }
+    }
+}
+template <int N>
+__device__ __forceinline__ void lds_add_row(const float* p, float (&x)[N]) {
+    if constexpr (N % 4 == 0) {
+        const float4* q = reinterpret_cast<const float4*>(p);
+#pragma unroll
+        for (int i = 0; i < N / 4; ++i) {
+            const float4 v = q[i];
+            x[4 * i] += v.x; x[4 * i + 1] += v.y; x[4 * i + 2] += v.z; x[4 * i + 3] += v.w;
+        }
+    } else {
+        const float2* q = reinterpret_cast<const float2*>(p);
+#pragma unroll
+        for (int i = 0; i < N / 2; ++i) {
+            const float2 v = q[i];
+            x[2 * i] += v.x; x[2 * i + 1] += v.y;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// weights through the uniform datapath: the small MLP weights are warp-uniform operands, so they
+// live in __constant__ memory (packed input-major by k_pack_weights, copied with
+// cudaMemcpyToSymbolAsync on the launch stream) and reach the FMAs as LDCU.128 -> uniform
+// registers -> FFMA R, R, UR, R.  Nothing is replicated per lane, so the shared-memory return
+// path (128 B/clk/SM, 4 clk per broadcast LDS.128) no longer caps the FMA pipe at ~25 %.
+// ------------------------------------------------------------------------------------------
+constexpr int kConstFloats = 15360;   // 60 KB of the 64 KB constant bank
+__constant__ __align__(16) float c_w[kConstFloats];
+
+// y[j] += sum_k c_w[OFF + k * J + j] * x[k]   (J even; packed FFMA2 R, R.F32, UR.F32x2, R)
+template <int K, int J, int OFF>
+__device__ __forceinline__ void dense_acc_c(const float (&x)[K], float (&y)[J]) {
+    static_assert(J % 2 == 0 && OFF % 2 == 0, "pairs of outputs");
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const float2 xx = make_float2(x[k], x[k]);
+#pragma unroll
+        for (int j = 0; j < J; j += 2) {
+            const float2 a = __ffma2_rn(make_float2(c_w[OFF + k * J + j], c_w[OFF + k * J + j + 1]), xx,
+                                        make_float2(y[j], y[j + 1]));
+            y[j] = a.x;
+            y[j + 1] = a.y;
+        }
+    }
+}
+
+// packs dst[k * J + j] = W[j * ld + koff + k] (input-major) or dst[j * K + k] (output-major)
+struct PackItem {
+    const float* W;
+    int ld, koff, K, J, transpose, dst_off;   // K inputs, J outputs
+};
+constexpr int kMaxPack = 8;
+struct PackList {
+    PackItem it[kMaxPack];
+    int n;
+};
+__global__ void k_pack_weights(const PackList pl, float* __restrict__ dst) {
+    for (int q = 0; q < pl.n; ++q) {
+        const PackItem& it = pl.it[q];
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < it.J * it.K; i += gridDim.x * blockDim.x) {
+            const int j = i / it.K, k = i - j * it.K;
+            const float v = __ldg(it.W + (size_t)j * it.ld + it.koff + k);
+            dst[it.dst_off + (it.transpose ? k * it.J + j : j * it.K + k)] = v;
         }
     }
 }
@@ -257,6 +453,101 @@ __device__ __forceinline__ void tile_bn_partial(const float (&z)[N], bool active
 __host__ __device__ constexpr int bn_partial_stride(int N) { return 2 * N + 2; }
 
 // ------------------------------------------------------------------------------------------
+// contiguous tile ranges: CTA c of n owns tiles [c * total / n, (c + 1) * total / n).  A CTA then
+// crosses only a few graph boundaries, so per-graph statistics can ride in registers and be
+// reduced once per graph segment instead of once per tile.
+// ------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ int chunk_begin(int cta, int ncta, int total) {
+    return (int)((long long)cta * total / ncta);
+}
+// records a CTA can emit: graph segments its chunk can touch
+__host__ __device__ __forceinline__ int chunk_records(int ncta, int total, int tiles_per_graph) {
+    const int chunk = (total + ncta - 1) / ncta;
+    return (chunk + tiles_per_graph - 1) / tiles_per_graph + 1;
+}
+
+// Running BatchNorm statistics of the rows a thread has seen (shifted by its first row, so the
+// single-pass sums do not cancel), flushed once per graph segment into a record
+// {mean[N], M2[N], count, graph}: Chan-combined over the warp by a fixed shuffle tree, then
+// over the warps in order.  `red` is shared scratch of kWarps * (2N + 1) floats.
+template <int N>
+struct RunningStats {
+    float z0[N], s1[N], s2[N];
+    int n;
+    __device__ __forceinline__ void reset() {
+        n = 0;
+#pragma unroll
+        for (int j = 0; j < N; ++j) z0[j] = s1[j] = s2[j] = 0.f;
+    }
+    __device__ __forceinline__ void add(const float (&z)[N]) {
+        if (n == 0) {
+#pragma unroll
+            for (int j = 0; j < N; ++j) z0[j] = z[j];
+        }
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            const float d = z[j] - z0[j];
+            s1[j] += d;
+            s2[j] = fmaf(d, d, s2[j]);
+        }
+        ++n;
+    }
+    // all threads of the CTA call flush(); writes one record and resets
+    __device__ __forceinline__ void flush(float* red, float* __restrict__ rec, int graph) {
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        float cnt = (float)n;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            float c = cnt;
+            float mean = n > 0 ? z0[j] + s1[j] / cnt : 0.f;
+            float m2 = n > 0 ? fmaxf(s2[j] - s1[j] * s1[j] / cnt, 0.f) : 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float cb = __shfl_xor_sync(0xffffffffu, c, o);
+                const float mb = __shfl_xor_sync(0xffffffffu, mean, o);
+                const float qb = __shfl_xor_sync(0xffffffffu, m2, o);
+                const float tot = c + cb;
+                if (tot > 0.f) {
+                    const float delta = mb - mean, fb = cb / tot;
+                    mean = fmaf(delta, fb, mean);
+                    m2 = m2 + qb + delta * delta * c * fb;
+                }
+                c = tot;
+            }
+            if (lane == 0) {
+                red[w * (2 * N + 1) + j] = mean;
+                red[w * (2 * N + 1) + N + j] = m2;
+                if (j == 0) red[w * (2 * N + 1) + 2 * N] = c;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < N) {
+            const int j = threadIdx.x;
+            float c = 0.f, mean = 0.f, m2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < kWarps; ++i) {
+                const float cb = red[i * (2 * N + 1) + 2 * N];
+                const float tot = c + cb;
+                if (cb > 0.f) {
+                    const float delta = red[i * (2 * N + 1) + j] - mean, fb = cb / tot;
+                    mean = fmaf(delta, fb, mean);
+                    m2 = m2 + red[i * (2 * N + 1) + N + j] + delta * delta * c * fb;
+                }
+                c = tot;
+            }
+            rec[j] = mean;
+            rec[N + j] = m2;
+            if (j == 0) {
+                rec[2 * N] = c;
+                rec[2 * N + 1] = (float)graph;
+            }
+        }
+        __syncthreads();
+        reset();
+    }
+};
+
+// ------------------------------------------------------------------------------------------
 // outer-product accumulation  dW[J][K] += sum_r D[r][0..J) (x) X[r][0..K)
 // D and X are shared-memory tiles with leading dimensions ldD / ldX.  The J x K result is
 // register-blocked TJ x TK per thread; rows are split over `groups` thread groups and the
@@ -286,20 +577,63 @@ struct OuterAcc {
 #pragma unroll
             for (int c = 0; c < TK; ++c) acc[a][c] = 0.f;
     }
-    __device__ __forceinline__ void accumulate(const float* D, int ldD, const float* X, int ldX, int rows) {
-        if (!live) return;
-        for (int r = grp; r < rows; r += GROUPS) {
-            float d[TJ], x[TK];
-            const float* dp = D + r * ldD + j0;
-            const float* xp = X + r * ldX + k0;
+    __device__ __forceinline__ void fma_row(const float (&d)[TJ], const float (&x)[TK]) {
+        if constexpr (TJ % 2 == 0) {
+            // packed FFMA2 over row pairs (a, a+1), x[c] broadcast
 #pragma unroll
-            for (int a = 0; a < TJ; ++a) d[a] = dp[a];
+            for (int a = 0; a < TJ; a += 2)
 #pragma unroll
-            for (int c = 0; c < TK; ++c) x[c] = xp[c];
+                for (int c = 0; c < TK; ++c) {
+                    const float2 v = __ffma2_rn(make_float2(d[a], d[a + 1]), make_float2(x[c], x[c]),
+                                                make_float2(acc[a][c], acc[a + 1][c]));
+                    acc[a][c] = v.x;
+                    acc[a + 1][c] = v.y;
+                }
+        } else {
 #pragma unroll
             for (int a = 0; a < TJ; ++a)
 #pragma unroll
                 for (int c = 0; c < TK; ++c) acc[a][c] = fmaf(d[a], x[c], acc[a][c]);
+        }
+    }
+    template <int N>
+    static __device__ __forceinline__ void load_vec_smem(const float* p, float (&v)[N]) {
+        // widest aligned loads the address allows (p's alignment is uniform over the loop)
+        if ((N % 4 == 0) && ((((uintptr_t)p) & 15) == 0)) {
+#pragma unroll
+            for (int i = 0; i < N / 4; ++i) {
+                const float4 t = reinterpret_cast<const float4*>(p)[i];
+                v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+            }
+        } else if ((N % 2 == 0) && ((((uintptr_t)p) & 7) == 0)) {
+#pragma unroll
+            for (int i = 0; i < N / 2; ++i) {
+                const float2 t = reinterpret_cast<const float2*>(p)[i];
+                v[2 * i] = t.x; v[2 * i + 1] = t.y;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < N; ++i) v[i] = p[i];
+        }
+    }
+    // two rows per iteration: both rows' loads are in flight before the first FMA needs them
+    __device__ __forceinline__ void accumulate(const float* D, int ldD, const float* X, int ldX, int rows) {
+        if (!live) return;
+        int r = grp;
+        for (; r + GROUPS < rows; r += 2 * GROUPS) {
+            float d0[TJ], x0[TK], d1[TJ], x1[TK];
+            load_vec_smem<TJ>(D + r * ldD + j0, d0);
+            load_vec_smem<TK>(X + r * ldX + k0, x0);
+            load_vec_smem<TJ>(D + (r + GROUPS) * ldD + j0, d1);
+            load_vec_smem<TK>(X + (r + GROUPS) * ldX + k0, x1);
+            fma_row(d0, x0);
+            fma_row(d1, x1);
+        }
+        if (r < rows) {
+            float d0[TJ], x0[TK];
+            load_vec_smem<TJ>(D + r * ldD + j0, d0);
+            load_vec_smem<TK>(X + r * ldX + k0, x0);
+            fma_row(d0, x0);
         }
     }
     // Sums the groups through `scratch` (kScratchFloats floats of shared memory, may alias the

@@ -19,44 +19,63 @@ struct EdgeFwdParams {
     const float* w2;    // [F,4F]
     const float* b2;    // [F]
     float* z_out;       // [G,E,F]
-    float* bn_partial;  // [G,ntiles,2F+2] or null
+    float* bn_partial;  // [ncta,nrec,2F+2] statistics records, or null
+    int max_fib;        // most fibres a tile can hold (sizes the staging buffers)
+    int stage_class;    // 1: the class table P_t is staged in shared memory too
+    int nrec;           // statistics records per CTA (chunk_records)
+    int nbuf;           // staging buffers (2 = prefetch the next tile)
 };
 
 template <int F>
-__global__ void __launch_bounds__(kThreads) k_edge_fwd(const EdgeFwdParams p) {
+__global__ void __launch_bounds__(kThreads, 2) k_edge_fwd(const EdgeFwdParams p) {
     constexpr int H = 4 * F;
-    __shared__ __align__(16) float W1t[F * H];   // [k<F][j<H]
-    __shared__ __align__(16) float W2t[H * F];   // [k<H][j<F]
-    __shared__ float b2s[F];
-    __shared__ float red[(kWarps + 1) * F];
-    load_w_inmajor<F, H>(W1t, p.w1, H, 2 * F);
-    load_w_inmajor<H, F>(W2t, p.w2, H, 0);
-    load_vec<F>(b2s, p.b2);
-    __syncthreads();
+    using Stage = TileStage<F, 1, H, H>;
+    // constant-memory layout written by edge_fwd_impl: W1_e input-major [F][H], W2 input-major [H][F], b2 [F]
+    constexpr int kW1 = 0, kW2 = F * H, kB2 = 2 * F * H;
+    __shared__ float red[kWarps * (2 * F + 1)];
+    extern __shared__ __align__(16) float dyn[];
     const Topo& tp = p.tp;
+    Stage stg;
+    stg.init(dyn, p.max_fib, tp.T, p.stage_class != 0, p.nbuf);
+    const float* esrc[1] = {p.x_e};
+    auto tile_of = [&](int i) { return get_tile(tp, i); };
     const int total = tp.ntiles * tp.G;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const int t_begin = chunk_begin(blockIdx.x, gridDim.x, total), t_end = chunk_begin(blockIdx.x + 1, gridDim.x, total);
+    RunningStats<F> rs;
+    rs.reset();
+    float* rec = p.bn_partial ? p.bn_partial + (size_t)blockIdx.x * p.nrec * bn_partial_stride(F) : nullptr;
+    int slot = 0, cur_graph = -1, par = 0;
+    stg.prologue(tp, t_begin, t_end, esrc, p.Ps, p.Pt, tile_of);
+    for (int tile = t_begin; tile < t_end; ++tile, par ^= 1) {
         const Tile t = get_tile(tp, tile);
-        const bool active = threadIdx.x < t.ne;
-        float z[F];
-#pragma unroll
-        for (int j = 0; j < F; ++j) z[j] = 0.f;
-        if (active) {
+        const int b = stg.step(tp, tile, t_end, par, esrc, p.Ps, p.Pt, tile_of);   // this tile's copies have landed
+        if (rec && t.g != cur_graph) {   // graph boundary: emit the finished graph's statistics
+            if (cur_graph >= 0) rs.flush(red, rec + (size_t)(slot++) * bn_partial_stride(F), cur_graph);
+            cur_graph = t.g;
+        }
+        __syncthreads();
+        if (threadIdx.x < t.ne) {
             const EdgeRef er = get_edge(tp, t, threadIdx.x);
-            float x[F], h[H];
-            load_row<F>(p.x_e + ((size_t)t.g * tp.E + er.e) * F, x);
-            load_row<H>(p.Ps + ((size_t)t.g * tp.S + er.src) * H, h);
-            add_row<H>(p.Pt + ((size_t)t.g * tp.T + er.tgt) * H, h);
-            dense_acc<F, H>(W1t, x, h);
+            float x[F], h[H], z[F];
+            lds_row<F>(stg.edge(b, 0) + threadIdx.x * F, x);
+            lds_row<H>(stg.fib(b) + (er.src - t.fibre0) * H, h);
+            if (p.stage_class) lds_add_row<H>(stg.cls(b) + er.tgt * Stage::PCP, h);
+            else add_row<H>(p.Pt + ((size_t)t.g * tp.T + er.tgt) * H, h);
+            dense_acc_c<F, H, kW1>(x, h);
 #pragma unroll
             for (int j = 0; j < H; ++j) h[j] = lrelu(h[j]);
 #pragma unroll
-            for (int j = 0; j < F; ++j) z[j] = b2s[j];
-            dense_acc<H, F>(W2t, h, z);
+            for (int j = 0; j < F; ++j) z[j] = c_w[kB2 + j];
+            dense_acc_c<H, F, kW2>(h, z);
             store_row<F>(p.z_out + ((size_t)t.g * tp.E + er.e) * F, z);
+            if (rec) rs.add(z);
         }
-        if (p.bn_partial)
-            tile_bn_partial<F>(z, active, t.ne, red, p.bn_partial + (size_t)tile * bn_partial_stride(F));
+        __syncthreads();     // the staging buffer is refilled two iterations later
+    }
+    if (rec) {
+        if (cur_graph >= 0) rs.flush(red, rec + (size_t)(slot++) * bn_partial_stride(F), cur_graph);
+        for (; slot < p.nrec; ++slot)      // unused records: count 0
+            if (threadIdx.x == 0) rec[(size_t)slot * bn_partial_stride(F) + 2 * F] = 0.f;
     }
 }
 
@@ -185,7 +204,6 @@ struct EdgeBwdParams {
     Topo tp;
     const float *x_e, *xe2, *gout;   // [G,E,F]
     const float *Ps, *Pt;            // [G,S,4F], [G,T,4F]
-    const float *w1, *w2;            // [4F,4F], [F,4F]
     const float* coef;               // [G,6,F]
     float* g_x_e;                    // [G,E,F]
     float* dPs;                      // [G,S,4F] fibre sums of dh
@@ -193,6 +211,15 @@ struct EdgeBwdParams {
     float* dh_rows;                  // general: [G,E(q),4F]
     float* wpartial;                 // [ncta][pstride]: dW1_e [4F*F], dW2 [F*4F], db2 [F]
     int pstride;
+    int max_fib, stage_class, nbuf;
+};
+
+// constant-bank layout of the edge backward (floats): W1_e input-major [F][H] (recompute h),
+// W2 as stored [F][H] (da_k += W2[j][k] dz_j), W1_e as stored [H][F] (dx_k += W1[j][2F+k] dh_j)
+template <int F>
+struct EdgeBwdConst {
+    static constexpr int H = 4 * F;
+    static constexpr int kW1t = 0, kW2o = F * H, kW1o = 2 * F * H, kFloats = 3 * F * H;
 };
 
 template <int F>
@@ -200,70 +227,73 @@ struct EdgeBwdSmem {
     static constexpr int H = 4 * F;
     static constexpr int LDH = H + 4;   // 16-byte aligned rows, bank-staggered
     static constexpr int LDF = F + 2;
-    static constexpr int kWeights = 3 * F * H;
-    static constexpr int kTiles = kTile * (2 * LDH + 2 * LDF);
-    static constexpr size_t bytes = sizeof(float) * (kWeights + kTiles);
+    using Stage = TileStage<F, 3, H, H>;
+    using AccW1 = OuterAcc<H, F, 8, F / 2, 0, kThreads / 2>;              // dW1_e[j][k] = sum dh_j x_k
+    using AccW2 = OuterAcc<F, H, 2, 2 * F, kThreads / 2, kThreads / 2>;   // dW2[j][k]   = sum dz_j a1_k
+    static constexpr int kTiles = kTile * (2 * LDH + LDF);
+    static size_t bytes(int max_fib, int T, bool with_class, int nbuf) {
+        return sizeof(float) * ((size_t)kTiles + Stage::floats(max_fib, T, with_class, nbuf));
+    }
 };
 
 template <int F>
 __global__ void __launch_bounds__(kThreads) k_edge_bwd(const EdgeBwdParams p) {
     constexpr int H = 4 * F;
     using SM = EdgeBwdSmem<F>;
+    using CW = EdgeBwdConst<F>;
+    using Stage = typename SM::Stage;
     constexpr int LDH = SM::LDH, LDF = SM::LDF;
     extern __shared__ __align__(16) float sm[];
-    float* W1t = sm;                 // [k<F][j<H]   forward layer 1 (edge columns)
-    float* W2o = W1t + F * H;        // [j<F][k<H]   backward through layer 2: da_k += W2[j][k] dz_j
-    float* W1o = W2o + F * H;        // [j<H][k<F]   backward through layer 1: dx_k += W1[j][2F+k] dh_j
-    float* DH = W1o + F * H;         // [kTile][LDH]
+    float* DH = sm;                  // [kTile][LDH]
     float* A1 = DH + kTile * LDH;    // [kTile][LDH]
     float* DZ = A1 + kTile * LDH;    // [kTile][LDF]
-    float* XE = DZ + kTile * LDF;    // [kTile][LDF]
-    load_w_inmajor<F, H>(W1t, p.w1, H, 2 * F);
-    load_w_outmajor<H, F>(W2o, p.w2, H, 0);
-    load_w_outmajor<F, H>(W1o, p.w1, H, 2 * F);
-    __syncthreads();
+    const Topo& tp = p.tp;
+    Stage stg;
+    stg.init(DZ + kTile * LDF, p.max_fib, tp.T, p.stage_class != 0, p.nbuf);
+    auto tile_of = [&](int i) { return get_tile(tp, i); };
     // the two weight-gradient accumulations run side by side on the two halves of the CTA
-    using AccW1 = OuterAcc<H, F, 8, F / 2, 0, kThreads / 2>;              // dW1_e[j][k] = sum dh_j x_k
-    using AccW2 = OuterAcc<F, H, F / 2, 8, kThreads / 2, kThreads / 2>;   // dW2[j][k]   = sum dz_j a1_k
-    AccW1 accw1;
-    AccW2 accw2;
+    typename SM::AccW1 accw1;
+    typename SM::AccW2 accw2;
     accw1.init();
     accw2.init();
     float dzsum[F];
 #pragma unroll
     for (int j = 0; j < F; ++j) dzsum[j] = 0.f;
-
-    const Topo& tp = p.tp;
+    const float* esrc[3] = {p.x_e, p.xe2, p.gout};
     const int total = tp.ntiles * tp.G;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const int t_begin = chunk_begin(blockIdx.x, gridDim.x, total), t_end = chunk_begin(blockIdx.x + 1, gridDim.x, total);
+    int par = 0;
+    stg.prologue(tp, t_begin, t_end, esrc, p.Ps, p.Pt, tile_of);
+    for (int tile = t_begin; tile < t_end; ++tile, par ^= 1) {
         const Tile t = get_tile(tp, tile);
-        const bool active = threadIdx.x < t.ne;
-        if (active) {
+        const int b = stg.step(tp, tile, t_end, par, esrc, p.Ps, p.Pt, tile_of);
+        __syncthreads();
+        const float* XE = stg.edge(b, 0);
+        if (threadIdx.x < t.ne) {
             const EdgeRef er = get_edge(tp, t, threadIdx.x);
-            const size_t row = ((size_t)t.g * tp.E + er.e) * F;
             float x[F], h[H], dz[F];
-            load_row<F>(p.x_e + row, x);
-            load_row<H>(p.Ps + ((size_t)t.g * tp.S + er.src) * H, h);
-            add_row<H>(p.Pt + ((size_t)t.g * tp.T + er.tgt) * H, h);
-            dense_acc<F, H>(W1t, x, h);
+            lds_row<F>(XE + threadIdx.x * F, x);
+            lds_row<H>(stg.fib(b) + (er.src - t.fibre0) * H, h);
+            if (p.stage_class) lds_add_row<H>(stg.cls(b) + er.tgt * Stage::PCP, h);
+            else add_row<H>(p.Pt + ((size_t)t.g * tp.T + er.tgt) * H, h);
+            dense_acc_c<F, H, CW::kW1t>(x, h);
             {
                 float gr[F], xo[F];
-                load_row<F>(p.gout + row, gr);
-                load_row<F>(p.xe2 + row, xo);
+                lds_row<F>(stg.edge(b, 2) + threadIdx.x * F, gr);
+                lds_row<F>(stg.edge(b, 1) + threadIdx.x * F, xo);
                 const float* c = p.coef + (size_t)t.g * 6 * F;
 #pragma unroll
                 for (int j = 0; j < F; ++j) {
-                    const float xh = (xo[j] - c[4 * F + j]) * c[3 * F + j];
-                    dz[j] = c[j] * (gr[j] - c[F + j] - xh * c[2 * F + j]);
+                    const float xh = (xo[j] - __ldg(c + 4 * F + j)) * __ldg(c + 3 * F + j);
+                    dz[j] = __ldg(c + j) * (gr[j] - __ldg(c + F + j) - xh * __ldg(c + 2 * F + j));
                     dzsum[j] += dz[j];
                 }
             }
             float da[H];
 #pragma unroll
             for (int k = 0; k < H; ++k) da[k] = 0.f;
-            dense_acc<F, H>(W2o, dz, da);
+            dense_acc_c<F, H, CW::kW2o>(dz, da);
             store_row_smem<F>(DZ + threadIdx.x * LDF, dz);
-            store_row_smem<F>(XE + threadIdx.x * LDF, x);
 #pragma unroll
             for (int k = 0; k < H; ++k) {
                 da[k] *= dlrelu(h[k]);      // dh
@@ -274,12 +304,12 @@ __global__ void __launch_bounds__(kThreads) k_edge_bwd(const EdgeBwdParams p) {
             float dx[F];
 #pragma unroll
             for (int k = 0; k < F; ++k) dx[k] = 0.f;
-            dense_acc<H, F>(W1o, da, dx);
-            store_row<F>(p.g_x_e + row, dx);
+            dense_acc_c<H, F, CW::kW1o>(da, dx);
+            store_row<F>(p.g_x_e + ((size_t)t.g * tp.E + er.e) * F, dx);
             if (p.dh_rows) store_row<H>(p.dh_rows + ((size_t)t.g * tp.E + t.q0 + threadIdx.x) * H, da);
         }
         __syncthreads();
-        accw1.accumulate(DH, LDH, XE, LDF, t.ne);
+        accw1.accumulate(DH, LDH, XE, F, t.ne);
         accw2.accumulate(DZ, LDF, A1, LDH, t.ne);
         // fibre sums of dh -> dPs
         for (int i = threadIdx.x; i < t.nfib * H; i += kThreads) {
@@ -302,6 +332,7 @@ __global__ void __launch_bounds__(kThreads) k_edge_bwd(const EdgeBwdParams p) {
         }
         __syncthreads();
     }
+    cp_async_wait<0>();
     float* out = p.wpartial + (size_t)blockIdx.x * p.pstride;
     accw1.flush(DH, out, F, 0);
     accw2.flush(DH, out + H * F, H, 0);

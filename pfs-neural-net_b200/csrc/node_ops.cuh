@@ -238,6 +238,49 @@ __global__ void k_bn_finalize(const float* __restrict__ partial, int ntiles, int
     s[3 * F + f] = (float)shift;
 }
 
+// same, from the per-CTA graph-segment records of the chunked edge kernels:
+// partial[cta][rec] = {mean[F], M2[F], count, graph}; CTA c owns tiles [c*total/ncta, (c+1)*total/ncta)
+__global__ void k_bn_finalize_rec(const float* __restrict__ partial, int ncta, int nrec, int tiles_per_graph, int F,
+                                  int G, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                  int twice, float* __restrict__ save) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= G * F) return;
+    const int g = i / F, f = i - g * F;
+    const long long total = (long long)tiles_per_graph * G;
+    long long c_lo = (long long)g * tiles_per_graph * ncta / total - 1;
+    long long c_hi = ((long long)(g + 1) * tiles_per_graph * ncta) / total + 1;
+    if (c_lo < 0) c_lo = 0;
+    if (c_hi > ncta - 1) c_hi = ncta - 1;
+    const int stride = 2 * F + 2;
+    double n = 0.0, mean = 0.0, m2 = 0.0;
+    for (long long c = c_lo; c <= c_hi; ++c)
+        for (int r = 0; r < nrec; ++r) {
+            const float* p = partial + ((size_t)c * nrec + r) * stride;
+            const double nb = p[2 * F];
+            if (nb <= 0.0 || (int)p[2 * F + 1] != g) continue;
+            const double mb = p[f], sb = p[F + f];
+            const double tot = n + nb, delta = mb - mean;
+            mean += delta * (nb / tot);
+            m2 += sb + delta * delta * (n * nb / tot);
+            n = tot;
+        }
+    const double var = n > 0 ? m2 / n : 0.0;
+    const double gm = gamma[f], bt = beta[f];
+    const double r1 = 1.0 / sqrt(var + (double)eps);
+    double scale;
+    if (twice) {
+        const double var2 = gm * gm * var * r1 * r1;
+        scale = gm * gm * r1 / sqrt(var2 + (double)eps);
+    } else {
+        scale = gm * r1;
+    }
+    float* s = save + (size_t)g * 4 * F;
+    s[f] = (float)mean;
+    s[F + f] = (float)var;
+    s[2 * F + f] = (float)scale;
+    s[3 * F + f] = (float)(bt - scale * mean);
+}
+
 // eval mode: coefficients from the running buffers (same for every graph)
 __global__ void k_bn_eval_coeffs(const float* __restrict__ rm, const float* __restrict__ rv, int F, int G,
                                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int twice,
@@ -262,43 +305,61 @@ __global__ void k_bn_eval_coeffs(const float* __restrict__ rm, const float* __re
     s[3 * F + f] = (float)shift;
 }
 
-// running buffers, graph after graph (what G sequential reference forwards would leave behind)
+// running buffers, graph after graph (what G sequential reference forwards would leave behind):
+// r_G = (1-m)^(kG) r_0 + sum_g (weights) -- a fixed-order weighted sum, one warp per feature.
 __global__ void k_bn_running(const float* __restrict__ save, int F, int G, long long n_rows,
                              const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                              float momentum, int twice, float* __restrict__ rm, float* __restrict__ rv,
                              long long* __restrict__ nbt) {
-    const int f = threadIdx.x;
-    if (f < F) {
-        double m = rm[f], v = rv[f];
-        const double mom = momentum, unb = (double)n_rows / (double)(n_rows - 1);
-        for (int g = 0; g < G; ++g) {
-            const double mean = save[(size_t)g * 4 * F + f], var = save[(size_t)g * 4 * F + F + f];
-            m = (1.0 - mom) * m + mom * mean;
-            v = (1.0 - mom) * v + mom * var * unb;
-            if (twice) {  // second application sees mean beta and variance gamma^2 var / (var + eps)
-                const double gm = gamma[f];
-                const double var2 = gm * gm * var / (var + (double)eps);
-                m = (1.0 - mom) * m + mom * (double)beta[f];
-                v = (1.0 - mom) * v + mom * var2 * unb;
-            }
+    const int f = blockIdx.x, lane = threadIdx.x;   // blockDim.x == 32
+    const double mom = momentum, keep = 1.0 - mom, unb = (double)n_rows / (double)(n_rows - 1);
+    const double step = twice ? keep * keep : keep;   // decay per graph
+    double am = 0.0, av = 0.0;
+    for (int g = lane; g < G; g += 32) {
+        const double mean = save[(size_t)g * 4 * F + f], var = save[(size_t)g * 4 * F + F + f];
+        double cm, cv;   // contribution of graph g right after its own update(s)
+        if (twice) {     // second application sees mean beta and variance gamma^2 var / (var + eps)
+            const double gm = gamma[f];
+            const double var2 = gm * gm * var / (var + (double)eps);
+            cm = keep * mom * mean + mom * (double)beta[f];
+            cv = keep * mom * var * unb + mom * var2 * unb;
+        } else {
+            cm = mom * mean;
+            cv = mom * var * unb;
         }
-        rm[f] = (float)m;
-        rv[f] = (float)v;
+        const double w = pow(step, (double)(G - 1 - g));
+        am += w * cm;
+        av += w * cv;
     }
-    if (f == 0 && nbt) *nbt += (long long)G * (twice ? 2 : 1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        am += __shfl_xor_sync(0xffffffffu, am, o);
+        av += __shfl_xor_sync(0xffffffffu, av, o);
+    }
+    if (lane == 0) {
+        const double d = pow(step, (double)G);
+        rm[f] = (float)(d * (double)rm[f] + am);
+        rv[f] = (float)(d * (double)rv[f] + av);
+        if (f == 0 && nbt) *nbt += (long long)G * (twice ? 2 : 1);
+    }
 }
 
-// out[g][r][f] = in[g][r][f] * scale[g][f] + shift[g][f]   (in place allowed)
+// out[g][r][f] = in[g][r][f] * scale[g][f] + shift[g][f]   (in place allowed); rows_f = rows * F (even)
 __global__ void k_affine_rows(const float* __restrict__ in, const float* __restrict__ save, int F, long long rows_f,
                               int G, float* __restrict__ out) {
-    // rows_f = rows_per_graph * F (elements per graph)
-    const long long total = rows_f * G;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const int g = (int)(i / rows_f);
-        const int f = (int)((i - (long long)g * rows_f) % F);
-        const float* s = save + (size_t)g * 4 * F;
-        out[i] = fmaf(in[i], s[2 * F + f], s[3 * F + f]);
+    // grid.y = graph; each thread handles float2 pairs of one graph
+    const int g = blockIdx.y;
+    const float* s = save + (size_t)g * 4 * F;
+    const float2* src = reinterpret_cast<const float2*>(in + (size_t)g * rows_f);
+    float2* dst = reinterpret_cast<float2*>(out + (size_t)g * rows_f);
+    const long long n2 = rows_f / 2;
+    const int half = F / 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+        const int f = 2 * (int)(i % half);
+        float2 v = src[i];
+        v.x = fmaf(v.x, s[2 * F + f], s[3 * F + f]);
+        v.y = fmaf(v.y, s[2 * F + f + 1], s[3 * F + f + 1]);
+        dst[i] = v;
     }
 }
 

@@ -275,7 +275,8 @@ struct SourceNodeBwdSmem {
     static constexpr int kNT3 = (F * F <= 224) ? 224 : kThreads;
     static constexpr int kT04 = (F * F <= 224) ? 224 : 0;
     using AccW3 = OuterAcc<J, K9, 10, 9, 0, kNT3>;
-    using AccW4 = OuterAcc<F, J, F / 2, 10, kT04, 32>;
+    static constexpr int kNT4 = ((F / 2) * 5 <= 32) ? 32 : 64;
+    using AccW4 = OuterAcc<F, J, 2, 2 * F, kT04, kNT4>;
     static constexpr int kRows = node_rows<F>() * (LDH + 2 * LDA + LDY);
     static constexpr int kScr = AccW3::kScratchFloats > AccW4::kScratchFloats ? AccW3::kScratchFloats : AccW4::kScratchFloats;
     // the row buffers double as the cross-group scratch of the weight-gradient flush
@@ -500,8 +501,8 @@ __global__ void __launch_bounds__(kThreads) k_source_edge_bwd(const SourceEdgeBw
     load_w_outmajor<F, M>(W1o, p.w1, M, F);
     load_vec<M>(b2s, p.b2);
     __syncthreads();
-    using AccW2 = OuterAcc<M, M, F / 2, F / 2, 0, 160>;        // dW2[j][k]   = sum dm_j as_k
-    using AccW1 = OuterAcc<M, F, F / 2, F / 2, 160, 96>;       // dW1_e[j][k] = sum dhs_j x_k
+    using AccW2 = OuterAcc<M, M, 4, F / 2, 0, 160>;            // dW2[j][k]   = sum dm_j as_k
+    using AccW1 = OuterAcc<M, F, 4, F / 2, 160, 96>;           // dW1_e[j][k] = sum dhs_j x_k
     AccW2 accw2;
     AccW1 accw1;
     accw2.init();

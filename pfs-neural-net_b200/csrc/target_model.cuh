@@ -338,7 +338,7 @@ struct TargetEdgeBwdParams {
 template <int F>
 struct TargetEdgeBwdSmem {
     static constexpr int M = 2 * F, LDM = M + 4, LDF = F + 2;
-    using AccW1 = OuterAcc<M, F, F / 2, F / 2>;
+    using AccW1 = OuterAcc<M, F, 4, F / 2>;
     static constexpr int kTiles = kTile * (LDM + LDF);
     // the tile region doubles as the cross-group scratch of the weight-gradient flush
     static constexpr int kRegion = kTiles > AccW1::kScratchFloats ? kTiles : AccW1::kScratchFloats;
@@ -632,7 +632,7 @@ __global__ void __launch_bounds__(kThreads) k_head_bwd(const HeadParams p) {
     __shared__ __align__(16) float W1t[F * F];
     __shared__ __align__(16) float W1o[F * F];
     __shared__ float b1s[F], w2s[F];
-    using AccW1 = OuterAcc<F, F, F / 2, F / 2, 0, 128>;
+    using AccW1 = OuterAcc<F, F, 2, F / 2, 0, 128>;
     // one region: the two staging tiles, reused as the flush scratch and the final reduction buffer
     constexpr int kRegion = (2 * kTile * LDF > AccW1::kScratchFloats) ? 2 * kTile * LDF : AccW1::kScratchFloats;
     __shared__ float REGION[kRegion];

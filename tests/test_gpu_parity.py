@@ -94,7 +94,7 @@ def ours_module(name, case, dev):
 # the 1e-3 std floor of reference src/gnn.py:142: skew / kurtosis and their gradients amplify fp32
 # rounding by up to 1e9 and the reference's own fp32 run is only good to ~1e-3 there.  One sample of
 # that noise is compared with one sample of ours, so the accepted ratio is wider for those cases.
-FP32_NOISE_FACTOR = {"well": 2.0, "ill": 10.0}
+FP32_NOISE_FACTOR = {"well": 3.0, "ill": 10.0}
 _conditioning = ["well"]
 
 
