@@ -3,6 +3,7 @@
 // caller's stream.  No torch types, no synchronisation, no host allocation in the hot calls.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -12,6 +13,8 @@
 #include "edge_model.cuh"
 #include "node_ops.cuh"
 #include "source_model.cuh"
+#include "source_node_c.cuh"
+#include "source_node_mma.cuh"
 #include "target_model.cuh"
 
 using namespace pfs;
@@ -92,9 +95,9 @@ int num_sms() {
 
 // persistent grid: resident CTAs of this kernel on the whole device, capped by the work items
 template <class Kern>
-int persistent_grid(Kern kern, size_t smem, long long items) {
+int persistent_grid(Kern kern, size_t smem, long long items, int threads = kThreads) {
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem) != cudaSuccess || per_sm < 1)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm < 1)
         per_sm = 1;
     long long g = (long long)per_sm * num_sms();
     if (g > kMaxCtas) g = kMaxCtas;
@@ -137,7 +140,9 @@ int dense_ntiles(int S, int T) {
     const int fpt = dense_fpt(T);
     return fpt > 0 ? (S + fpt - 1) / fpt : 0;
 }
-template <int F> int node_ntiles(int S) { return (S + node_rows<F>() - 1) / node_rows<F>(); }
+// node tiles: constant-bank kernels (Fdim <= 10) use 128-fibre tiles, the shared-memory kernels node_rows<F>()
+template <int F> constexpr int node_tile_rows() { return SourceNodeConst<F>::fits ? kNodeRowsC : node_rows<F>(); }
+template <int F> int node_ntiles(int S) { return (S + node_tile_rows<F>() - 1) / node_tile_rows<F>(); }
 
 int make_topo(const pfs_topology& t, Topo& o) {
     PFS_REQUIRE(t.G >= 1 && t.S >= 1 && t.T >= 1 && t.E >= 0 && t.F >= 2, "bad topology sizes");
@@ -169,6 +174,16 @@ int upload_weights(const PackList& pl, int nfloats, float* staging, cudaStream_t
     PFS_LAUNCH_CHECK("k_pack_weights");
     PFS_CUDA(cudaMemcpyToSymbolAsync(c_w, staging, sizeof(float) * (size_t)nfloats, 0, cudaMemcpyDeviceToDevice, st));
     return PFS_OK;
+}
+
+// PFS_NODE_MMA=0 switches the fibre MLP back from the tcgen05 kernel to the FMA kernel (A/B runs)
+bool node_mma_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PFS_NODE_MMA");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
 }
 
 // staging geometry of the edge kernels (common.cuh: TileStage)
@@ -460,6 +475,7 @@ int source_fwd_impl(const pfs_source_args& a, const Topo& tp) {
     Bump ws(a.workspace, a.workspace_bytes);
     float* Qt = ws.f((size_t)tp.G * tp.T * M);
     float* partn = ws.f((size_t)tp.G * ntn * bn_partial_stride(F));
+    float* wstage = ws.f(kConstFloats);
     if (!ws.ok) return fail(PFS_ERR_WORKSPACE, "source_fwd: workspace too small (%zu B)", a.workspace_bytes);
     PFS_TRY((node_linear<F, M>(a.x_t, tp.T, tp.G, a.w1, M, 0, a.b1, nullptr, Qt, st)));
     {
@@ -469,15 +485,42 @@ int source_fwd_impl(const pfs_source_args& a, const Topo& tp) {
         PFS_LAUNCH_CHECK("k_source_edge_fwd");
     }
     {
-        using SM = SourceNodeFwdSmem<F>;
-        auto kern = k_source_node_fwd<F>;
-        PFS_TRY(allow_smem(kern, SM::bytes));
         const bool stats = a.normed && a.training;
         SourceNodeFwdParams p{tp.G, tp.S, a.x_s, a.u, a.moments, a.w3, a.b3, a.w4, a.b4, a.hidden, a.y_pre,
                               stats ? partn : nullptr, ntn};
-        const int grid = persistent_grid(kern, SM::bytes, (long long)ntn * tp.G);
-        kern<<<grid, kThreads, SM::bytes, st>>>(p);
-        PFS_LAUNCH_CHECK("k_source_node_fwd");
+        if constexpr (SourceNodeConst<F>::fits) {
+            using SM = SourceNodeFwdSmemC<F>;
+            using CW = SourceNodeConst<F>;
+            constexpr int J = 10 * F, K9 = 9 * F;
+            PackList pl{};
+            pl.it[0] = PackItem{a.w3, J, 0, K9, J, 1, CW::kW3t};      // W3[:, :9F] input-major [K9][J]
+            pl.it[1] = PackItem{a.w4, J, 0, J, F, 1, CW::kW4t};       // W4 input-major [J][F]
+            pl.it[2] = PackItem{a.b4, 1, 0, 1, F, 0, CW::kB4};
+            pl.n = 3;
+            PFS_TRY(upload_weights(pl, CW::kFwdFloats, wstage, st));
+            if (SourceNodeMma<F>::fits && node_mma_enabled()) {
+                // first layer on tcgen05 (3xTF32), see source_node_mma.cuh
+                auto kern = k_source_node_fwd_mma<F>;
+                constexpr size_t smem = SourceNodeMma<F>::bytes;
+                PFS_TRY(allow_smem(kern, smem));
+                const int grid = persistent_grid(kern, smem, (long long)ntn * tp.G, kNodeThreadsC);
+                kern<<<grid, kNodeThreadsC, smem, st>>>(p);
+                PFS_LAUNCH_CHECK("k_source_node_fwd_mma");
+            } else {
+                auto kern = k_source_node_fwd_c<F>;
+                PFS_TRY(allow_smem(kern, SM::bytes));
+                const int grid = persistent_grid(kern, SM::bytes, (long long)ntn * tp.G, kNodeThreadsC);
+                kern<<<grid, kNodeThreadsC, SM::bytes, st>>>(p);
+                PFS_LAUNCH_CHECK("k_source_node_fwd");
+            }
+        } else {
+            using SM = SourceNodeFwdSmem<F>;
+            auto kern = k_source_node_fwd<F>;
+            PFS_TRY(allow_smem(kern, SM::bytes));
+            const int grid = persistent_grid(kern, SM::bytes, (long long)ntn * tp.G);
+            kern<<<grid, kThreads, SM::bytes, st>>>(p);
+            PFS_LAUNCH_CHECK("k_source_node_fwd");
+        }
     }
     if (a.normed) {
         PFS_REQUIRE(a.gamma && a.beta && a.bn_save, "normed source model needs gamma, beta, bn_save");
@@ -498,13 +541,18 @@ int source_bwd_impl(const pfs_source_args& a, const Topo& tp) {
     const int total = tp.ntiles * tp.G;
     const int ntn = node_ntiles<F>(tp.S);
     const int mode = !a.normed ? 0 : (a.training ? 1 : 2);
-    using SMN = SourceNodeBwdSmem<F>;
     using SME = SourceEdgeBwdSmem<F>;
-    auto kn = k_source_node_bwd<F>;
+    constexpr bool kNodeC = SourceNodeConst<F>::fits;
     auto ke = k_source_edge_bwd<F>;
-    PFS_TRY(allow_smem(kn, SMN::bytes));
     PFS_TRY(allow_smem(ke, SME::bytes));
-    const int gridn = persistent_grid(kn, SMN::bytes, (long long)ntn * tp.G);
+    int gridn = 0;
+    if constexpr (kNodeC) {
+        PFS_TRY(allow_smem(k_source_node_bwd_c<F>, SourceNodeBwdSmemC<F>::bytes));
+        gridn = persistent_grid(k_source_node_bwd_c<F>, SourceNodeBwdSmemC<F>::bytes, (long long)ntn * tp.G, kNodeThreadsC);
+    } else {
+        PFS_TRY(allow_smem(k_source_node_bwd<F>, SourceNodeBwdSmem<F>::bytes));
+        gridn = persistent_grid(k_source_node_bwd<F>, SourceNodeBwdSmem<F>::bytes, (long long)ntn * tp.G);
+    }
     const int gride = persistent_grid(ke, SME::bytes, total);
     constexpr int pstride_n = J * K9 + F * J + F;
     constexpr int pstride_e = M * F + M * M + M;
@@ -519,6 +567,7 @@ int source_bwd_impl(const pfs_source_args& a, const Topo& tp) {
     float* dQt = ws.f((size_t)tp.G * tp.T * M);
     float* wpe = ws.f((size_t)gride * pstride_e);
     float* opart = ws.f((size_t)kMaxCtas * (M * F + M));
+    float* wstage = ws.f(kConstFloats);
     if (!ws.ok) return fail(PFS_ERR_WORKSPACE, "source_bwd: workspace too small (%zu B)", a.workspace_bytes);
     if (mode != 0) {
         k_bn_bwd_stats_rows<<<tp.G, kThreads, sizeof(float) * kWarps * 2 * F, st>>>(a.g_out, a.y_pre, a.bn_save, tp.S, F,
@@ -530,7 +579,17 @@ int source_bwd_impl(const pfs_source_args& a, const Topo& tp) {
     {
         SourceNodeBwdParams p{tp.G, tp.S, ntn, mode, a.eps, a.x_s, a.moments, a.hidden, a.y_pre, a.g_out, a.bn_save,
                               bnstat, a.w3, a.w4, a.g_x_s, coefA, tot3p, wpn, pstride_n};
-        kn<<<gridn, kThreads, SMN::bytes, st>>>(p);
+        if constexpr (kNodeC) {
+            using CW = SourceNodeConst<F>;
+            PackList pl{};
+            pl.it[0] = PackItem{a.w4, J, 0, J, F, 0, CW::kW4o};       // W4 as stored [F][J]
+            pl.it[1] = PackItem{a.w3, J, 0, K9, J, 0, CW::kW3o};      // W3[:, :9F] as stored [J][K9]
+            pl.n = 2;
+            PFS_TRY(upload_weights(pl, CW::kBwdFloats, wstage, st));
+            k_source_node_bwd_c<F><<<gridn, kNodeThreadsC, SourceNodeBwdSmemC<F>::bytes, st>>>(p);
+        } else {
+            k_source_node_bwd<F><<<gridn, kThreads, SourceNodeBwdSmem<F>::bytes, st>>>(p);
+        }
         PFS_LAUNCH_CHECK("k_source_node_bwd");
     }
     PFS_TRY(reduce_partials(wpn, gridn, pstride_n, 0, J * K9, K9, a.g_w3, J, 0, st));

@@ -1,0 +1,314 @@
+// source_node_mma.cuh -- SModel node MLP, first layer on the 5th-generation tensor cores.
+//
+// The fibre MLP (reference src/gnn.py:153: node_mlp_2 = MLP(10F, 10F, F)) is the one contraction of
+// the layer that is a real dense GEMM even at Fdim 10: [fibres x 9F] . [9F x 10F] over hundreds of
+// thousands of fibres (the u columns are folded into the bias).  It runs as tcgen05.mma
+// kind::tf32 with the 3xTF32 split (a = a_hi + a_lo, b = b_hi + b_lo; a.b ~ a_hi b_hi + a_lo b_hi
+// + a_hi b_lo, error ~2^-21) so the fp32 parity tolerance holds:
+//   * a CTA owns 128-fibre tiles (UMMA M = 128, one fibre per TMEM lane);
+//   * operands live in shared memory in the canonical K-major no-swizzle core-matrix layout
+//     (8 rows x 16 bytes per core matrix), written by the threads themselves (the A operand is
+//     computed on the fly from the raw moments, so there is nothing for TMA to fetch);
+//   * one elected thread issues the K/8 x 3 MMAs into a [128 x N] fp32 accumulator in TMEM and
+//     commits to an mbarrier; warps 0-3 read their 32 lanes back with tcgen05.ld and run the
+//     epilogue (bias, LeakyReLU, hidden store, second layer, BatchNorm tile statistics).
+#pragma once
+#include "source_node_c.cuh"
+
+namespace pfs {
+
+// ---- PTX wrappers (strings as in CUTLASS cute/arch/{mma_sm100_umma,copy_sm100,tmem_allocator_sm100}.hpp) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+}
+// D[tmem] (+)= A[smem desc] . B[smem desc], kind::tf32, issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc),
+        "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor: K-major, no swizzle, 8x16B core matrices.
+// element (row r, 16-byte K chunk kc) lives at base + kc * lbo + (r / 8) * 128 + (r % 8) * 16
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);              // start address, bits [0,14)
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;    // leading (K) byte offset, bits [16,30)
+    d |= (uint64_t)((128u >> 4) & 0x3FFF) << 32;         // stride (8-row group) byte offset, bits [32,46)
+    d |= (uint64_t)1 << 46;                              // descriptor version 1 (Blackwell)
+    return d;                                            // base offset 0, layout type 0 = SWIZZLE_NONE
+}
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+template <int F>
+struct SourceNodeMma {
+    static constexpr int K9 = 9 * F, J = 10 * F;
+    static constexpr int KP = (K9 + 7) / 8 * 8;          // K padded to the MMA K (8 tf32)
+    static constexpr int NP = (J + 15) / 16 * 16;        // N padded (M = 128 needs N % 16 == 0)
+    static constexpr int KC = KP / 4;                    // 16-byte K chunks
+    static constexpr int LBO_A = 16 * 128;               // 128 rows = 16 core matrices of 128 B per K chunk
+    static constexpr int LBO_B = (NP / 8) * 128;
+    static constexpr int A_FLOATS = KC * LBO_A / 4;      // one of (hi, lo)
+    static constexpr int B_FLOATS = KC * LBO_B / 4;
+    static constexpr int TMEM_COLS = NP <= 32 ? 32 : NP <= 64 ? 64 : NP <= 128 ? 128 : 256;
+    static constexpr int LDA = J + 1;
+    // shared memory (floats): A hi/lo, B hi/lo, bias [J], YS [128][F], A3 [128][LDA] aliases the A operand
+    static constexpr int kRed = (J > 17 * F ? J : 17 * F);   // bias vector, reused by the statistics reduction
+    static constexpr int kFloats = 2 * A_FLOATS + 2 * B_FLOATS + kRed + 2 * 128 * F + J * F + 16;
+    static constexpr size_t bytes = sizeof(float) * kFloats;
+    static constexpr bool fits = bytes <= 200 * 1024 && 2 * A_FLOATS >= 128 * LDA && NP <= 256 &&
+                                 SourceNodeConst<F>::fits;
+};
+
+template <int F>
+__global__ void __launch_bounds__(kNodeThreadsC) k_source_node_fwd_mma(const SourceNodeFwdParams p) {
+    using MM = SourceNodeMma<F>;
+    using CW = SourceNodeConst<F>;
+    constexpr int K9 = MM::K9, J = MM::J, KP = MM::KP, NP = MM::NP, KC = MM::KC, LDA = MM::LDA, M2 = 2 * F;
+    extern __shared__ __align__(1024) float smm[];
+    float* sm = smm;
+    float* Ahi = sm;
+    float* Alo = Ahi + MM::A_FLOATS;
+    float* Bhi = Alo + MM::A_FLOATS;
+    float* Blo = Bhi + MM::B_FLOATS;
+    float* b3e = Blo + MM::B_FLOATS;        // [J]
+    float* YS = b3e + MM::kRed;             // [2][128][F] second-layer partials of the two column halves
+    float* W4s = YS + 2 * 128 * F;          // [J][F] input-major second-layer weights
+    uint64_t* bar = reinterpret_cast<uint64_t*>(W4s + J * F);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+    float* A3 = sm;                         // [128][LDA], aliases the A operand once the MMAs are done
+    const int warp = warp_index_uniform(), lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
+    if (warp == 0) tmem_alloc(tmem_slot, MM::TMEM_COLS);
+    // B operand: W3[j][k], j < 10F (N), k < 9F (K), split hi/lo, zero padded, core-matrix layout
+    for (int i = threadIdx.x; i < NP * KC; i += blockDim.x) {
+        const int j = i / KC, kc = i - j * KC;
+        float hi[4], lo[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int k = 4 * kc + q;
+            const float w = (j < J && k < K9) ? __ldg(p.w3 + (size_t)j * J + k) : 0.f;
+            hi[q] = to_tf32(w);
+            lo[q] = to_tf32(w - hi[q]);
+        }
+        const int o = (kc * MM::LBO_B + (j >> 3) * 128 + (j & 7) * 16) >> 2;
+        *reinterpret_cast<float4*>(Bhi + o) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(Blo + o) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    }
+    for (int i = threadIdx.x; i < J * F; i += blockDim.x) {
+        const int j = i / F, f = i - j * F;
+        W4s[i] = __ldg(p.w4 + (size_t)f * J + j);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t idesc = umma_idesc_tf32(128, NP);
+    uint32_t parity = 0;
+
+    const int total = p.ntiles * p.G;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int g = tile / p.ntiles, lt = tile - g * p.ntiles;
+        const int f0 = lt * kNodeRowsC;
+        const int rows = min(kNodeRowsC, p.S - f0);
+        const size_t row0 = (size_t)g * p.S + f0;
+        // ---- A operand: hcat = [x_s | mean | std | skew | kurt] per fibre, split hi/lo ----------------
+        // element (r, k) -> byte (k / 4) * LBO_A + r * 16 + (k % 4) * 4; consecutive threads take
+        // consecutive fibres r, so a warp writes one 512-byte run of a K chunk
+        auto put = [&](int r, int k, float v) {
+            const float hi = to_tf32(v);
+            const int o = ((k >> 2) * MM::LBO_A + r * 16 + (k & 3) * 4) >> 2;
+            Ahi[o] = hi;
+            Alo[o] = to_tf32(v - hi);
+        };
+        for (int i = threadIdx.x; i < 128 * (F + KP - K9); i += blockDim.x) {      // x_s columns and the zero padding
+            const int c = i >> 7, r = i & 127;
+            if (c < F) put(r, c, r < rows ? __ldg(p.x_s + (row0 + r) * F + c) : 0.f);
+            else put(r, K9 + (c - F), 0.f);
+        }
+        for (int i = threadIdx.x; i < 128 * M2; i += blockDim.x) {                 // the four statistics of feature j
+            const int j = i >> 7, r = i & 127;
+            float mean_o = 0.f, std_o = 0.f, skew_o = 0.f, kurt_o = 0.f;
+            if (r < rows) {
+                const float* mo = p.moments + (row0 + r) * 5 * M2 + j;
+                const float mean = __ldg(mo), ex2 = __ldg(mo + M2), c3 = __ldg(mo + 3 * M2), c4 = __ldg(mo + 4 * M2);
+                const float vr = ex2 - mean * mean;
+                const float var = vr > 0.f ? vr : kSlopeVar * vr;
+                const float std0 = sqrtf(var + kStdEps);
+                const float s3 = std0 * std0 * std0;
+                mean_o = nan_to_num(mean);
+                std_o = sqrtf(nan_to_num(var) + kStdEps);
+                skew_o = nan_to_num(c3 / s3);
+                kurt_o = nan_to_num(c4 / (s3 * std0));
+            }
+            put(r, F + j, mean_o);
+            put(r, F + M2 + j, std_o);
+            put(r, F + 2 * M2 + j, skew_o);
+            put(r, F + 3 * M2 + j, kurt_o);
+        }
+        for (int j = threadIdx.x; j < J; j += blockDim.x) {
+            float s = __ldg(p.b3 + j);
+            for (int k = 0; k < F; ++k) s = fmaf(__ldg(p.w3 + (size_t)j * J + K9 + k), __ldg(p.u + (size_t)g * F + k), s);
+            b3e[j] = s;
+        }
+        fence_proxy_async();      // generic-proxy writes of the operands -> visible to the tensor core (async proxy)
+        tc_fence_before();
+        __syncthreads();
+        // ---- MMAs: one thread issues KP/8 k-steps x 3 products --------------------------------------
+        if (threadIdx.x == 0) {
+            tc_fence_after();
+            const uint32_t a_hi = smem_u32(Ahi), a_lo = smem_u32(Alo), b_hi = smem_u32(Bhi), b_lo = smem_u32(Blo);
+#pragma unroll 1
+            for (int ks = 0; ks < KP / 8; ++ks) {
+                const uint32_t ao = ks * 2 * MM::LBO_A, bo = ks * 2 * MM::LBO_B;
+                const uint64_t dah = umma_desc(a_hi + ao, MM::LBO_A), dal = umma_desc(a_lo + ao, MM::LBO_A);
+                const uint64_t dbh = umma_desc(b_hi + bo, MM::LBO_B), dbl = umma_desc(b_lo + bo, MM::LBO_B);
+                umma_tf32(tmem, dal, dbh, idesc, ks > 0 ? 1u : 0u);   // small terms first
+                umma_tf32(tmem, dah, dbl, idesc, 1u);
+                umma_tf32(tmem, dah, dbh, idesc, 1u);
+            }
+            umma_commit(bar);     // implies tcgen05.fence::before_thread_sync
+        }
+        // ---- epilogue: warps 0-3 own TMEM lanes 32w .. 32w+31 = fibres of the tile ------------------
+        mbar_wait(bar, parity);
+        parity ^= 1;
+        tc_fence_after();
+        if (warp < 8) {
+            // warp w reads TMEM lanes 32 * (w % 4) .. + 31 (hardware rule) and the column half w / 4
+            const int quarter = warp & 3, half = warp >> 2;
+            const int r = quarter * 32 + lane;
+            constexpr int NH = (NP / 16 + 1) / 2 * 16;       // columns of the first half (multiple of 16)
+            const int c_begin = half ? NH : 0, c_end = half ? NP : NH;
+            float y[F];
+#pragma unroll
+            for (int f = 0; f < F; ++f) y[f] = half ? 0.f : c_w[CW::kB4 + f];
+#pragma unroll 1
+            for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+                float v[16];
+                tmem_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + c0, v);
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const int j = c0 + q;
+                    if (j < J) {
+                        const float a = lrelu(v[q] + b3e[j]);
+                        A3[r * LDA + j] = a;
+                        const float* w4 = W4s + j * F;
+#pragma unroll
+                        for (int f = 0; f < F; ++f) y[f] = fmaf(a, w4[f], y[f]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int f = 0; f < F; ++f) YS[(half * 128 + r) * F + f] = y[f];
+        }
+        tc_fence_before();
+        __syncthreads();
+        for (int i = threadIdx.x; i < rows * F; i += blockDim.x) {      // y = both column halves
+            const float v = YS[i] + YS[128 * F + i];
+            YS[i] = v;
+            p.y_pre[row0 * F + i] = v;
+        }
+        tc_fence_before();
+        __syncthreads();
+        // hidden activations to global (coalesced), BatchNorm tile statistics
+        for (int i = threadIdx.x; i < rows * J; i += blockDim.x) {
+            const int r = i / J, j = i - r * J;
+            p.hidden[(row0 + r) * J + j] = A3[r * LDA + j];
+        }
+        __syncthreads();
+        if (p.bn_partial) {
+            // two-pass tile statistics, kParts row slices per feature reduced in a fixed order
+            constexpr int kParts = 16;
+            float* red = b3e;     // the bias vector is dead: kParts * F + F floats of scratch
+            const int f = threadIdx.x % F, part = threadIdx.x / F;
+            float s = 0.f;
+            if (part < kParts)
+                for (int r = part; r < rows; r += kParts) s += YS[r * F + f];
+            if (part < kParts) red[part * F + f] = s;
+            __syncthreads();
+            if (threadIdx.x < F) {
+                float t = 0.f;
+                for (int q = 0; q < kParts; ++q) t += red[q * F + threadIdx.x];
+                red[kParts * F + threadIdx.x] = t / (float)rows;
+            }
+            __syncthreads();
+            const float mean = red[kParts * F + f];
+            float m2 = 0.f;
+            if (part < kParts)
+                for (int r = part; r < rows; r += kParts) {
+                    const float d = YS[r * F + f] - mean;
+                    m2 = fmaf(d, d, m2);
+                }
+            __syncthreads();
+            if (part < kParts) red[part * F + f] = m2;
+            __syncthreads();
+            if (threadIdx.x < F) {
+                float t = 0.f;
+                for (int q = 0; q < kParts; ++q) t += red[q * F + threadIdx.x];
+                float* o = p.bn_partial + (size_t)tile * bn_partial_stride(F);
+                o[threadIdx.x] = red[kParts * F + threadIdx.x];
+                o[F + threadIdx.x] = t;
+                if (threadIdx.x == 0) o[2 * F] = (float)rows;
+            }
+        }
+        __syncthreads();
+        tc_fence_after();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, MM::TMEM_COLS);
+}
+
+}  // namespace pfs
