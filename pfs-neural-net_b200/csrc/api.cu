@@ -244,6 +244,22 @@ int reduce_partials(const float* partial, int ncta, int pstride, int poff, int n
     PFS_LAUNCH_CHECK("k_reduce_partials");
     return PFS_OK;
 }
+// builder for k_reduce_multi
+struct Reducer {
+    ReduceList rl{};
+    void add(int poff, int n, int cols, float* out, int ldo, int coff) {
+        if (!out || n <= 0) return;
+        rl.seg[rl.nseg++] = ReduceSeg{poff, n, cols, ldo, coff, out};
+        rl.total += n;
+    }
+    int run(const float* partial, int ncta, int pstride, cudaStream_t st) {
+        if (rl.nseg == 0) return PFS_OK;
+        k_reduce_multi<<<(rl.total + 127) / 128, 128, 0, st>>>(partial, ncta, pstride, rl);
+        PFS_LAUNCH_CHECK("k_reduce_partials");
+        return PFS_OK;
+    }
+};
+
 int colsum_all(const float* x, long long N, int ld, int off, int J, float* out, cudaStream_t st) {
     k_colsum_all<<<(J + 31) / 32, dim3(32, 8), 0, st>>>(x, N, ld, off, J, out);
     PFS_LAUNCH_CHECK("k_colsum_all");
@@ -271,8 +287,10 @@ int outer_rows(const float* D, const float* X, long long N, float* scratch_parti
     constexpr int pstride = J * K + J;
     kern<<<grid, kThreads, smem, st>>>(D, X, N, scratch_partial, pstride);
     PFS_LAUNCH_CHECK("k_outer_rows");
-    PFS_TRY(reduce_partials(scratch_partial, grid, pstride, 0, J * K, K, dW, ldo, coff, st));
-    if (db) PFS_TRY(reduce_partials(scratch_partial, grid, pstride, J * K, J, J, db, J, 0, st));
+    Reducer rd;
+    rd.add(0, J * K, K, dW, ldo, coff);
+    if (db) rd.add(J * K, J, J, db, J, 0);
+    PFS_TRY(rd.run(scratch_partial, grid, pstride, st));
     return PFS_OK;
 }
 // class-side sums: dense -> second stage over per-tile partials; CSR -> class-sorted segment sums
@@ -447,9 +465,13 @@ int edge_bwd_impl(const pfs_edge_args& a, const Topo& tp) {
                     dense ? stage : nullptr, dense ? nullptr : stage, wpart, pstride, max_fib, sc ? 1 : 0, nbuf};
     kern<<<grid, kThreads, smem_bwd, st>>>(p);
     PFS_LAUNCH_CHECK("k_edge_bwd");
-    PFS_TRY(reduce_partials(wpart, grid, pstride, 0, H * F, F, a.g_w1, H, 2 * F, st));
-    PFS_TRY(reduce_partials(wpart, grid, pstride, H * F, F * H, H, a.g_w2, H, 0, st));
-    PFS_TRY(reduce_partials(wpart, grid, pstride, 2 * H * F, F, F, a.g_b2, F, 0, st));
+    {
+        Reducer rd;
+        rd.add(0, H * F, F, a.g_w1, H, 2 * F);
+        rd.add(H * F, F * H, H, a.g_w2, H, 0);
+        rd.add(2 * H * F, F, F, a.g_b2, F, 0);
+        PFS_TRY(rd.run(wpart, grid, pstride, st));
+    }
     PFS_TRY(class_sums(tp, stage, H, dPt, st));
     PFS_TRY((node_linear_bwd<F, H>(dPs, (long long)tp.G * tp.S, a.w1, H, 0, a.g_x_s, st)));
     PFS_TRY((node_linear_bwd<F, H>(dPt, (long long)tp.G * tp.T, a.w1, H, F, a.g_x_t, st)));
@@ -592,9 +614,13 @@ int source_bwd_impl(const pfs_source_args& a, const Topo& tp) {
         }
         PFS_LAUNCH_CHECK("k_source_node_bwd");
     }
-    PFS_TRY(reduce_partials(wpn, gridn, pstride_n, 0, J * K9, K9, a.g_w3, J, 0, st));
-    PFS_TRY(reduce_partials(wpn, gridn, pstride_n, J * K9, F * J, J, a.g_w4, J, 0, st));
-    PFS_TRY(reduce_partials(wpn, gridn, pstride_n, J * K9 + F * J, F, F, a.g_b4, F, 0, st));
+    {
+        Reducer rd;
+        rd.add(0, J * K9, K9, a.g_w3, J, 0);
+        rd.add(J * K9, F * J, J, a.g_w4, J, 0);
+        rd.add(J * K9 + F * J, F, F, a.g_b4, F, 0);
+        PFS_TRY(rd.run(wpn, gridn, pstride_n, st));
+    }
     k_class_reduce<<<dim3((J + 127) / 128, tp.G), 128, 0, st>>>(tot3p, ntn, J, tot3);
     PFS_LAUNCH_CHECK("k_class_reduce(tot3)");
     PFS_TRY(colsum_all(tot3, tp.G, J, 0, J, a.g_b3, st));
@@ -608,9 +634,13 @@ int source_bwd_impl(const pfs_source_args& a, const Topo& tp) {
         ke<<<gride, kThreads, SME::bytes, st>>>(p);
         PFS_LAUNCH_CHECK("k_source_edge_bwd");
     }
-    PFS_TRY(reduce_partials(wpe, gride, pstride_e, 0, M * F, F, a.g_w1, M, F, st));
-    PFS_TRY(reduce_partials(wpe, gride, pstride_e, M * F, M * M, M, a.g_w2, M, 0, st));
-    PFS_TRY(reduce_partials(wpe, gride, pstride_e, M * F + M * M, M, M, a.g_b2, M, 0, st));
+    {
+        Reducer rd;
+        rd.add(0, M * F, F, a.g_w1, M, F);
+        rd.add(M * F, M * M, M, a.g_w2, M, 0);
+        rd.add(M * F + M * M, M, M, a.g_b2, M, 0);
+        PFS_TRY(rd.run(wpe, gride, pstride_e, st));
+    }
     PFS_TRY(class_sums(tp, stage, M, dQt, st));
     PFS_TRY((node_linear_bwd<F, M>(dQt, (long long)tp.G * tp.T, a.w1, M, 0, a.g_x_t, st)));
     PFS_TRY((outer_rows<M, F, 4, F / 2>(dQt, a.x_t, (long long)tp.G * tp.T, opart, a.g_w1, M, 0, a.g_b1, st)));
@@ -704,15 +734,19 @@ int target_bwd_impl(const pfs_target_args& a, const Topo& tp) {
         k_target_tail_bwd<<<tp.G, kThreads, smem, st>>>(p);
         PFS_LAUNCH_CHECK("k_target_tail_bwd");
     }
-    PFS_TRY(reduce_partials(gpart, tp.G, ptail, tail_off_w2(F), M * M, M, a.g_w2, M, 0, st));
-    PFS_TRY(reduce_partials(gpart, tp.G, ptail, tail_off_b2(F), M, M, a.g_b2, M, 0, st));
-    PFS_TRY(reduce_partials(gpart, tp.G, ptail, tail_off_w3(F), H * H, H, a.g_w3, H, 0, st));
-    PFS_TRY(reduce_partials(gpart, tp.G, ptail, tail_off_b3(F), H, H, a.g_b3, H, 0, st));
-    PFS_TRY(reduce_partials(gpart, tp.G, ptail, tail_off_w4(F), F * H, H, a.g_w4, H, 0, st));
-    PFS_TRY(reduce_partials(gpart, tp.G, ptail, tail_off_b4(F), F, F, a.g_b4, F, 0, st));
-    if (a.normed) {
-        PFS_TRY(reduce_partials(gpart, tp.G, ptail, tail_off_gamma(F), F, F, a.g_gamma, F, 0, st));
-        PFS_TRY(reduce_partials(gpart, tp.G, ptail, tail_off_beta(F), F, F, a.g_beta, F, 0, st));
+    {
+        Reducer rd;
+        rd.add(tail_off_w2(F), M * M, M, a.g_w2, M, 0);
+        rd.add(tail_off_b2(F), M, M, a.g_b2, M, 0);
+        rd.add(tail_off_w3(F), H * H, H, a.g_w3, H, 0);
+        rd.add(tail_off_b3(F), H, H, a.g_b3, H, 0);
+        rd.add(tail_off_w4(F), F * H, H, a.g_w4, H, 0);
+        rd.add(tail_off_b4(F), F, F, a.g_b4, F, 0);
+        if (a.normed) {
+            rd.add(tail_off_gamma(F), F, F, a.g_gamma, F, 0);
+            rd.add(tail_off_beta(F), F, F, a.g_beta, F, 0);
+        }
+        PFS_TRY(rd.run(gpart, tp.G, ptail, st));
     }
     PFS_TRY((node_linear<F, M>(a.x_s, tp.S, tp.G, a.w1, M, 0, a.b1, nullptr, Rs, st)));
     {
@@ -754,10 +788,14 @@ int head_impl(const pfs_head_args& a, const Topo& tp, bool backward) {
     p.wpartial = wpart;
     k_head_bwd<F><<<grid, kThreads, 0, st>>>(p);
     PFS_LAUNCH_CHECK("k_head_bwd");
-    PFS_TRY(reduce_partials(wpart, grid, pstride, 0, F * F, F, a.g_w1, F, 0, st));
-    PFS_TRY(reduce_partials(wpart, grid, pstride, F * F, F, F, a.g_b1, F, 0, st));
-    PFS_TRY(reduce_partials(wpart, grid, pstride, F * F + F, F, F, a.g_w2, F, 0, st));
-    PFS_TRY(reduce_partials(wpart, grid, pstride, F * F + 2 * F, 1, 1, a.g_b2, 1, 0, st));
+    {
+        Reducer rd;
+        rd.add(0, F * F, F, a.g_w1, F, 0);
+        rd.add(F * F, F, F, a.g_b1, F, 0);
+        rd.add(F * F + F, F, F, a.g_w2, F, 0);
+        rd.add(F * F + 2 * F, 1, 1, a.g_b2, 1, 0);
+        PFS_TRY(rd.run(wpart, grid, pstride, st));
+    }
     return PFS_OK;
 }
 
@@ -1040,13 +1078,15 @@ int pfs_global_bwd(const pfs_global_args* a) {
     const size_t smem = sizeof(float) * (22 * (size_t)F + 2);
     k_global_bwd<<<a->G, kThreads, smem, st>>>(p);
     PFS_LAUNCH_CHECK("k_global_bwd");
-    PFS_TRY(reduce_partials(gpart, a->G, pg, glob_off_w1(F), K * K, K, a->g_w1, K, 0, st));
-    PFS_TRY(reduce_partials(gpart, a->G, pg, glob_off_b1(F), K, K, a->g_b1, K, 0, st));
-    PFS_TRY(reduce_partials(gpart, a->G, pg, glob_off_w2(F), F * K, K, a->g_w2, K, 0, st));
-    PFS_TRY(reduce_partials(gpart, a->G, pg, glob_off_b2(F), F, F, a->g_b2, F, 0, st));
-    if (a->normed) {
-        PFS_REQUIRE(a->g_rms_weight, "null pointer");
-        PFS_TRY(reduce_partials(gpart, a->G, pg, glob_off_rms(F), F, F, a->g_rms_weight, F, 0, st));
+    {
+        if (a->normed) PFS_REQUIRE(a->g_rms_weight, "null pointer");
+        Reducer rd;
+        rd.add(glob_off_w1(F), K * K, K, a->g_w1, K, 0);
+        rd.add(glob_off_b1(F), K, K, a->g_b1, K, 0);
+        rd.add(glob_off_w2(F), F * K, K, a->g_w2, K, 0);
+        rd.add(glob_off_b2(F), F, F, a->g_b2, F, 0);
+        if (a->normed) rd.add(glob_off_rms(F), F, F, a->g_rms_weight, F, 0);
+        PFS_TRY(rd.run(gpart, a->G, pg, st));
     }
     return PFS_OK;
 }

@@ -121,6 +121,38 @@ __global__ void k_reduce_partials(const float* __restrict__ partial, int ncta, i
     out[(i / cols) * ldo + coff + (i % cols)] = s;
 }
 
+// several reductions of one partial buffer in one launch (fewer latency-bound launches)
+struct ReduceSeg {
+    int poff, n, cols, ldo, coff;
+    float* out;
+};
+constexpr int kMaxReduceSegs = 8;
+struct ReduceList {
+    ReduceSeg seg[kMaxReduceSegs];
+    int nseg, total;
+};
+__global__ void k_reduce_multi(const float* __restrict__ partial, int ncta, int pstride, const ReduceList rl) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rl.total) return;
+    int q = 0;
+    while (q < rl.nseg - 1 && i >= rl.seg[q].n) {
+        i -= rl.seg[q].n;
+        ++q;
+    }
+    const ReduceSeg sg = rl.seg[q];
+    const float* p = partial + sg.poff + i;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // fixed association: four interleaved chains, then a fixed tree
+    int c = 0;
+    for (; c + 3 < ncta; c += 4) {
+        s0 += p[(size_t)c * pstride];
+        s1 += p[(size_t)(c + 1) * pstride];
+        s2 += p[(size_t)(c + 2) * pstride];
+        s3 += p[(size_t)(c + 3) * pstride];
+    }
+    for (; c < ncta; ++c) s0 += p[(size_t)c * pstride];
+    sg.out[(i / sg.cols) * sg.ldo + sg.coff + (i % sg.cols)] = (s0 + s1) + (s2 + s3);
+}
+
 // colsum over rows and graphs: out[j] = sum_n x[n][j] (single CTA per 32 columns; fixed order)
 __global__ void k_colsum_all(const float* __restrict__ x, long long N, int ld, int off, int J,
                              float* __restrict__ out) {
