@@ -239,6 +239,90 @@ typedef struct pfs_head_args {
 int pfs_time_head_fwd(const pfs_head_args* a);
 int pfs_time_head_bwd(const pfs_head_args* a);
 
+/* -------------------------------------------------------------------------------------------
+ * Wide-feature path (Fdim >= 32, bf16 storage, fp32 accumulation and statistics; BASELINE
+ * configs C4 / C5b).  At these widths every MLP layer of src/gnn.py:65-71 is a dense contraction
+ * and runs on tcgen05 tensor cores; the Python host (`pfs-neural-net_b200/wide.py`) composes the
+ * module forward/backward passes of src/gnn.py:73-223 from the primitives below, one graph per
+ * call (G = 1).  bf16 tensors are passed as void*; rows are row-major with the stated leading
+ * dimension in ELEMENTS; all pointers must be 16-byte aligned and leading dimensions multiples of 8.
+ * ---------------------------------------------------------------------------------------- */
+
+/* C[M,N] = epilogue(A[M,K] . B[N,K]^T): one Linear layer (B = torch weight [out,in] or a column
+ * slice of it), forward or input-gradient direction (reference src/gnn.py:65-71).  Epilogue, in
+ * order: + bias[n] * (bias_rowscale ? bias_rowscale[m] : 1); + tab0[row0(m)][n]; + tab1[row1(m)][n]
+ * (row0 = idx0 ? idx0[m] : m / div0, row1 = idx1 ? idx1[m] : m % mod1 -- the gathered first-layer
+ * node tables replacing the concatenations of src/gnn.py:100,136,188); LeakyReLU(0.1) if act;
+ * * (mask[m][n] > 0 ? 1 : 0.1) if mask (LeakyReLU derivative from the saved activation).
+ * Outputs: bf16 [M,ldc] and/or fp32 [M,ldf]. */
+typedef struct pfs_wide_gemm_args {
+    const void* A; int64_t lda;                  /* bf16 [M,K] */
+    const void* B; int64_t ldb;                  /* bf16 [N,K] */
+    int32_t M, N, K;
+    const float* bias;                           /* [N] or NULL */
+    const float* bias_rowscale;                  /* [M] or NULL */
+    const float* tab0; const int32_t* idx0; int32_t div0;   /* fp32 [*,N] or NULL */
+    const float* tab1; const int32_t* idx1; int32_t mod1;   /* fp32 [*,N] or NULL */
+    const void* mask; int64_t ldmask;            /* bf16 [M,ldmask] or NULL */
+    int32_t act;
+    void* out_bf16; int64_t ldc;                 /* or NULL */
+    float* out_f32; int64_t ldf;                 /* or NULL */
+    void* stream;
+} pfs_wide_gemm_args;
+size_t pfs_sizeof_wide_gemm_args(void);
+int pfs_wide_gemm_nt(const pfs_wide_gemm_args* a);
+
+/* W[J, Kx] (+)= D[E,J]^T . X[E,Kx]: a weight gradient, contraction over edges / nodes
+ * (autograd of src/gnn.py:65-71).  Split over row ranges, partial sums reduced in a fixed order.
+ * out is fp32 with leading dimension ldo; workspace from pfs_wide_gemm_tn_workspace. */
+size_t pfs_wide_gemm_tn_workspace(int64_t E, int32_t J, int32_t Kx);
+int pfs_wide_gemm_tn(const void* D, int64_t ldd, const void* X, int64_t ldx, int64_t E, int32_t J, int32_t Kx,
+                     float* out, int64_t ldo, int32_t accumulate, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
+/* Row segments for the segmented reductions that replace torch_scatter (src/gnn.py:140-144,190):
+ * mode 0 = dense fibres (rows seg*T + i), 1 = dense classes (rows i*T + seg), 2 = listed rows
+ * list[ptr[seg] .. ptr[seg+1]) (list NULL: the positions themselves). */
+typedef struct pfs_wide_segments {
+    int32_t mode, nseg, S, T;
+    const int32_t* ptr;
+    const int32_t* list;
+} pfs_wide_segments;
+size_t pfs_sizeof_wide_segments(void);
+
+/* Column statistics over rows (dtype codes: 0 = bf16, 1 = fp32).
+ * kind 0: out[0][c] = mean, out[1][c] = sum of squared deviations of x (BatchNorm forward);
+ * kind 1: out[0][c] = sum_r w[r] g[r][c], out[1][c] = sum_r w[r] g[r][c] (v[r][c] - p0[c]) p1[c]
+ *         (BatchNorm backward sums, bias gradients; v, p0, p1, w optional). */
+size_t pfs_wide_colstats_workspace(int64_t R, int32_t C);
+int pfs_wide_colstats(int32_t kind, const void* g, int32_t g_dtype, int64_t ldg, const void* v, int32_t v_dtype,
+                      int64_t ldv, const float* p0, const float* p1, const float* roww, int64_t R, int32_t C,
+                      float* out, void* workspace, size_t workspace_bytes, void* stream);
+/* kind 0: out = a[c] x + b[c];  kind 1: out = a[c] (x - b[c] - (v - p0[c]) p1[c] c2[c])  -> bf16 */
+int pfs_wide_rowmap(int32_t kind, const void* x, int32_t x_dtype, int64_t ldx, const void* v, int32_t v_dtype,
+                    int64_t ldv, const float* a, const float* b, const float* p0, const float* p1, const float* c2,
+                    int64_t R, int32_t C, void* out_bf16, int64_t ldo, void* stream);
+/* out[seg][c] = sum of x[row][c] over the segment's rows -> fp32 and/or bf16 [nseg, C] */
+size_t pfs_wide_segsum_workspace(const pfs_wide_segments* sd, int32_t C);
+int pfs_wide_segsum(const pfs_wide_segments* sd, const void* x_bf16, int64_t ldx, int32_t C, float* out_f32,
+                    void* out_bf16, void* workspace, size_t workspace_bytes, void* stream);
+/* SModel moment statistics (src/gnn.py:140-151) of the messages m [E,2F] per fibre:
+ * moments [S,5,2F] = {mean, E[m^2], c2, c3, c4}; hcat [S,9F] = [x_s|mean|std|skew|kurt] */
+int pfs_wide_moments_fwd(const pfs_wide_segments* sd, const void* m_bf16, int32_t C, float* moments, void* stream);
+int pfs_wide_source_hcat(const void* x_s_bf16, const float* moments, int32_t S, int32_t F, void* hcat_bf16, void* stream);
+/* backward of the statistics: dh [S,9F] fp32 -> dx_s bf16 [S,F] and cubic coefficients coef [S,4,2F];
+ * dm[e] = A0 + A1 m + A2 d^2 + A3 d^3 per edge (src = fibre of every edge, NULL: e / T) */
+int pfs_wide_source_coef(const pfs_wide_segments* sd, const float* dh, const float* moments, int32_t S, int32_t F,
+                         void* dx_s_bf16, float* coef, void* stream);
+int pfs_wide_source_dm(const void* m_bf16, const float* moments, const float* coef, const int32_t* src, int32_t T,
+                       int64_t E, int32_t C, void* dm_bf16, void* stream);
+/* out[e] = tab[idx ? idx[e] : e % mod] * (act[e] > 0 ? 1 : 0.1)   (TModel backward, src/gnn.py:188-190) */
+int pfs_wide_gather_mask(const float* tab, const int32_t* idx, int32_t mod, const void* act_bf16, int64_t E, int32_t C,
+                         void* out_bf16, void* stream);
+/* dtype conversion (0 = bf16, 1 = fp32) and bf16 transpose out[c][r] = in[r][c] */
+int pfs_wide_cast(const void* in, int32_t in_dtype, void* out, int32_t out_dtype, int64_t n, void* stream);
+int pfs_wide_transpose(const void* in_bf16, int32_t R, int32_t C, int64_t ld, void* out_bf16, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

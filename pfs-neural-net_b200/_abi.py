@@ -101,6 +101,26 @@ class HeadArgs(ct.Structure):
     ])
 
 
+class WideGemmArgs(ct.Structure):
+    _fields_ = [
+        ("A", _P), ("lda", ct.c_int64), ("B", _P), ("ldb", ct.c_int64),
+        ("M", ct.c_int32), ("N", ct.c_int32), ("K", ct.c_int32),
+        ("bias", _P), ("bias_rowscale", _P),
+        ("tab0", _P), ("idx0", _P), ("div0", ct.c_int32),
+        ("tab1", _P), ("idx1", _P), ("mod1", ct.c_int32),
+        ("mask", _P), ("ldmask", ct.c_int64),
+        ("act", ct.c_int32),
+        ("out_bf16", _P), ("ldc", ct.c_int64),
+        ("out_f32", _P), ("ldf", ct.c_int64),
+        ("stream", _P),
+    ]
+
+
+class WideSegments(ct.Structure):
+    _fields_ = [("mode", ct.c_int32), ("nseg", ct.c_int32), ("S", ct.c_int32), ("T", ct.c_int32),
+                ("ptr", _P), ("list", _P)]
+
+
 # every symbol include/pfs_b200.h declares: name -> (restype, argtypes)
 _I64, _I32 = ct.c_int64, ct.c_int32
 SYMBOLS = {
@@ -130,10 +150,29 @@ SYMBOLS = {
     "pfs_global_bwd": (ct.c_int, [ct.POINTER(GlobalArgs)]),
     "pfs_time_head_fwd": (ct.c_int, [ct.POINTER(HeadArgs)]),
     "pfs_time_head_bwd": (ct.c_int, [ct.POINTER(HeadArgs)]),
+    # wide-feature path (bf16, tcgen05 GEMMs + HBM-bound row kernels)
+    "pfs_sizeof_wide_gemm_args": (ct.c_size_t, []),
+    "pfs_sizeof_wide_segments": (ct.c_size_t, []),
+    "pfs_wide_gemm_nt": (ct.c_int, [ct.POINTER(WideGemmArgs)]),
+    "pfs_wide_gemm_tn_workspace": (ct.c_size_t, [_I64, _I32, _I32]),
+    "pfs_wide_gemm_tn": (ct.c_int, [_P, _I64, _P, _I64, _I64, _I32, _I32, _P, _I64, _I32, _P, ct.c_size_t, _P]),
+    "pfs_wide_colstats_workspace": (ct.c_size_t, [_I64, _I32]),
+    "pfs_wide_colstats": (ct.c_int, [_I32, _P, _I32, _I64, _P, _I32, _I64, _P, _P, _P, _I64, _I32, _P, _P, ct.c_size_t, _P]),
+    "pfs_wide_rowmap": (ct.c_int, [_I32, _P, _I32, _I64, _P, _I32, _I64, _P, _P, _P, _P, _P, _I64, _I32, _P, _I64, _P]),
+    "pfs_wide_segsum_workspace": (ct.c_size_t, [ct.POINTER(WideSegments), _I32]),
+    "pfs_wide_segsum": (ct.c_int, [ct.POINTER(WideSegments), _P, _I64, _I32, _P, _P, _P, ct.c_size_t, _P]),
+    "pfs_wide_moments_fwd": (ct.c_int, [ct.POINTER(WideSegments), _P, _I32, _P, _P]),
+    "pfs_wide_source_hcat": (ct.c_int, [_P, _P, _I32, _I32, _P, _P]),
+    "pfs_wide_source_coef": (ct.c_int, [ct.POINTER(WideSegments), _P, _P, _I32, _I32, _P, _P, _P]),
+    "pfs_wide_source_dm": (ct.c_int, [_P, _P, _P, _P, _I32, _I64, _I32, _P, _P]),
+    "pfs_wide_gather_mask": (ct.c_int, [_P, _P, _I32, _P, _I64, _I32, _P, _P]),
+    "pfs_wide_cast": (ct.c_int, [_P, _I32, _P, _I32, _I64, _P]),
+    "pfs_wide_transpose": (ct.c_int, [_P, _I32, _I32, _I64, _P, _P]),
 }
 _SIZEOF_CHECKS = {
     "pfs_sizeof_topology": TopologyStruct, "pfs_sizeof_edge_args": EdgeArgs, "pfs_sizeof_source_args": SourceArgs,
     "pfs_sizeof_target_args": TargetArgs, "pfs_sizeof_global_args": GlobalArgs, "pfs_sizeof_head_args": HeadArgs,
+    "pfs_sizeof_wide_gemm_args": WideGemmArgs, "pfs_sizeof_wide_segments": WideSegments,
 }
 
 
@@ -144,22 +183,49 @@ class PfsError(RuntimeError):
 _lib = None
 
 
-def nvcc_command(out_path=LIB_PATH):
+# translation units of the library: source -> headers it depends on (besides include/pfs_b200.h)
+_WIDE_HEADERS = ("wide_gemm.cuh", "wide_ops.cuh", "tc_ptx.cuh")
+_UNITS = {
+    "api.cu": lambda f: f.endswith(".cuh") and not f.startswith("wide_"),
+    "wide.cu": lambda f: f in _WIDE_HEADERS,
+}
+
+
+def nvcc_command(src, obj):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    return [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
-            "-Xcompiler", "-fPIC", "-o", out_path, os.path.join(CSRC, "api.cu")]
+    return [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+            "-Xcompiler", "-fPIC", "-c", "-o", obj, src]
+
+
+def link_command(objs, out_path=LIB_PATH):
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    return [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", out_path] + objs
 
 
 def build_library(force=False, verbose=False):
-    """Compile csrc/*.cu into csrc/libpfs_b200.so for sm_100a (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))] + [HEADER]
-    if not force and os.path.exists(LIB_PATH) and \
-            os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(s) for s in srcs):
-        return LIB_PATH
-    cmd = nvcc_command()
-    if verbose:
-        print(" ".join(cmd))
-    subprocess.run(cmd, check=True, cwd=CSRC)
+    """Compile csrc/*.cu for sm_100a (one object per translation unit, in parallel) and link them
+    into csrc/libpfs_b200.so; nvcc cross-compiles without a GPU.  Only stale objects are rebuilt."""
+    procs, objs = [], []
+    for unit, dep in _UNITS.items():
+        src = os.path.join(CSRC, unit)
+        obj = os.path.join(CSRC, unit[:-3] + ".o")
+        objs.append(obj)
+        deps = [src, HEADER] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if dep(f)]
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(d) for d in deps):
+            continue
+        cmd = nvcc_command(src, obj)
+        if verbose:
+            print(" ".join(cmd))
+        procs.append((cmd, subprocess.Popen(cmd, cwd=CSRC)))
+    for cmd, p in procs:
+        if p.wait() != 0:
+            raise subprocess.CalledProcessError(p.returncode, cmd)
+    if procs or force or not os.path.exists(LIB_PATH) or \
+            os.path.getmtime(LIB_PATH) < max(os.path.getmtime(o) for o in objs):
+        cmd = link_command(objs)
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.run(cmd, check=True, cwd=CSRC)
     return LIB_PATH
 
 

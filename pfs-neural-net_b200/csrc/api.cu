@@ -861,6 +861,13 @@ size_t sort_temp_bytes(long long E) {
 
 }  // namespace
 
+// host-side services shared with the other translation units of the library (wide.cu)
+namespace pfs_host {
+int fail_msg(int code, const char* msg) { return fail(code, "%s", msg); }
+void mark_launch(const char* name, cudaStream_t st) { prof_mark(name, st); }
+int sm_count() { return num_sms(); }
+}  // namespace pfs_host
+
 // ==========================================================================================
 // extern "C"
 // ==========================================================================================

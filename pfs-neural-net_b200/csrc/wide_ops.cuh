@@ -1,0 +1,375 @@
+// wide_ops.cuh -- HBM-bound kernels of the wide-feature path (bf16 rows of 2F .. 10F features):
+// column statistics (BatchNorm forward / backward sums, bias gradients), per-feature affine maps,
+// deterministic segmented reductions over fibres and classes (reference torch_scatter call sites
+// src/gnn.py:140-144,190 -- no atomics, fixed summation order), the moment statistics of SModel and
+// their backward, and small layout helpers.  Every kernel moves rows as 4-byte bf16 pairs so a warp
+// reads 128 contiguous bytes of a row.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pfs {
+
+using bf16 = __nv_bfloat16;
+using bf162 = __nv_bfloat162;
+
+__device__ __forceinline__ float2 ld_pair(const bf16* p) { return __bfloat1622float2(*reinterpret_cast<const bf162*>(p)); }
+__device__ __forceinline__ float2 ld_pair(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ void st_pair(bf16* p, float a, float b) { *reinterpret_cast<bf162*>(p) = __floats2bfloat162_rn(a, b); }
+__device__ __forceinline__ void st_pair(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+
+// segments of rows: fibres or classes, dense (implicit) or listed
+struct SegDesc {
+    int mode;          // 0: dense fibre (rows seg*T + i, i < T), 1: dense class (rows i*T + seg, i < S), 2: list
+    int nseg, S, T;
+    const int* ptr;    // [nseg+1] (mode 2)
+    const int* list;   // rows of segment seg: list[ptr[seg] .. ptr[seg+1])  (null: the positions themselves)
+};
+__device__ __forceinline__ int seg_len(const SegDesc& sd, int seg) {
+    return sd.mode == 0 ? sd.T : sd.mode == 1 ? sd.S : sd.ptr[seg + 1] - sd.ptr[seg];
+}
+__device__ __forceinline__ long long seg_row(const SegDesc& sd, int seg, int i) {
+    if (sd.mode == 0) return (long long)seg * sd.T + i;
+    if (sd.mode == 1) return (long long)i * sd.T + seg;
+    const int p = sd.ptr[seg] + i;
+    return sd.list ? sd.list[p] : p;
+}
+
+// ------------------------------------------------------------------------------------------------
+// column statistics over the rows of x [R, C] (leading dimension ld):
+//   kind 0 (moments): s0 = sum (x - shift), s1 = sum (x - shift)^2, shift[c] = x[0][c]
+//   kind 1 (BN backward): s0 = sum w g, s1 = sum w g (v - p0) p1    (v, p0, p1 optional: s1 = 0 without v)
+// partial [nrb][2][C]; block (32, 8): x = column pair, y = row lane; grid (ceil(C / 64), nrb)
+// ------------------------------------------------------------------------------------------------
+template <class TG, class TV>
+__global__ void __launch_bounds__(256) k_wide_colstats(int kind, const TG* __restrict__ g, int ldg, const TV* __restrict__ v,
+                                                       int ldv, const float* __restrict__ p0, const float* __restrict__ p1,
+                                                       const float* __restrict__ roww, long long R, int C,
+                                                       long long rows_per_block, float* __restrict__ partial) {
+    __shared__ float red[8][32][4];
+    const int c = 2 * (blockIdx.x * 32 + threadIdx.x);
+    const long long r0 = (long long)blockIdx.y * rows_per_block;
+    const long long r1 = min(R, r0 + rows_per_block);
+    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+    if (c < C) {
+        float sh0 = 0.f, sh1 = 0.f, q0 = 0.f, q1 = 0.f, e0 = 1.f, e1 = 1.f;
+        if (kind == 0) {
+            const float2 s = ld_pair(g + c);
+            sh0 = s.x; sh1 = s.y;
+        } else if (v) {
+            if (p0) { q0 = p0[c]; q1 = p0[c + 1]; }
+            if (p1) { e0 = p1[c]; e1 = p1[c + 1]; }
+        }
+        for (long long r = r0 + threadIdx.y; r < r1; r += 8) {
+            const float2 x = ld_pair(g + r * ldg + c);
+            if (kind == 0) {
+                const float d0 = x.x - sh0, d1 = x.y - sh1;
+                a0 += d0; a1 += d1;
+                b0 = fmaf(d0, d0, b0); b1 = fmaf(d1, d1, b1);
+            } else {
+                const float w = roww ? roww[r] : 1.f;
+                const float g0 = w * x.x, g1 = w * x.y;
+                a0 += g0; a1 += g1;
+                if (v) {
+                    const float2 y = ld_pair(v + r * ldv + c);
+                    b0 = fmaf(g0, (y.x - q0) * e0, b0);
+                    b1 = fmaf(g1, (y.y - q1) * e1, b1);
+                }
+            }
+        }
+    }
+    red[threadIdx.y][threadIdx.x][0] = a0;
+    red[threadIdx.y][threadIdx.x][1] = a1;
+    red[threadIdx.y][threadIdx.x][2] = b0;
+    red[threadIdx.y][threadIdx.x][3] = b1;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int y = 0; y < 8; ++y)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) s[q] += red[y][threadIdx.x][q];
+        float* o = partial + (size_t)blockIdx.y * 2 * C;
+        o[c] = s[0]; o[c + 1] = s[1];
+        o[C + c] = s[2]; o[C + c + 1] = s[3];
+    }
+}
+// out[0][c] = sum over row blocks of s0, out[1][c] = of s1 (fp64 accumulation, fixed order);
+// kind 0 converts to (mean, M2) using the shift row
+template <class TG>
+__global__ void k_wide_colstats_final(int kind, const float* __restrict__ partial, int nrb, int C, long long R,
+                                      const TG* __restrict__ shift_row, float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s0 = 0.0, s1 = 0.0;
+    for (int b = 0; b < nrb; ++b) {
+        s0 += partial[(size_t)b * 2 * C + c];
+        s1 += partial[(size_t)b * 2 * C + C + c];
+    }
+    if (kind == 0) {
+        const double n = (double)R;
+        const double sh = (double)(float)shift_row[c];
+        out[c] = (float)(sh + s0 / n);
+        const double m2 = s1 - s0 * s0 / n;
+        out[C + c] = (float)(m2 > 0.0 ? m2 : 0.0);
+    } else {
+        out[c] = (float)s0;
+        out[C + c] = (float)s1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-feature maps over rows
+//   kind 0: out = a[c] * x + b[c]
+//   kind 1: out = a[c] * (x - b[c] - (v - p0[c]) * p1[c] * c2[c])          (BatchNorm backward)
+// ------------------------------------------------------------------------------------------------
+template <class TX, class TV>
+__global__ void __launch_bounds__(256) k_wide_rowmap(int kind, const TX* __restrict__ x, int ldx, const TV* __restrict__ v, int ldv,
+                                                     const float* __restrict__ a, const float* __restrict__ b,
+                                                     const float* __restrict__ p0, const float* __restrict__ p1,
+                                                     const float* __restrict__ c2, long long R, int C,
+                                                     bf16* __restrict__ out, int ldo) {
+    const int half = C >> 1;
+    const long long total = R * half;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / half;
+        const int c = 2 * (int)(i - r * half);
+        const float2 xx = ld_pair(x + r * ldx + c);
+        float o0, o1;
+        if (kind == 0) {
+            o0 = fmaf(a[c], xx.x, b[c]);
+            o1 = fmaf(a[c + 1], xx.y, b[c + 1]);
+        } else {
+            const float2 vv = ld_pair(v + r * ldv + c);
+            o0 = a[c] * (xx.x - b[c] - (vv.x - p0[c]) * p1[c] * c2[c]);
+            o1 = a[c + 1] * (xx.y - b[c + 1] - (vv.y - p0[c + 1]) * p1[c + 1] * c2[c + 1]);
+        }
+        st_pair(out + r * ldo + c, o0, o1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// segmented sums: out[seg][c] = sum over the segment's rows of x[row][c]
+// grid (nseg, nchunk), 256 threads, thread = column pair (loops when C > 512);
+// nchunk > 1 writes partial[chunk][seg][C] for k_wide_segsum_final
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_wide_segsum(const SegDesc sd, const bf16* __restrict__ x, int ldx, int C, int nchunk,
+                                                     float* __restrict__ out_f32, bf16* __restrict__ out_bf16,
+                                                     float* __restrict__ partial) {
+    const int seg = blockIdx.x, chunk = blockIdx.y;
+    const int len = seg_len(sd, seg);
+    const int i0 = (int)((long long)len * chunk / nchunk), i1 = (int)((long long)len * (chunk + 1) / nchunk);
+    for (int c = 2 * threadIdx.x; c < C; c += 512) {
+        float s0 = 0.f, s1 = 0.f, t0 = 0.f, t1 = 0.f;
+        int i = i0;
+        for (; i + 1 < i1; i += 2) {      // two independent chains keep two loads in flight
+            const float2 a = ld_pair(x + seg_row(sd, seg, i) * ldx + c);
+            const float2 b = ld_pair(x + seg_row(sd, seg, i + 1) * ldx + c);
+            s0 += a.x; s1 += a.y;
+            t0 += b.x; t1 += b.y;
+        }
+        if (i < i1) {
+            const float2 a = ld_pair(x + seg_row(sd, seg, i) * ldx + c);
+            s0 += a.x; s1 += a.y;
+        }
+        s0 += t0; s1 += t1;
+        if (nchunk > 1) {
+            float* p = partial + ((size_t)chunk * sd.nseg + seg) * C + c;
+            p[0] = s0; p[1] = s1;
+        } else {
+            if (out_f32) st_pair(out_f32 + (size_t)seg * C + c, s0, s1);
+            if (out_bf16) st_pair(out_bf16 + (size_t)seg * C + c, s0, s1);
+        }
+    }
+}
+__global__ void k_wide_segsum_final(const float* __restrict__ partial, int nchunk, long long n, float* __restrict__ out_f32,
+                                    bf16* __restrict__ out_bf16) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float s = 0.f;
+    for (int q = 0; q < nchunk; ++q) s += partial[(size_t)q * n + i];
+    if (out_f32) out_f32[i] = s;
+    if (out_bf16) out_bf16[i] = __float2bfloat16_rn(s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// SModel moments (reference src/gnn.py:140-144): per fibre over its message rows m [E, C], C = 2F:
+// moments[fibre] = {mean, E[m^2], c2, c3, c4} (central moments about the mean, two passes), [S,5,C]
+// grid (S), C / 2 threads
+// ------------------------------------------------------------------------------------------------
+__global__ void k_wide_moments_fwd(const SegDesc sd, const bf16* __restrict__ m, int C, float* __restrict__ moments) {
+    const int seg = blockIdx.x;
+    const int len = seg_len(sd, seg);
+    const float inv = 1.f / (float)max(len, 1);
+    for (int c = 2 * threadIdx.x; c < C; c += 2 * blockDim.x) {
+        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+        for (int i = 0; i < len; ++i) {
+            const float2 a = ld_pair(m + seg_row(sd, seg, i) * C + c);
+            s0 += a.x; s1 += a.y;
+            q0 = fmaf(a.x, a.x, q0); q1 = fmaf(a.y, a.y, q1);
+        }
+        const float mean0 = s0 * inv, mean1 = s1 * inv;
+        float a20 = 0.f, a21 = 0.f, a30 = 0.f, a31 = 0.f, a40 = 0.f, a41 = 0.f;
+        for (int i = 0; i < len; ++i) {
+            const float2 a = ld_pair(m + seg_row(sd, seg, i) * C + c);
+            const float d0 = a.x - mean0, d1 = a.y - mean1;
+            const float d02 = d0 * d0, d12 = d1 * d1;
+            a20 += d02; a21 += d12;
+            a30 = fmaf(d02, d0, a30); a31 = fmaf(d12, d1, a31);
+            a40 = fmaf(d02, d02, a40); a41 = fmaf(d12, d12, a41);
+        }
+        float* o = moments + (size_t)seg * 5 * C + c;
+        st_pair(o, mean0, mean1);
+        st_pair(o + C, q0 * inv, q1 * inv);
+        st_pair(o + 2 * C, a20 * inv, a21 * inv);
+        st_pair(o + 3 * C, a30 * inv, a31 * inv);
+        st_pair(o + 4 * C, a40 * inv, a41 * inv);
+    }
+}
+
+__device__ __forceinline__ float wide_nan_to_num(float x) {   // torch.nan_to_num(nan=0): +-inf -> +-FLT_MAX
+    if (x != x) return 0.f;
+    if (isinf(x)) return x > 0.f ? 3.402823466e+38f : -3.402823466e+38f;
+    return x;
+}
+struct MomentStats {
+    float mean, std, skew, kurt, var_raw, std0;
+};
+__device__ __forceinline__ MomentStats wide_moment_stats(float mean, float ex2, float c3, float c4) {
+    MomentStats s;
+    s.var_raw = ex2 - mean * mean;
+    const float var = s.var_raw > 0.f ? s.var_raw : 0.01f * s.var_raw;    // F.leaky_relu default slope (src/gnn.py:141)
+    s.std0 = sqrtf(var + 1e-6f);
+    const float s3 = s.std0 * s.std0 * s.std0;
+    s.mean = wide_nan_to_num(mean);
+    s.std = sqrtf(wide_nan_to_num(var) + 1e-6f);
+    s.skew = wide_nan_to_num(c3 / s3);
+    s.kurt = wide_nan_to_num(c4 / (s3 * s.std0));
+    return s;
+}
+// hcat[fibre] = [x_s | mean | std | skew | kurt]  (bf16 [S, 9F]; reference src/gnn.py:147-152)
+__global__ void k_wide_source_hcat(const bf16* __restrict__ x_s, const float* __restrict__ moments, int S, int F,
+                                   bf16* __restrict__ hcat) {
+    const int C = 2 * F, K9 = 9 * F;
+    const long long total = (long long)S * (F + C);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long s = i / (F + C);
+        const int j = (int)(i - s * (F + C));
+        bf16* o = hcat + s * K9;
+        if (j < F) {
+            o[j] = x_s[s * F + j];
+        } else {
+            const int c = j - F;
+            const float* mo = moments + s * 5 * C + c;
+            const MomentStats st = wide_moment_stats(mo[0], mo[C], mo[3 * C], mo[4 * C]);
+            o[F + c] = __float2bfloat16_rn(st.mean);
+            o[F + C + c] = __float2bfloat16_rn(st.std);
+            o[F + 2 * C + c] = __float2bfloat16_rn(st.skew);
+            o[F + 3 * C + c] = __float2bfloat16_rn(st.kurt);
+        }
+    }
+}
+// moments backward: dh [S, 9F] fp32 (gradient of hcat) -> dx_s [S,F] bf16 and the per-fibre cubic
+// coefficients coef [S,4,C]: dm = A0 + A1 m + A2 d^2 + A3 d^3, already divided by the count
+__global__ void k_wide_source_coef(const SegDesc sd, const float* __restrict__ dh, const float* __restrict__ moments, int S, int F,
+                                   bf16* __restrict__ dx_s, float* __restrict__ coef) {
+    const int C = 2 * F, K9 = 9 * F;
+    const long long total = (long long)S * (F + C);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long s = i / (F + C);
+        const int j = (int)(i - s * (F + C));
+        const float* d = dh + s * K9;
+        if (j < F) {
+            dx_s[s * F + j] = __float2bfloat16_rn(d[j]);
+            continue;
+        }
+        const int c = j - F;
+        const float* mo = moments + s * 5 * C + c;
+        const float mean = mo[0], ex2 = mo[C], c2 = mo[2 * C], c3 = mo[3 * C], c4 = mo[4 * C];
+        const MomentStats st = wide_moment_stats(mean, ex2, c3, c4);
+        const float cnt = (float)max(seg_len(sd, (int)s), 1);
+        // gradients w.r.t. the four statistics; zero where nan_to_num replaced the value
+        const float s3 = st.std0 * st.std0 * st.std0, s4 = s3 * st.std0;
+        const bool ok_mean = mean == mean && !isinf(mean);
+        const float var = st.var_raw > 0.f ? st.var_raw : 0.01f * st.var_raw;
+        const bool ok_var = var == var && !isinf(var);
+        const float skew_raw = c3 / s3, kurt_raw = c4 / s4;
+        const bool ok_skew = skew_raw == skew_raw && !isinf(skew_raw);
+        const bool ok_kurt = kurt_raw == kurt_raw && !isinf(kurt_raw);
+        const float d_mean = ok_mean ? d[F + c] : 0.f;
+        const float d_std = d[F + C + c];
+        const float d_skew = ok_skew ? d[F + 2 * C + c] : 0.f;
+        const float d_kurt = ok_kurt ? d[F + 3 * C + c] : 0.f;
+        const float d_c3 = d_skew / s3, d_c4 = d_kurt / s4;
+        // std (output) = sqrt(nan_to_num(var) + eps); skew, kurt use std0 = sqrt(var + eps) (same value when finite)
+        float d_var = ok_var ? d_std / (2.f * st.std) : 0.f;
+        d_var += (-3.f * c3 / (s4) * d_skew - 4.f * c4 / (s4 * st.std0) * d_kurt) / (2.f * st.std0);
+        const float d_var_raw = d_var * (st.var_raw > 0.f ? 1.f : 0.01f);
+        const float d_mu = d_mean - 2.f * mean * d_var_raw - 3.f * c2 * d_c3 - 4.f * c3 * d_c4;
+        float* o = coef + s * 4 * C + c;
+        o[0] = d_mu / cnt;
+        o[C] = 2.f * d_var_raw / cnt;
+        o[2 * C] = 3.f * d_c3 / cnt;
+        o[3 * C] = 4.f * d_c4 / cnt;
+    }
+}
+// dm[e] = A0[src] + A1[src] m + A2[src] d^2 + A3[src] d^3, d = m - mean[src]   (bf16 [E, C])
+__global__ void __launch_bounds__(256) k_wide_source_dm(const bf16* __restrict__ m, const float* __restrict__ moments,
+                                                        const float* __restrict__ coef, const int* __restrict__ src, int T,
+                                                        long long E, int C, bf16* __restrict__ dm) {
+    const int half = C >> 1;
+    const long long total = E * half;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long e = i / half;
+        const int c = 2 * (int)(i - e * half);
+        const long long s = src ? src[e] : e / T;
+        const float2 mm = ld_pair(m + e * C + c);
+        const float2 mean = ld_pair(moments + s * 5 * C + c);
+        const float* cf = coef + s * 4 * C + c;
+        const float2 a0 = ld_pair(cf), a1 = ld_pair(cf + C), a2 = ld_pair(cf + 2 * C), a3 = ld_pair(cf + 3 * C);
+        const float d0 = mm.x - mean.x, d1 = mm.y - mean.y;
+        const float o0 = a0.x + a1.x * mm.x + (a2.x + a3.x * d0) * d0 * d0;
+        const float o1 = a0.y + a1.y * mm.y + (a2.y + a3.y * d1) * d1 * d1;
+        st_pair(dm + e * C + c, o0, o1);
+    }
+}
+// out[e] = tab[idx[e]] * (act[e] > 0 ? 1 : slope)    (TModel backward: dht = dasum[tgt] . lrelu'(ht))
+__global__ void __launch_bounds__(256) k_wide_gather_mask(const float* __restrict__ tab, const int* __restrict__ idx, int mod,
+                                                          const bf16* __restrict__ act, long long E, int C,
+                                                          bf16* __restrict__ out) {
+    const int half = C >> 1;
+    const long long total = E * half;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long e = i / half;
+        const int c = 2 * (int)(i - e * half);
+        const long long r = idx ? idx[e] : e % mod;
+        const float2 t = ld_pair(tab + r * C + c);
+        const float2 a = ld_pair(act + e * C + c);
+        st_pair(out + e * C + c, t.x * (a.x > 0.f ? 1.f : 0.1f), t.y * (a.y > 0.f ? 1.f : 0.1f));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout helpers
+// ------------------------------------------------------------------------------------------------
+template <class TI, class TO>
+__global__ void k_wide_cast(const TI* __restrict__ in, long long n, TO* __restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = (TO)(float)in[i];
+}
+// out[c][r] = in[r][c]  (bf16, in [R, C] with leading dimension ld)
+__global__ void k_wide_transpose(const bf16* __restrict__ in, int R, int C, int ld, bf16* __restrict__ out) {
+    __shared__ bf16 tile[32][34];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+        const int r = r0 + y, c = c0 + threadIdx.x;
+        if (r < R && c < C) tile[y][threadIdx.x] = in[(size_t)r * ld + c];
+    }
+    __syncthreads();
+    for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+        const int c = c0 + y, r = r0 + threadIdx.x;
+        if (r < R && c < C) out[(size_t)c * R + r] = tile[threadIdx.x][y];
+    }
+}
+
+}  // namespace pfs
