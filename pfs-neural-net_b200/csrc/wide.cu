@@ -75,6 +75,17 @@ int make_map(CUtensorMap* m, const void* base, long long rows, long long cols, l
     return PFS_OK;
 }
 
+// a row of zeros standing in for an absent gather table (the kernel then has no per-table branches)
+constexpr int kZeroRowElems = 4096;
+const __nv_bfloat16* zero_row() {
+    static __nv_bfloat16* p = nullptr;       // one per process; device memory is zero-filled once
+    if (!p) {
+        if (cudaMalloc(&p, kZeroRowElems * sizeof(__nv_bfloat16)) != cudaSuccess) return nullptr;
+        if (cudaMemset(p, 0, kZeroRowElems * sizeof(__nv_bfloat16)) != cudaSuccess) return nullptr;
+    }
+    return p;
+}
+
 template <class Kern>
 int allow_smem(Kern kern, size_t smem) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -82,21 +93,29 @@ int allow_smem(Kern kern, size_t smem) {
     return PFS_OK;
 }
 
-template <int BN, int STAGES>
-int launch_nt(const pfs_wide_gemm_args& a, const GemmEpilogue& ep, cudaStream_t st) {
-    CUtensorMap tmA, tmB, tmC;
+template <int BN, int STAGES, bool TABLES, bool MASK>
+int launch_nt_impl(const pfs_wide_gemm_args& a, const GemmEpilogue& ep, cudaStream_t st) {
+    CUtensorMap tmA, tmB;
     W_TRY(make_map(&tmA, a.A, a.M, a.K, a.lda, kGemmBM));
     W_TRY(make_map(&tmB, a.B, a.N, a.K, a.ldb, BN));
-    if (a.out_bf16) W_TRY(make_map(&tmC, a.out_bf16, a.M, a.N, a.ldc, kGemmBM));
-    else tmC = tmA;
-    auto kern = k_wide_gemm_nt<BN, STAGES>;
+    auto kern = k_wide_gemm_nt<BN, STAGES, TABLES, MASK>;
     constexpr size_t smem = GemmNtSmem<BN, STAGES>::bytes;
     W_TRY(allow_smem(kern, smem));
     const long long tiles = (long long)((a.M + kGemmBM - 1) / kGemmBM) * ((a.N + BN - 1) / BN);
     const int grid = (int)(tiles < pfs_host::sm_count() ? tiles : pfs_host::sm_count());
-    kern<<<grid, kGemmThreads, smem, st>>>(tmA, tmB, tmC, ep, a.M, a.N, a.K);
+    kern<<<grid, kGemmNtThreads, smem, st>>>(tmA, tmB, ep, (__nv_bfloat16*)a.out_bf16, (int)a.ldc, a.M, a.N, a.K);
     W_LAUNCH_CHECK("k_wide_gemm_nt");
     return PFS_OK;
+}
+
+// FULL = gathered tables / derivative mask in the epilogue; the plain variant carries no code for them
+template <int BN, int STAGES>
+int launch_nt(const pfs_wide_gemm_args& a, const GemmEpilogue& ep, cudaStream_t st) {
+    const bool tables = ep.tab0 != nullptr, mask = ep.mask != nullptr;
+    if (tables && mask) return launch_nt_impl<BN, STAGES, true, true>(a, ep, st);
+    if (tables) return launch_nt_impl<BN, STAGES, true, false>(a, ep, st);
+    if (mask) return launch_nt_impl<BN, STAGES, false, true>(a, ep, st);
+    return launch_nt_impl<BN, STAGES, false, false>(a, ep, st);
 }
 
 int tn_bn(int Kx) { return Kx > 128 ? 256 : Kx > 64 ? 128 : 64; }
@@ -183,15 +202,25 @@ int pfs_wide_gemm_nt(const pfs_wide_gemm_args* a) {
     pfs_host::mark_launch(nullptr, st);
     GemmEpilogue ep{};
     ep.bias = a->bias; ep.bias_rowscale = a->bias_rowscale;
-    ep.tab0 = a->tab0; ep.idx0 = a->idx0; ep.div0 = a->div0 > 0 ? a->div0 : 1;
-    ep.tab1 = a->tab1; ep.idx1 = a->idx1; ep.mod1 = a->mod1 > 0 ? a->mod1 : 1;
+    ep.tab0 = (const __nv_bfloat16*)a->tab0; ep.idx0 = a->idx0; ep.div0 = a->div0 > 0 ? a->div0 : 1;
+    ep.tab1 = (const __nv_bfloat16*)a->tab1; ep.idx1 = a->idx1; ep.mod1 = a->mod1 > 0 ? a->mod1 : 1;
+    ep.rows0 = 1 << 30;
+    if (ep.tab0 || ep.tab1) {
+        // a single table: the other one reads a row of zeros (dense addressing, one row)
+        W_REQUIRE(a->N <= kZeroRowElems, "gather tables wider than the zero row");
+        if (!ep.tab0) { ep.tab0 = zero_row(); ep.idx0 = nullptr; ep.div0 = 1 << 30; ep.rows0 = 1; }
+        if (!ep.tab1) { ep.tab1 = zero_row(); ep.idx1 = nullptr; ep.mod1 = 1; }
+        if (!ep.tab0 || !ep.tab1) return wfail(PFS_ERR_CUDA, "could not allocate the zero row");
+        W_REQUIRE(a->N % 4 == 0 && ((uintptr_t)ep.tab0 & 7) == 0 && ((uintptr_t)ep.tab1 & 7) == 0, "gather table alignment");
+    }
     ep.mask = (const __nv_bfloat16*)a->mask; ep.ldmask = (int)a->ldmask;
     ep.act = a->act;
     ep.out_f32 = a->out_f32; ep.ldf = (int)a->ldf;
     ep.out_bf16 = a->out_bf16 ? 1 : 0;
-    if (a->N > 128) return launch_nt<256, 4>(*a, ep, st);
-    if (a->N > 64) return launch_nt<128, 6>(*a, ep, st);
-    return launch_nt<64, 8>(*a, ep, st);
+    if (a->out_bf16) W_REQUIRE(a->ldc % 4 == 0 && ((uintptr_t)a->out_bf16 & 7) == 0, "bf16 output alignment");
+    if (a->N > 128) return launch_nt<256, 3>(*a, ep, st);
+    if (a->N > 64) return launch_nt<128, 5>(*a, ep, st);
+    return launch_nt<64, 6>(*a, ep, st);
 }
 
 size_t pfs_wide_gemm_tn_workspace(int64_t E, int32_t J, int32_t Kx) {

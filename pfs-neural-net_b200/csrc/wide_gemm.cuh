@@ -13,7 +13,7 @@
 //       edge range is split over CTAs, partials are summed in a fixed order (deterministic).
 //
 // Structure (both): warp 0 = TMA producer (128-byte-swizzled boxes into a STAGES-deep ring),
-// warp 1 = single-thread tcgen05.mma issuer, warps 2-5 = epilogue (tcgen05.ld of their 32 TMEM
+// warp 1 = single-thread tcgen05.mma issuer, remaining warps = epilogue (tcgen05.ld of their 32 TMEM
 // lanes).  NT is persistent over output tiles with a double-buffered accumulator so the epilogue
 // of tile i overlaps the MMAs of tile i+1.
 #pragma once
@@ -32,10 +32,11 @@ constexpr float kWideSlope = 0.1f;
 struct GemmEpilogue {
     const float* bias;             // [N] or null
     const float* bias_rowscale;    // [M] or null: bias[n] * bias_rowscale[m]
-    const float* tab0;             // [R0, N] fp32 row table gathered by idx0[m] (or m / div0), or null
+    const __nv_bfloat16* tab0;     // [R0, N] bf16 row table gathered by idx0[m] (or m / div0), or null
     const int* idx0;
     int div0;
-    const float* tab1;             // [R1, N] fp32 row table gathered by idx1[m] (or m % mod1), or null
+    int rows0;                     // rows of tab0 (dense addressing is clamped to it)
+    const __nv_bfloat16* tab1;     // [R1, N] bf16 row table gathered by idx1[m] (or m % mod1), or null
     const int* idx1;
     int mod1;
     const __nv_bfloat16* mask;     // [M, ldmask] saved activation: multiply by (mask > 0 ? 1 : slope)
@@ -46,31 +47,39 @@ struct GemmEpilogue {
     int out_bf16;                  // 1: bf16 output through the TMA store map
 };
 
+constexpr int kGemmEpiWarps = 16;
+constexpr int kGemmNtThreads = 64 + 32 * kGemmEpiWarps;      // warp 0 = TMA, warp 1 = MMA, warps 2..17 = epilogue
+constexpr int kGemmEpiChunk = 128;       // accumulator columns staged per epilogue round
+
 template <int BN, int STAGES>
 struct GemmNtSmem {
     static constexpr int kA = kGemmBM * kGemmBK * 2;     // 16 KB
     static constexpr int kB = BN * kGemmBK * 2;
-    static constexpr int kC = kGemmBM * 64 * 2;          // staging of a 128 x 64 bf16 output box
+    static constexpr int kC = kGemmBM * kGemmEpiChunk * 4;   // fp32 staging of a 128 x 128 accumulator block
     static constexpr int kBars = 256;
-    static constexpr size_t bytes = (size_t)STAGES * (kA + kB) + 2 * kC + kBars + 1024;   // + alignment slack
+    static constexpr size_t bytes = (size_t)STAGES * (kA + kB) + kC + kBars;
 };
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
 }
+__device__ __forceinline__ bool bf16_bits_positive(uint32_t h) { return (h & 0x8000u) == 0 && (h & 0x7FFFu) != 0; }
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(kGemmThreads, 1)
-k_wide_gemm_nt(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmC, const GemmEpilogue ep, int M, int N, int K) {
+// Epilogue in two phases per 128-column block, so that TMEM is read in its natural mapping
+// (thread = accumulator row) while every global access is coalesced (warp = one row, lane = 4 columns):
+//   phase 1: tcgen05.ld -> fp32 staging tile in shared memory (16-byte chunks XOR-swizzled by row)
+//   phase 2: staging -> registers, + bias / gathered table rows, LeakyReLU, derivative mask, bf16 / fp32 stores
+template <int BN, int STAGES, bool TABLES, bool MASK>
+__global__ void __launch_bounds__(kGemmNtThreads, 1)
+k_wide_gemm_nt(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmEpilogue ep,
+               __nv_bfloat16* __restrict__ out_bf16, int ldc, int M, int N, int K) {
     using SM = GemmNtSmem<BN, STAGES>;
-    extern __shared__ uint8_t gemm_smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gemm_smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* sA = smem;
+    extern __shared__ __align__(1024) uint8_t gemm_smem[];   // no static shared memory: the window starts 1024-aligned
+    uint8_t* sA = gemm_smem;
     uint8_t* sB = sA + STAGES * SM::kA;
-    uint8_t* sC = sB + STAGES * SM::kB;
-    uint64_t* full = reinterpret_cast<uint64_t*>(sC + 2 * SM::kC);
+    float* stg = reinterpret_cast<float*>(sB + STAGES * SM::kB);
+    uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stg) + SM::kC);
     uint64_t* empty = full + STAGES;
     uint64_t* tfull = empty + STAGES;
     uint64_t* tempty = tfull + 2;
@@ -88,12 +97,11 @@ k_wide_gemm_nt(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(tfull + s, 1);
-            mbar_init(tempty + s, 4);
+            mbar_init(tempty + s, kGemmEpiWarps);
         }
         fence_barrier_init();
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
-        tma_prefetch_desc(&tmC);
     }
     if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
     tc_fence_before();
@@ -153,117 +161,145 @@ k_wide_gemm_nt(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else {
-        // ===== epilogue warps 2..5: TMEM lanes 32 * (warp % 4) .. + 31 =====
-        const int quarter = warp & 3;
-        const int row = quarter * 32 + lane;
-        const bool issuer = threadIdx.x == 64;          // first epilogue thread issues the TMA stores
-        int it = 0, chunk = 0;
+        // ===== epilogue warps 2..17 =====
+        const int ew = warp - 2;
+        const int quarter = warp & 3;                    // TMEM lanes this warp may read: 32 * (warp % 4) ..
+        const int cq = ew >> 2;                          // which 32 of the block's 128 columns it drains
+        const int trow = quarter * 32 + lane;            // accumulator row of this thread in phase 1
+        constexpr int kRows = kGemmBM / kGemmEpiWarps;   // rows per warp in phase 2: ew, ew + 16, ...
+        // phase-1 / phase-2 staging addresses (16-byte chunks XOR-swizzled by the row; rows ew + 16 rr share ew's low bits)
+        float4* const p1row = reinterpret_cast<float4*>(stg + trow * kGemmEpiChunk);
+        const float4* const p2row = reinterpret_cast<const float4*>(stg + ew * kGemmEpiChunk) + ((lane & ~7) | ((lane ^ ew) & 7));
+        int it = 0;
         for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
             const int as = it & 1;
             const uint32_t aph = (it >> 1) & 1;
             const int m0 = (t / nt) * kGemmBM, n0 = (t % nt) * BN;
-            const int m = m0 + row;
-            const bool row_ok = m < M;
+            const int ncols = min(BN, N - n0);
+            // per-row addressing, once per tile: rows beyond M are clamped for the loads and masked at the stores
+            int mrow[kRows];
+            uint32_t off0[kRows], off1[kRows];
+#pragma unroll
+            for (int rr = 0; rr < kRows; ++rr) mrow[rr] = min(m0 + ew + kGemmEpiWarps * rr, M - 1);
+            if constexpr (TABLES) {
+                if (ep.idx0) {
+#pragma unroll
+                    for (int rr = 0; rr < kRows; ++rr) off0[rr] = (uint32_t)__ldg(ep.idx0 + mrow[rr]) * (uint32_t)N;
+                } else {
+#pragma unroll
+                    for (int rr = 0; rr < kRows; ++rr) off0[rr] = (uint32_t)min(mrow[rr] / ep.div0, ep.rows0 - 1) * (uint32_t)N;
+                }
+                if (ep.idx1) {
+#pragma unroll
+                    for (int rr = 0; rr < kRows; ++rr) off1[rr] = (uint32_t)__ldg(ep.idx1 + mrow[rr]) * (uint32_t)N;
+                } else {
+#pragma unroll
+                    for (int rr = 0; rr < kRows; ++rr) off1[rr] = (uint32_t)(mrow[rr] % ep.mod1) * (uint32_t)N;
+                }
+            }
+            const bool last_rows_ok = m0 + kGemmBM <= M;
             mbar_wait(tfull + as, aph);
             tc_fence_after();
-            const float* t0 = nullptr;
-            const float* t1 = nullptr;
-            float rs = 1.f;
-            if (row_ok) {
-                if (ep.tab0) t0 = ep.tab0 + (size_t)(ep.idx0 ? ep.idx0[m] : m / ep.div0) * N;
-                if (ep.tab1) t1 = ep.tab1 + (size_t)(ep.idx1 ? ep.idx1[m] : m % ep.mod1) * N;
-                if (ep.bias_rowscale) rs = ep.bias_rowscale[m];
-            }
-            const int ncols = min(BN, N - n0);
-            for (int c64 = 0; c64 < ncols; c64 += 64, ++chunk) {
-                uint8_t* stg = sC + (chunk & 1) * SM::kC;
-                if (ep.out_bf16) {
-                    if (issuer) tma_store_wait_read<1>();    // the store that last read this buffer is done
-                    named_bar_sync(1, 128);
-                }
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int c0 = c64 + 32 * h;
-                    if (c0 >= ncols) break;
+            for (int c0 = 0; c0 < ncols; c0 += kGemmEpiChunk) {
+                named_bar_sync(1, 32 * kGemmEpiWarps);   // phase 2 of the previous block has left the staging tile
+                // ---- phase 1: TMEM -> staging ----
+                if (c0 + 32 * cq < ncols) {
                     float v[32];
-                    tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + as * BN + c0, v);
-                    const int n = n0 + c0;
-                    if (row_ok) {
+                    tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + as * BN + c0 + 32 * cq, v);
 #pragma unroll
-                        for (int q = 0; q < 32; q += 4) {
-                            if (n + q + 4 <= N) {
-                                if (ep.bias) {
-                                    const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n + q));
-                                    v[q] = fmaf(b.x, rs, v[q]); v[q + 1] = fmaf(b.y, rs, v[q + 1]);
-                                    v[q + 2] = fmaf(b.z, rs, v[q + 2]); v[q + 3] = fmaf(b.w, rs, v[q + 3]);
-                                }
-                                if (t0) {
-                                    const float4 b = __ldg(reinterpret_cast<const float4*>(t0 + n + q));
-                                    v[q] += b.x; v[q + 1] += b.y; v[q + 2] += b.z; v[q + 3] += b.w;
-                                }
-                                if (t1) {
-                                    const float4 b = __ldg(reinterpret_cast<const float4*>(t1 + n + q));
-                                    v[q] += b.x; v[q + 1] += b.y; v[q + 2] += b.z; v[q + 3] += b.w;
-                                }
-                            }
-                        }
-                        if (ep.act) {
-#pragma unroll
-                            for (int q = 0; q < 32; ++q) v[q] = fmaxf(v[q], kWideSlope * v[q]);
-                        }
-                        if (ep.mask) {
-                            const __nv_bfloat16* mp = ep.mask + (size_t)m * ep.ldmask + n;
-#pragma unroll
-                            for (int q = 0; q < 32; q += 8) {
-                                if (n + q + 8 <= N) {
-                                    const uint4 w = __ldg(reinterpret_cast<const uint4*>(mp + q));
-                                    const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-                                    for (int e = 0; e < 4; ++e) {
-                                        // bf16 sign/zero test on the raw bits: value > 0 <=> not negative and not zero
-                                        const uint32_t lo = ww[e] & 0xFFFFu, hi = ww[e] >> 16;
-                                        const bool plo = (lo & 0x8000u) == 0 && (lo & 0x7FFFu) != 0;
-                                        const bool phi = (hi & 0x8000u) == 0 && (hi & 0x7FFFu) != 0;
-                                        v[q + 2 * e] *= plo ? 1.f : kWideSlope;
-                                        v[q + 2 * e + 1] *= phi ? 1.f : kWideSlope;
-                                    }
-                                }
-                            }
-                        }
-                        if (ep.out_f32) {
-                            float* op = ep.out_f32 + (size_t)m * ep.ldf + n;
-#pragma unroll
-                            for (int q = 0; q < 32; q += 4)
-                                if (n + q + 4 <= N)
-                                    *reinterpret_cast<float4*>(op + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
-                        }
-                    }
-                    if (ep.out_bf16) {
-                        // staging row = 128 bytes (64 bf16), 16-byte chunk c stored at c ^ (row % 8): the
-                        // 128-byte swizzle the TMA store map expects, and bank-conflict free
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const uint4 w = make_uint4(pack_bf16(v[8 * c], v[8 * c + 1]), pack_bf16(v[8 * c + 2], v[8 * c + 3]),
-                                                       pack_bf16(v[8 * c + 4], v[8 * c + 5]), pack_bf16(v[8 * c + 6], v[8 * c + 7]));
-                            const int cc = (4 * h + c) ^ (row & 7);
-                            *reinterpret_cast<uint4*>(stg + row * 128 + cc * 16) = w;
-                        }
+                    for (int q = 0; q < 8; ++q) {
+                        const int chunk = 8 * cq + q;
+                        p1row[(chunk & ~7) | ((chunk ^ trow) & 7)] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                     }
                 }
-                if (ep.out_bf16) {
-                    fence_proxy_async();
-                    named_bar_sync(1, 128);
-                    if (issuer) {
-                        tma_store_2d(&tmC, stg, n0 + c64, m0);
-                        tma_store_commit();
+                if (c0 + kGemmEpiChunk >= ncols) {       // accumulator fully drained: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty + as);
+                }
+                named_bar_sync(1, 32 * kGemmEpiWarps);
+                // ---- phase 2: warp = row, lane = 4 consecutive columns; straight-line, loads first ----
+                const int col = c0 + 4 * lane;
+                const int n = n0 + col;
+                if (col < ncols && n + 4 <= N) {
+                    float4 acc[kRows];
+#pragma unroll
+                    for (int rr = 0; rr < kRows; ++rr) acc[rr] = p2row[rr * (kGemmEpiWarps * kGemmEpiChunk / 4)];
+                    uint2 t0v[kRows], t1v[kRows], mkv[kRows];
+                    if constexpr (TABLES) {
+                        const __nv_bfloat16* t0p = ep.tab0 + n;
+                        const __nv_bfloat16* t1p = ep.tab1 + n;
+#pragma unroll
+                        for (int rr = 0; rr < kRows; ++rr) {
+                            t0v[rr] = __ldg(reinterpret_cast<const uint2*>(t0p + off0[rr]));
+                            t1v[rr] = __ldg(reinterpret_cast<const uint2*>(t1p + off1[rr]));
+                        }
+                    }
+                    if constexpr (MASK) {
+                        const __nv_bfloat16* mp = ep.mask + n;
+#pragma unroll
+                        for (int rr = 0; rr < kRows; ++rr)
+                            mkv[rr] = __ldg(reinterpret_cast<const uint2*>(mp + (size_t)mrow[rr] * ep.ldmask));
+                    }
+                    if (ep.bias) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
+                        if (ep.bias_rowscale) {
+#pragma unroll
+                            for (int rr = 0; rr < kRows; ++rr) {
+                                const float rs = __ldg(ep.bias_rowscale + mrow[rr]);
+                                acc[rr].x = fmaf(b.x, rs, acc[rr].x); acc[rr].y = fmaf(b.y, rs, acc[rr].y);
+                                acc[rr].z = fmaf(b.z, rs, acc[rr].z); acc[rr].w = fmaf(b.w, rs, acc[rr].w);
+                            }
+                        } else {
+#pragma unroll
+                            for (int rr = 0; rr < kRows; ++rr) {
+                                acc[rr].x += b.x; acc[rr].y += b.y; acc[rr].z += b.z; acc[rr].w += b.w;
+                            }
+                        }
+                    }
+                    if constexpr (TABLES) {
+#pragma unroll
+                        for (int rr = 0; rr < kRows; ++rr) {
+                            acc[rr].x += __uint_as_float(t0v[rr].x << 16) + __uint_as_float(t1v[rr].x << 16);
+                            acc[rr].y += __uint_as_float(t0v[rr].x & 0xFFFF0000u) + __uint_as_float(t1v[rr].x & 0xFFFF0000u);
+                            acc[rr].z += __uint_as_float(t0v[rr].y << 16) + __uint_as_float(t1v[rr].y << 16);
+                            acc[rr].w += __uint_as_float(t0v[rr].y & 0xFFFF0000u) + __uint_as_float(t1v[rr].y & 0xFFFF0000u);
+                        }
+                    }
+                    if (ep.act) {
+#pragma unroll
+                        for (int rr = 0; rr < kRows; ++rr) {
+                            acc[rr].x = fmaxf(acc[rr].x, kWideSlope * acc[rr].x); acc[rr].y = fmaxf(acc[rr].y, kWideSlope * acc[rr].y);
+                            acc[rr].z = fmaxf(acc[rr].z, kWideSlope * acc[rr].z); acc[rr].w = fmaxf(acc[rr].w, kWideSlope * acc[rr].w);
+                        }
+                    }
+                    if constexpr (MASK) {
+#pragma unroll
+                        for (int rr = 0; rr < kRows; ++rr) {
+                            acc[rr].x *= bf16_bits_positive(mkv[rr].x & 0xFFFFu) ? 1.f : kWideSlope;
+                            acc[rr].y *= bf16_bits_positive(mkv[rr].x >> 16) ? 1.f : kWideSlope;
+                            acc[rr].z *= bf16_bits_positive(mkv[rr].y & 0xFFFFu) ? 1.f : kWideSlope;
+                            acc[rr].w *= bf16_bits_positive(mkv[rr].y >> 16) ? 1.f : kWideSlope;
+                        }
+                    }
+                    if (out_bf16) {
+                        __nv_bfloat16* op = out_bf16 + (size_t)(m0 + ew) * ldc + n;
+#pragma unroll
+                        for (int rr = 0; rr < kRows; ++rr)
+                            if (last_rows_ok || m0 + ew + kGemmEpiWarps * rr < M)
+                                *reinterpret_cast<uint2*>(op + (size_t)rr * kGemmEpiWarps * ldc) =
+                                    make_uint2(pack_bf16(acc[rr].x, acc[rr].y), pack_bf16(acc[rr].z, acc[rr].w));
+                    }
+                    if (ep.out_f32) {
+                        float* op = ep.out_f32 + (size_t)(m0 + ew) * ep.ldf + n;
+#pragma unroll
+                        for (int rr = 0; rr < kRows; ++rr)
+                            if (last_rows_ok || m0 + ew + kGemmEpiWarps * rr < M)
+                                *reinterpret_cast<float4*>(op + (size_t)rr * kGemmEpiWarps * ep.ldf) = acc[rr];
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty + as);
         }
-        if (issuer) tma_store_wait<0>();
     }
     tc_fence_before();
     __syncthreads();
@@ -278,7 +314,7 @@ template <int BN, int STAGES>
 struct GemmTnSmem {
     static constexpr int kA = kGemmBK * kGemmBM * 2;     // 64 rows x 128 features: two 8 KB boxes
     static constexpr int kB = kGemmBK * BN * 2;          // BN / 64 boxes of 8 KB
-    static constexpr size_t bytes = (size_t)STAGES * (kA + kB) + 256 + 1024;
+    static constexpr size_t bytes = (size_t)STAGES * (kA + kB) + 256;
 };
 
 template <int BN, int STAGES>
@@ -286,9 +322,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 k_wide_gemm_tn(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmX,
                float* __restrict__ partial, int E, int J, int Kx, int rows_per_split) {
     using SM = GemmTnSmem<BN, STAGES>;
-    extern __shared__ uint8_t gemm_smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gemm_smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* sA = smem;
+    extern __shared__ __align__(1024) uint8_t gemm_smem[];
+    uint8_t* sA = gemm_smem;
     uint8_t* sB = sA + STAGES * SM::kA;
     uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * SM::kB);
     uint64_t* empty = full + STAGES;
