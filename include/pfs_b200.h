@@ -261,8 +261,8 @@ typedef struct pfs_wide_gemm_args {
     int32_t M, N, K;
     const float* bias;                           /* [N] or NULL */
     const float* bias_rowscale;                  /* [M] or NULL */
-    const void* tab0; const int32_t* idx0; int32_t div0;    /* bf16 [*,N] or NULL */
-    const void* tab1; const int32_t* idx1; int32_t mod1;    /* bf16 [*,N] or NULL */
+    const float* tab0; const int32_t* idx0; int32_t div0;   /* fp32 [*,N] or NULL */
+    const float* tab1; const int32_t* idx1; int32_t mod1;   /* fp32 [*,N] or NULL */
     const void* mask; int64_t ldmask;            /* bf16 [M,ldmask] or NULL */
     int32_t act;
     void* out_bf16; int64_t ldc;                 /* or NULL */

@@ -89,9 +89,11 @@ def batch_norm(sd, prefix, x, training, buffers=None):
     return (x - mean) / torch.sqrt(var + BN_EPS) * w + b
 
 
-def rms_norm(weight, x):
-    """torch.nn.RMSNorm(F) with eps=None -> finfo(x.dtype).eps (reference src/gnn.py:203)."""
-    eps = torch.finfo(x.dtype).eps
+def rms_norm(weight, x, eps=None):
+    """torch.nn.RMSNorm(F) with eps=None -> finfo(x.dtype).eps (reference src/gnn.py:203).  `eps` overrides
+    it so that an fp64 run can stand in for the reference executed in another dtype (bf16 parity)."""
+    if eps is None:
+        eps = torch.finfo(x.dtype).eps
     return x * torch.rsqrt(x.pow(2).mean(dim=-1, keepdim=True) + eps) * weight
 
 
@@ -146,18 +148,18 @@ def t_model(sd, prefix, x_s, x_t, edge_index, x_e, u, training=True, normed=True
     return batch_norm(sd, prefix + "norm.", y, training, buffers) if normed else y
 
 
-def global_model(sd, prefix, x_s, x_t, u, normed=True):
+def global_model(sd, prefix, x_s, x_t, u, normed=True, rms_eps=None):
     """reference src/gnn.py:195-223; RMSNorm applied twice for the same Sequential reason."""
     h = torch.cat([u, x_s.mean(dim=0, keepdim=True), x_t.mean(dim=0, keepdim=True)], dim=-1)
     y = mlp(sd, prefix, h)
     if not normed:
         return y
     w = sd[prefix + "norm.weight"]
-    return rms_norm(w, rms_norm(w, y))
+    return rms_norm(w, rms_norm(w, y, rms_eps), rms_eps)
 
 
 def block(sd, prefix, edge_index, x_s, x_t, x_e, u, training=True, normed=True, buffers=None,
-          e_model=True, s_model_on=True, t_model_on=True, u_model=True):
+          e_model=True, s_model_on=True, t_model_on=True, u_model=True, rms_eps=None):
     """reference src/gnn.py:243-259: edge -> source -> target -> global, each stage consuming
     the previous stage's outputs."""
     if e_model:
@@ -167,7 +169,7 @@ def block(sd, prefix, edge_index, x_s, x_t, x_e, u, training=True, normed=True, 
     if t_model_on:
         x_t = t_model(sd, prefix + "t_model.", x_s, x_t, edge_index, x_e, u, training, normed, buffers)
     if u_model:
-        u = global_model(sd, prefix + "global_model.", x_s, x_t, u, normed)
+        u = global_model(sd, prefix + "global_model.", x_s, x_t, u, normed, rms_eps)
     return x_s, x_t, x_e, u
 
 

@@ -77,11 +77,11 @@ int make_map(CUtensorMap* m, const void* base, long long rows, long long cols, l
 
 // a row of zeros standing in for an absent gather table (the kernel then has no per-table branches)
 constexpr int kZeroRowElems = 4096;
-const __nv_bfloat16* zero_row() {
-    static __nv_bfloat16* p = nullptr;       // one per process; device memory is zero-filled once
+const float* zero_row() {
+    static float* p = nullptr;               // one per process; device memory is zero-filled once
     if (!p) {
-        if (cudaMalloc(&p, kZeroRowElems * sizeof(__nv_bfloat16)) != cudaSuccess) return nullptr;
-        if (cudaMemset(p, 0, kZeroRowElems * sizeof(__nv_bfloat16)) != cudaSuccess) return nullptr;
+        if (cudaMalloc(&p, kZeroRowElems * sizeof(float)) != cudaSuccess) return nullptr;
+        if (cudaMemset(p, 0, kZeroRowElems * sizeof(float)) != cudaSuccess) return nullptr;
     }
     return p;
 }
@@ -202,8 +202,8 @@ int pfs_wide_gemm_nt(const pfs_wide_gemm_args* a) {
     pfs_host::mark_launch(nullptr, st);
     GemmEpilogue ep{};
     ep.bias = a->bias; ep.bias_rowscale = a->bias_rowscale;
-    ep.tab0 = (const __nv_bfloat16*)a->tab0; ep.idx0 = a->idx0; ep.div0 = a->div0 > 0 ? a->div0 : 1;
-    ep.tab1 = (const __nv_bfloat16*)a->tab1; ep.idx1 = a->idx1; ep.mod1 = a->mod1 > 0 ? a->mod1 : 1;
+    ep.tab0 = a->tab0; ep.idx0 = a->idx0; ep.div0 = a->div0 > 0 ? a->div0 : 1;
+    ep.tab1 = a->tab1; ep.idx1 = a->idx1; ep.mod1 = a->mod1 > 0 ? a->mod1 : 1;
     ep.rows0 = 1 << 30;
     if (ep.tab0 || ep.tab1) {
         // a single table: the other one reads a row of zeros (dense addressing, one row)
@@ -211,7 +211,7 @@ int pfs_wide_gemm_nt(const pfs_wide_gemm_args* a) {
         if (!ep.tab0) { ep.tab0 = zero_row(); ep.idx0 = nullptr; ep.div0 = 1 << 30; ep.rows0 = 1; }
         if (!ep.tab1) { ep.tab1 = zero_row(); ep.idx1 = nullptr; ep.mod1 = 1; }
         if (!ep.tab0 || !ep.tab1) return wfail(PFS_ERR_CUDA, "could not allocate the zero row");
-        W_REQUIRE(a->N % 4 == 0 && ((uintptr_t)ep.tab0 & 7) == 0 && ((uintptr_t)ep.tab1 & 7) == 0, "gather table alignment");
+        W_REQUIRE(a->N % 4 == 0 && ((uintptr_t)ep.tab0 & 15) == 0 && ((uintptr_t)ep.tab1 & 15) == 0, "gather table alignment");
     }
     ep.mask = (const __nv_bfloat16*)a->mask; ep.ldmask = (int)a->ldmask;
     ep.act = a->act;

@@ -32,11 +32,11 @@ constexpr float kWideSlope = 0.1f;
 struct GemmEpilogue {
     const float* bias;             // [N] or null
     const float* bias_rowscale;    // [M] or null: bias[n] * bias_rowscale[m]
-    const __nv_bfloat16* tab0;     // [R0, N] bf16 row table gathered by idx0[m] (or m / div0), or null
+    const float* tab0;             // [R0, N] fp32 row table gathered by idx0[m] (or m / div0), or null
     const int* idx0;
     int div0;
     int rows0;                     // rows of tab0 (dense addressing is clamped to it)
-    const __nv_bfloat16* tab1;     // [R1, N] bf16 row table gathered by idx1[m] (or m % mod1), or null
+    const float* tab1;             // [R1, N] fp32 row table gathered by idx1[m] (or m % mod1), or null
     const int* idx1;
     int mod1;
     const __nv_bfloat16* mask;     // [M, ldmask] saved activation: multiply by (mask > 0 ? 1 : slope)
@@ -225,16 +225,7 @@ k_wide_gemm_nt(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     float4 acc[kRows];
 #pragma unroll
                     for (int rr = 0; rr < kRows; ++rr) acc[rr] = p2row[rr * (kGemmEpiWarps * kGemmEpiChunk / 4)];
-                    uint2 t0v[kRows], t1v[kRows], mkv[kRows];
-                    if constexpr (TABLES) {
-                        const __nv_bfloat16* t0p = ep.tab0 + n;
-                        const __nv_bfloat16* t1p = ep.tab1 + n;
-#pragma unroll
-                        for (int rr = 0; rr < kRows; ++rr) {
-                            t0v[rr] = __ldg(reinterpret_cast<const uint2*>(t0p + off0[rr]));
-                            t1v[rr] = __ldg(reinterpret_cast<const uint2*>(t1p + off1[rr]));
-                        }
-                    }
+                    uint2 mkv[kRows];
                     if constexpr (MASK) {
                         const __nv_bfloat16* mp = ep.mask + n;
 #pragma unroll
@@ -258,12 +249,23 @@ k_wide_gemm_nt(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                     if constexpr (TABLES) {
+                        // fp32 tables (a bf16 table would flip LeakyReLU signs near zero); gathers in batches of
+                        // four rows: eight 16-byte loads in flight per lane
+                        const float* t0p = ep.tab0 + n;
+                        const float* t1p = ep.tab1 + n;
 #pragma unroll
-                        for (int rr = 0; rr < kRows; ++rr) {
-                            acc[rr].x += __uint_as_float(t0v[rr].x << 16) + __uint_as_float(t1v[rr].x << 16);
-                            acc[rr].y += __uint_as_float(t0v[rr].x & 0xFFFF0000u) + __uint_as_float(t1v[rr].x & 0xFFFF0000u);
-                            acc[rr].z += __uint_as_float(t0v[rr].y << 16) + __uint_as_float(t1v[rr].y << 16);
-                            acc[rr].w += __uint_as_float(t0v[rr].y & 0xFFFF0000u) + __uint_as_float(t1v[rr].y & 0xFFFF0000u);
+                        for (int r4 = 0; r4 < kRows; r4 += 4) {
+                            float4 t0v[4], t1v[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                t0v[q] = __ldg(reinterpret_cast<const float4*>(t0p + off0[r4 + q]));
+                                t1v[q] = __ldg(reinterpret_cast<const float4*>(t1p + off1[r4 + q]));
+                            }
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                acc[r4 + q].x += t0v[q].x + t1v[q].x; acc[r4 + q].y += t0v[q].y + t1v[q].y;
+                                acc[r4 + q].z += t0v[q].z + t1v[q].z; acc[r4 + q].w += t0v[q].w + t1v[q].w;
+                            }
                         }
                     }
                     if (ep.act) {

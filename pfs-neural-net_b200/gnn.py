@@ -17,6 +17,7 @@ import torch
 import torch.nn.functional as Fn
 
 from . import functional as pf
+from . import wide as pw
 from .topology import get_topology
 
 # same device pick as reference src/config.py:4-9 (captured at import by BipartiteData there)
@@ -93,6 +94,18 @@ def _batched(x_s, x_t, edge_attr, u):
     return single, x_s, x_t, edge_attr, u
 
 
+def _wide_args(x_s, x_t, edge_attr, u):
+    """bf16 tensors of one graph for the wide (tensor-core) path, or None for the fp32 kernels."""
+    if not pw.supported(edge_attr.shape[-1], edge_attr.dtype):
+        return None
+    if x_s.dim() != 2:
+        raise RuntimeError("the bf16 wide path takes one graph per call (2-D tensors); batch graphs with dp.py")
+    if u.shape[0] != 1:
+        raise RuntimeError("global features with %d rows cannot be expanded over one graph "
+                           "(reference src/gnn.py:100 fails the same way)" % u.shape[0])
+    return x_s, x_t, edge_attr, u.reshape(1, -1)
+
+
 def _norm_tensors(mod):
     norm = mod.norm if isinstance(mod.norm, torch.nn.Module) else None
     if norm is None:
@@ -112,6 +125,12 @@ class EdgeModel(MLP):
         self.norm = torch.nn.BatchNorm1d(Fdim) if normed else (lambda x: x)
 
     def forward(self, x_s, x_t, edge_index, edge_attr, u):
+        wide = _wide_args(x_s, x_t, edge_attr, u)
+        if wide is not None:
+            topo = get_topology(edge_index, x_s.shape[0], x_t.shape[0])
+            normed, gamma, beta, rm, rv, nbt = _norm_tensors(self)
+            return pw.WideEdgeFunction.apply(topo, self.training, normed, *wide, self[0].weight, self[0].bias,
+                                             self[2].weight, self[2].bias, gamma, beta, rm, rv, nbt)
         single, x_s, x_t, edge_attr, u = _batched(x_s, x_t, edge_attr, u)
         topo = get_topology(edge_index, x_s.shape[1], x_t.shape[1])
         normed, gamma, beta, rm, rv, nbt = _norm_tensors(self)
@@ -132,6 +151,13 @@ class SModel(torch.nn.Module):
         self.norm = torch.nn.BatchNorm1d(Fdim) if normed else (lambda x: x)
 
     def forward(self, x_s, x_t, edge_index, edge_attr, u):
+        wide = _wide_args(x_s, x_t, edge_attr, u)
+        if wide is not None:
+            topo = get_topology(edge_index, x_s.shape[0], x_t.shape[0])
+            normed, gamma, beta, rm, rv, nbt = _norm_tensors(self)
+            m1, m2 = self.node_mlp_1, self.node_mlp_2
+            return pw.WideSourceFunction.apply(topo, self.training, normed, *wide, m1[0].weight, m1[0].bias, m1[2].weight,
+                               m1[2].bias, m2[0].weight, m2[0].bias, m2[2].weight, m2[2].bias, gamma, beta, rm, rv, nbt)
         single, x_s, x_t, edge_attr, u = _batched(x_s, x_t, edge_attr, u)
         topo = get_topology(edge_index, x_s.shape[1], x_t.shape[1])
         normed, gamma, beta, rm, rv, nbt = _norm_tensors(self)
@@ -154,6 +180,13 @@ class TModel(torch.nn.Module):
         self.norm = torch.nn.BatchNorm1d(Fdim) if normed else (lambda x: x)
 
     def forward(self, x_s, x_t, edge_index, edge_attr, u):
+        wide = _wide_args(x_s, x_t, edge_attr, u)
+        if wide is not None:
+            topo = get_topology(edge_index, x_s.shape[0], x_t.shape[0])
+            normed, gamma, beta, rm, rv, nbt = _norm_tensors(self)
+            m1, m2 = self.node_mlp_1, self.node_mlp_2
+            return pw.WideTargetFunction.apply(topo, self.training, normed, *wide, m1[0].weight, m1[0].bias, m1[2].weight,
+                               m1[2].bias, m2[0].weight, m2[0].bias, m2[2].weight, m2[2].bias, gamma, beta, rm, rv, nbt)
         single, x_s, x_t, edge_attr, u = _batched(x_s, x_t, edge_attr, u)
         topo = get_topology(edge_index, x_s.shape[1], x_t.shape[1])
         normed, gamma, beta, rm, rv, nbt = _norm_tensors(self)
@@ -174,6 +207,14 @@ class GlobalModel(MLP):
         self.norm = torch.nn.RMSNorm(Fdim) if normed else (lambda x: x)
 
     def forward(self, x_s, x_t, edge_index, edge_attr, u):
+        if pw.supported(x_s.shape[-1], x_s.dtype):
+            if x_s.dim() != 2:
+                raise RuntimeError("the bf16 wide path takes one graph per call (2-D tensors)")
+            normed = isinstance(self.norm, torch.nn.Module)
+            # nn.RMSNorm(eps=None) uses finfo(input dtype).eps (reference src/gnn.py:203 run in bf16)
+            return pw.WideGlobalFunction.apply(normed, x_s, x_t, u, self[0].weight, self[0].bias, self[2].weight,
+                                               self[2].bias, self.norm.weight if normed else None,
+                                               float(torch.finfo(u.dtype).eps))
         single = x_s.dim() == 2
         if single:
             x_s, x_t = x_s.unsqueeze(0), x_t.unsqueeze(0)

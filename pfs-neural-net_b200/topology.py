@@ -30,13 +30,27 @@ class Topology:
         flag = torch.zeros(1, dtype=torch.int32, device=self.device)
         _abi.check(lib.pfs_detect_dense(self.edge_index.data_ptr(), self.E, self.S, self.T, flag.data_ptr(), stream),
                    "pfs_detect_dense")
-        self.dense = bool(flag.item()) and self.T <= _abi.PFS_TILE_EDGES
+        self.canonical = bool(flag.item())            # e = k*T + i (reference src/train.py:94)
+        self.dense = self.canonical and self.T <= _abi.PFS_TILE_EDGES   # what the narrow fp32 kernels call dense
         self.arrays = None
         self.ntiles = 0
-        self.max_degree = self.T if self.dense else None
-        if not self.dense:
-            self._build_csr(lib, stream)
+        self.max_degree = self.T if self.canonical else None
+        self._wide = None
         self._workspaces = {}
+
+    def csr(self):
+        """int32 CSR / CSC arrays of pfs_build_topology, built on first use and cached."""
+        if self.arrays is None:
+            lib = _abi.load_library()
+            self._build_csr(lib, torch.cuda.current_stream(self.device).cuda_stream)
+        return self.arrays
+
+    def wide(self):
+        """Segments / index arrays for the wide (bf16, tensor-core) path."""
+        if self._wide is None:
+            from .wide import WideTopology
+            self._wide = WideTopology(self)
+        return self._wide
 
     def _build_csr(self, lib, stream):
         lo = int(self.edge_index.min().item())
@@ -60,9 +74,6 @@ class Topology:
             a["tile_fibre"].data_ptr(), scalars[0:1].data_ptr(), scalars[1:2].data_ptr(), tmp.data_ptr(), tmp_bytes,
             stream), "pfs_build_topology")
         self.ntiles, self.max_degree = (int(v) for v in scalars.tolist())
-        if self.max_degree > _abi.PFS_TILE_EDGES:
-            raise _abi.PfsError("a fibre has %d edges; this build handles at most %d per fibre"
-                                % (self.max_degree, _abi.PFS_TILE_EDGES))
         self.arrays = a
 
     def struct(self, G, F):
@@ -70,7 +81,10 @@ class Topology:
         t.layout = _abi.PFS_LAYOUT_DENSE if self.dense else _abi.PFS_LAYOUT_CSR
         t.G, t.F, t.S, t.T, t.E = int(G), int(F), self.S, self.T, self.E
         if not self.dense:
-            a = self.arrays
+            a = self.csr()
+            if self.max_degree > _abi.PFS_TILE_EDGES:
+                raise _abi.PfsError("a fibre has %d edges; the fp32 kernels handle at most %d per fibre (the bf16 wide "
+                                    "path has no such limit)" % (self.max_degree, _abi.PFS_TILE_EDGES))
             t.csr_rowptr, t.csr_eid = a["csr_rowptr"].data_ptr(), a["csr_eid"].data_ptr()
             t.csr_src, t.csr_tgt = a["csr_src"].data_ptr(), a["csr_tgt"].data_ptr()
             t.tile_fibre, t.ntiles = a["tile_fibre"].data_ptr(), self.ntiles

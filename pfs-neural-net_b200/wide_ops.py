@@ -65,11 +65,11 @@ def gemm_nt(A, B, bias=None, bias_rowscale=None, tab0=None, idx0=None, div0=0, t
     if B.shape[1] != K:
         raise _abi.PfsError("gemm_nt: A %s vs B %s" % (tuple(A.shape), tuple(B.shape)))
     dev = A.device
-    for t, n in ((bias, "bias"), (bias_rowscale, "bias_rowscale")):
+    for t, n in ((bias, "bias"), (bias_rowscale, "bias_rowscale"), (tab0, "tab0"), (tab1, "tab1")):
         _chk(t, F32, n)
     for t, n in ((idx0, "idx0"), (idx1, "idx1")):
         _chk(t, torch.int32, n)
-    _chk(mask, BF16, "mask"), _chk(tab0, BF16, "tab0"), _chk(tab1, BF16, "tab1")
+    _chk(mask, BF16, "mask")
     if want in ("bf16", "both") and out_bf16 is None:
         out_bf16 = torch.empty(M, N, dtype=BF16, device=dev)
     if want in ("f32", "both") and out_f32 is None:

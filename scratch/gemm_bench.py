@@ -19,7 +19,7 @@ for (M, N, K, name) in [(E, 512, 128, "E1"), (E, 128, 512, "E2"), (E, 256, 128, 
     ms = bench(lambda: torch.matmul(A, B.T, out=out))
     print("   cuBLAS same: %.3f ms  %.1f TFLOP/s" % (ms, fl / ms / 1e9))
 T = 512
-t0 = torch.randn(E // T, 512, device=dev).bfloat16(); t1 = torch.randn(T, 512, device=dev).bfloat16()
+t0 = torch.randn(E // T, 512, device=dev); t1 = torch.randn(T, 512, device=dev)
 A = torch.randn(E, 128, device=dev).bfloat16(); B = torch.randn(512, 128, device=dev).bfloat16()
 out = torch.empty(E, 512, device=dev, dtype=torch.bfloat16)
 ms = bench(lambda: wo.gemm_nt(A, B, tab0=t0, div0=T, tab1=t1, mod1=T, act=True, out_bf16=out, want="none"))

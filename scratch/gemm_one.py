@@ -6,7 +6,7 @@ mode = sys.argv[1] if len(sys.argv) > 1 else "plain"
 A = torch.randn(E, 128, device=dev).bfloat16(); B = torch.randn(512, 128, device=dev).bfloat16()
 out = torch.empty(E, 512, device=dev, dtype=torch.bfloat16)
 T = 512
-t0 = torch.randn(E // T, 512, device=dev).bfloat16(); t1 = torch.randn(T, 512, device=dev).bfloat16()
+t0 = torch.randn(E // T, 512, device=dev); t1 = torch.randn(T, 512, device=dev)
 for _ in range(3):
     if mode == "plain":
         wo.gemm_nt(A, B, out_bf16=out, want="none")

@@ -43,8 +43,8 @@ def test_gemm_nt_epilogue():
     B = torch.randn(N, K, generator=g).to(dev).bfloat16()
     bias = torch.randn(N, generator=g).to(dev)
     rs = torch.rand(E, generator=g).to(dev)
-    t0 = torch.randn(S, N, generator=g).to(dev).bfloat16()
-    t1 = torch.randn(T, N, generator=g).to(dev).bfloat16()
+    t0 = torch.randn(S, N, generator=g).to(dev)
+    t1 = torch.randn(T, N, generator=g).to(dev)
     mask = torch.randn(E, N, generator=g).to(dev).bfloat16()
     mask[0, :8] = 0
     src = torch.arange(E, device=dev) // T
