@@ -59,6 +59,12 @@ def parse_args():
     ap.add_argument("--classes", type=int, default=12)
     ap.add_argument("--fdim", type=int, default=10)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget of the cpu_baseline sample")
+    ap.add_argument("--workload", default="c3", choices=["c3", "c4", "c5"],
+                    help="c3: 256 x 2394x12 graphs, Fdim 10 fp32 (headline); c4: one 12500*N x 512 graph, Fdim 128 bf16, "
+                         "fibre-sharded over the N GPUs; c5: 10%% sparse 100000x512 edge list, Fdim 128 bf16 (CSR/CSC path)")
+    ap.add_argument("--wide-fibres", type=int, default=12500, help="c4: fibres per GPU")
+    ap.add_argument("--wide-classes", type=int, default=512)
+    ap.add_argument("--wide-fdim", type=int, default=128)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
@@ -361,9 +367,224 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------
+# wide workloads (C4 / C5b): one large graph, Fdim 128, bf16, tensor-core path
+# ---------------------------------------------------------------------------------------------
+WIDE_MAC_PER_EDGE_F2 = 48     # executed: fwd 16 F^2 (five GEMMs), bwd 32 F^2 (input + weight gradients), DESIGN.md 6
+WIDE_MAC_PER_FIBRE_F2 = 318
+
+
+def wide_graph(args, rank, world, dev):
+    """(edge_index of this rank's shard, S_local, T, E_local, description)."""
+    T, S = args.wide_classes, args.wide_fibres
+    if args.workload == "c4":
+        ei = torch.cartesian_prod(torch.arange(S), torch.arange(T)).T.contiguous().to(dev)
+        return ei, S, T, S * T, "C4: complete bipartite %d x %d (fibre range of %d per GPU), Fdim %d, bf16" % (
+            S * world, T, S, args.wide_fdim)
+    S = 100000 if args.wide_fibres == 12500 else args.wide_fibres
+    g = torch.Generator().manual_seed(7)
+    keep = torch.rand(S * T, generator=g) < 0.1
+    e = torch.nonzero(keep).flatten()
+    e = e[torch.randperm(e.numel(), generator=g)]
+    ei = torch.stack([e // T, e % T]).contiguous().to(dev)
+    return ei, S, T, int(e.numel()), "C5b: 10%% Bernoulli edge list of %d x %d, shuffled, Fdim %d, bf16 (CSR/CSC path)" % (
+        S, T, args.wide_fdim)
+
+
+def cpu_reference_wide(args, S_sub, seconds):
+    """Oracle port on the host cores, fp32, on a fibre sub-range of the wide graph (linear in fibres)."""
+    from oracle import block_oracle as bo
+    ncores = os.cpu_count() or 1
+    torch.set_num_threads(ncores)
+    F, T = args.wide_fdim, args.wide_classes
+    E = S_sub * T
+    state = bo.random_block_state(F, seed=0)
+    ei = bo.complete_bipartite(S_sub, T)
+    g = torch.Generator().manual_seed(1234)
+    ins = [torch.randn(S_sub, F, generator=g), torch.randn(T, F, generator=g), torch.randn(E, F, generator=g),
+           torch.randn(1, F, generator=g)]
+    ups = [torch.linspace(0.5, 1.5, t.numel()).reshape(t.shape) for t in ins]
+    cpu_reference_graph_step(bo, state, ei, ins, ups)
+    times, t_begin = [], time.perf_counter()
+    while len(times) < 2 or time.perf_counter() - t_begin < seconds:
+        t0 = time.perf_counter()
+        cpu_reference_graph_step(bo, state, ei, ins, ups)
+        times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return E * len(times) / total, ncores, "%d steps on a %d-fibre sub-range (%d edges, Fdim %d, fp32) of the graph, %.1f s; " \
+        "throughput is linear in fibres" % (len(times), S_sub, E, F, total)
+
+
+def run_wide(args):
+    import torch.distributed as dist
+    from pfs_neural_net_b200 import _abi, gnn, shard
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if rank == 0:
+            t0 = time.perf_counter()
+            eps, ncores, sample = cpu_reference_wide(args, 48, seconds=max(5.0, 2.0 * args.steps))
+            print(json.dumps({
+                "impl": "reference", "metric": METRIC, "value": eps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": {"workload": args.workload + " (CPU oracle port, sub-range)"},
+                "cpu_baseline": {"value": eps, "unit": UNIT, "cores": ncores, "kind": "port", "sample": sample},
+                "e2e": {"value": eps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0, "wall_s": time.perf_counter() - t0}))
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the message-passing layer has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    sharded = world > 1 and args.workload == "c4"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _abi.load_library()
+    F = args.wide_fdim
+    ei, S, T, E, desc = wide_graph(args, rank, world, dev)
+    torch.manual_seed(0)
+    blk = gnn.Block(F)
+    g = torch.Generator().manual_seed(1)
+    for m in blk.modules():
+        if isinstance(m, torch.nn.BatchNorm1d):
+            m.weight.data = 0.5 + torch.rand(m.weight.shape, generator=g)
+            m.bias.data = 2 * torch.rand(m.bias.shape, generator=g) - 1
+    blk = blk.to(torch.bfloat16).to(dev).train()
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    gen_rep = torch.Generator(device=dev).manual_seed(99)            # replicated tensors: same on every rank
+    bf = torch.bfloat16
+    ins = [torch.randn(S, F, generator=gen, device=dev).to(bf), torch.randn(T, F, generator=gen_rep, device=dev).to(bf),
+           torch.randn(E, F, generator=gen, device=dev).to(bf), torch.randn(1, F, generator=gen_rep, device=dev).to(bf)]
+    ups = [torch.linspace(0.5, 1.5, t.shape[1], device=dev).to(bf).expand(t.shape).contiguous() for t in ins]
+    ctx = (lambda: shard.fibre_sharded()) if sharded else (lambda: __import__("contextlib").nullcontext())
+
+    def step(xs):
+        for p in blk.parameters():
+            p.grad = None
+        xs = [x.requires_grad_(True) for x in xs]
+        with ctx():
+            _, o_s, o_t, o_e, o_u = blk((ei, xs[0], xs[1], xs[2], xs[3]))
+            torch.autograd.backward([o_s, o_t, o_e, o_u], ups)
+        return o_u
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = lib.pfs_launch_count()
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        launches = lib.pfs_launch_count() - n0
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms, launches
+
+    detached = [x.detach() for x in ins]
+    for _ in range(max(args.warmup, 3)):
+        step([x.detach() for x in detached])
+    shard.reset_traffic()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms, launches = timed(lambda: step([x.detach() for x in detached]), args.steps)
+    clocks = sampler.stop()
+    coll_calls, coll_bytes = shard.traffic()
+    ms_per_step = ms / args.steps
+    edges_total = float(E) * (world if args.workload == "c4" or world == 1 else world)
+    value = edges_total / (ms_per_step * 1e-3)
+    hbm_gbs, peak_src, sm_max = measured_peaks()
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            tensor_peak = float(json.load(f)["bf16_tflops_sustained"])
+        tpeak_src = "measured sustained bf16 matmul (MEASURED_PEAKS.json)"
+    except Exception:
+        tensor_peak, tpeak_src = 1387.0, "fallback (B200_PROFILING.md)"
+    flops = 2.0 * F * F * (WIDE_MAC_PER_EDGE_F2 * E + WIDE_MAC_PER_FIBRE_F2 * S)
+    kernels, roofline = None, None
+    if not args.no_profile:
+        lib.pfs_profile_enable(1)
+        torch.cuda.synchronize(dev)
+        nprof = min(args.steps, 5)
+        for _ in range(nprof):
+            step([x.detach() for x in detached])
+        torch.cuda.synchronize(dev)
+        rep = _abi.profile_report()
+        lib.pfs_profile_enable(0)
+        tot = sum(v[1] for v in rep.values())
+        kernels = {k: {"launches": v[0], "ms_per_step": v[1] / nprof, "share": v[1] / tot}
+                   for k, v in sorted(rep.items(), key=lambda kv: -kv[1][1])[:12]}
+        gemm_ms = sum(v[1] for k, v in rep.items() if k.startswith("k_wide_gemm")) / nprof
+        achieved = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+        roofline = {"kernel": "k_wide_gemm_nt + k_wide_gemm_tn (all tcgen05 GEMM launches of the step)", "bound": "tensor",
+                    "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
+                    "frac": achieved / tensor_peak if achieved else None, "traffic": None, "peak_source": tpeak_src,
+                    "gemm_ms_per_step": gemm_ms, "share_of_step": gemm_ms * nprof / tot,
+                    "executed_flops_per_step": flops}
+    step_bytes = (5.0 * F * 2 + (0 if args.workload == "c4" else 16)) * E + 6.0 * (S + T) * F * 2
+    step_roofline = {"bound": "hbm", "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9, "peak": hbm_gbs, "unit": "GB/s",
+                     "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_gbs, "algorithmic_bytes_per_step": step_bytes}
+    tensor = {"executed_tflops": flops / (ms_per_step * 1e-3) / 1e12, "peak_tflops": tensor_peak,
+              "frac": flops / (ms_per_step * 1e-3) / 1e12 / tensor_peak, "peak_source": tpeak_src}
+    e2e = None
+    if not args.no_e2e:
+        host = [x.detach().cpu().pin_memory() for x in ins]
+        dbuf = [torch.empty_like(x) for x in detached]
+        h2d = sum(h.numel() * h.element_size() for h in host)
+
+        def e2e_step():
+            for d, h in zip(dbuf, host):
+                d.copy_(h, non_blocking=True)
+            for p in blk.parameters():
+                p.grad = None
+            xs = [d.detach().requires_grad_(True) for d in dbuf]
+            with ctx():
+                _, o_s, o_t, o_e, o_u = blk((ei, xs[0], xs[1], xs[2], xs[3]))
+                torch.autograd.backward([o_s, o_t, o_e, o_u], ups)
+            return float(o_u.float().sum().item())       # device -> host read of the step's result
+
+        for _ in range(2):
+            e2e_step()
+        k = max(3, args.steps // 2)
+        ms_e, _ = timed(e2e_step, k)
+        ms_e /= k
+        e2e = {"value": edges_total / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+               "ms_per_step": ms_e}
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        eps, ncores, sample = cpu_reference_wide(args, 48, seconds=args.cpu_seconds)
+        cpu = {"value": eps, "unit": UNIT, "cores": ncores, "kind": "port", "sample": sample}
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": desc, "fibres_per_gpu": S, "classes": T, "fdim": F, "edges_per_step": edges_total,
+                       "parallelism": ("fibre-sharded x%d (class-side all-reduces: %d calls, %d bytes per step)"
+                                       % (world, coll_calls // max(args.steps, 1), coll_bytes // max(args.steps, 1)))
+                       if sharded else "single GPU" if world == 1 else "replicas x%d" % world,
+                       "l2": "inputs larger than L2 (x_e %.0f MB per step)" % (E * F * 2 / 1e6)},
+            "roofline": roofline, "step_roofline": step_roofline, "tensor": tensor, "kernels": kernels, "cpu_baseline": cpu,
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
-    if args.impl == "reference":
+    if args.workload != "c3":
+        run_wide(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -310,7 +310,8 @@ size_t pfs_wide_segsum_workspace(const pfs_wide_segments* sd, int32_t C) {
 int pfs_wide_segsum(const pfs_wide_segments* sd, const void* x_bf16, int64_t ldx, int32_t C, float* out_f32, void* out_bf16,
                     void* workspace, size_t workspace_bytes, void* stream) {
     W_TRY(check_seg(sd));
-    W_REQUIRE(x_bf16 && (out_f32 || out_bf16) && C >= 2 && C % 2 == 0, "bad arguments");
+    W_REQUIRE(x_bf16 && (out_f32 || out_bf16) && C >= 8 && C % 8 == 0 && ldx % 8 == 0 && ((uintptr_t)x_bf16 & 15) == 0,
+              "bad arguments (C and ldx multiples of 8, 16-byte aligned rows)");
     cudaStream_t st = (cudaStream_t)stream;
     pfs_host::mark_launch(nullptr, st);
     const int nchunk = segsum_chunks(*sd, C);
@@ -333,12 +334,10 @@ int pfs_wide_segsum(const pfs_wide_segments* sd, const void* x_bf16, int64_t ldx
 
 int pfs_wide_moments_fwd(const pfs_wide_segments* sd, const void* m_bf16, int32_t C, float* moments, void* stream) {
     W_TRY(check_seg(sd));
-    W_REQUIRE(m_bf16 && moments && C >= 2 && C % 2 == 0, "bad arguments");
+    W_REQUIRE(m_bf16 && moments && C >= 8 && C % 8 == 0 && C <= 2048 && ((uintptr_t)m_bf16 & 15) == 0, "bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     pfs_host::mark_launch(nullptr, st);
-    int threads = C / 2;
-    threads = threads > 256 ? 256 : (threads + 31) / 32 * 32;
-    k_wide_moments_fwd<<<sd->nseg, threads, 0, st>>>(make_seg(*sd), (const bf16*)m_bf16, C, moments);
+    k_wide_moments_fwd<<<sd->nseg, 256, 0, st>>>(make_seg(*sd), (const bf16*)m_bf16, C, moments);
     W_LAUNCH_CHECK("k_wide_moments_fwd");
     return PFS_OK;
 }
@@ -365,20 +364,20 @@ int pfs_wide_source_coef(const pfs_wide_segments* sd, const float* dh, const flo
 
 int pfs_wide_source_dm(const void* m_bf16, const float* moments, const float* coef, const int32_t* src, int32_t T, int64_t E,
                        int32_t C, void* dm_bf16, void* stream) {
-    W_REQUIRE(m_bf16 && moments && coef && dm_bf16 && E >= 1 && C >= 2 && C % 2 == 0 && (src || T >= 1), "bad arguments");
+    W_REQUIRE(m_bf16 && moments && coef && dm_bf16 && E >= 1 && C >= 8 && C % 8 == 0 && (src || T >= 1), "bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     pfs_host::mark_launch(nullptr, st);
-    k_wide_source_dm<<<grid_for(E * (C / 2)), 256, 0, st>>>((const bf16*)m_bf16, moments, coef, src, T, E, C, (bf16*)dm_bf16);
+    k_wide_source_dm<<<grid_for(E * (C / 8)), 256, 0, st>>>((const bf16*)m_bf16, moments, coef, src, T, E, C, (bf16*)dm_bf16);
     W_LAUNCH_CHECK("k_wide_source_dm");
     return PFS_OK;
 }
 
 int pfs_wide_gather_mask(const float* tab, const int32_t* idx, int32_t mod, const void* act_bf16, int64_t E, int32_t C,
                          void* out_bf16, void* stream) {
-    W_REQUIRE(tab && act_bf16 && out_bf16 && E >= 1 && C >= 2 && C % 2 == 0 && (idx || mod >= 1), "bad arguments");
+    W_REQUIRE(tab && act_bf16 && out_bf16 && E >= 1 && C >= 8 && C % 8 == 0 && (idx || mod >= 1), "bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     pfs_host::mark_launch(nullptr, st);
-    k_wide_gather_mask<<<grid_for(E * (C / 2)), 256, 0, st>>>(tab, idx, mod, (const bf16*)act_bf16, E, C, (bf16*)out_bf16);
+    k_wide_gather_mask<<<grid_for(E * (C / 8)), 256, 0, st>>>(tab, idx, mod, (const bf16*)act_bf16, E, C, (bf16*)out_bf16);
     W_LAUNCH_CHECK("k_wide_gather_mask");
     return PFS_OK;
 }

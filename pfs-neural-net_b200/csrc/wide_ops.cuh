@@ -19,6 +19,29 @@ __device__ __forceinline__ float2 ld_pair(const float* p) { return *reinterpret_
 __device__ __forceinline__ void st_pair(bf16* p, float a, float b) { *reinterpret_cast<bf162*>(p) = __floats2bfloat162_rn(a, b); }
 __device__ __forceinline__ void st_pair(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
 
+// 8 bf16 columns (16 bytes) per thread: the access width of the streaming kernels below
+__device__ __forceinline__ void ld8(const bf16* p, float (&v)[8]) {
+    const uint4 w = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t u[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[2 * i] = __uint_as_float(u[i] << 16);
+        v[2 * i + 1] = __uint_as_float(u[i] & 0xFFFF0000u);
+    }
+}
+__device__ __forceinline__ void st8(bf16* p, const float (&v)[8]) {
+    uint4 w;
+    bf162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    bf162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+    w.x = *reinterpret_cast<uint32_t*>(&a); w.y = *reinterpret_cast<uint32_t*>(&b);
+    w.z = *reinterpret_cast<uint32_t*>(&c); w.w = *reinterpret_cast<uint32_t*>(&d);
+    *reinterpret_cast<uint4*>(p) = w;
+}
+__device__ __forceinline__ void ld8f(const float* p, float (&v)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
 // segments of rows: fibres or classes, dense (implicit) or listed
 struct SegDesc {
     int mode;          // 0: dense fibre (rows seg*T + i, i < T), 1: dense class (rows i*T + seg, i < S), 2: list
@@ -156,29 +179,64 @@ __global__ void __launch_bounds__(256) k_wide_rowmap(int kind, const TX* __restr
 __global__ void __launch_bounds__(256) k_wide_segsum(const SegDesc sd, const bf16* __restrict__ x, int ldx, int C, int nchunk,
                                                      float* __restrict__ out_f32, bf16* __restrict__ out_bf16,
                                                      float* __restrict__ partial) {
+    // thread = 8 columns (one 16-byte load) of one row lane; tpr threads cover a row, 256 / tpr rows are
+    // in flight per pass and 4 passes are unrolled, so a block keeps 16 KB of loads outstanding
+    __shared__ float red[256 * 8];
     const int seg = blockIdx.x, chunk = blockIdx.y;
     const int len = seg_len(sd, seg);
     const int i0 = (int)((long long)len * chunk / nchunk), i1 = (int)((long long)len * (chunk + 1) / nchunk);
-    for (int c = 2 * threadIdx.x; c < C; c += 512) {
-        float s0 = 0.f, s1 = 0.f, t0 = 0.f, t1 = 0.f;
-        int i = i0;
-        for (; i + 1 < i1; i += 2) {      // two independent chains keep two loads in flight
-            const float2 a = ld_pair(x + seg_row(sd, seg, i) * ldx + c);
-            const float2 b = ld_pair(x + seg_row(sd, seg, i + 1) * ldx + c);
-            s0 += a.x; s1 += a.y;
-            t0 += b.x; t1 += b.y;
+    const int cgroups = C >> 3;
+    const int tpr = cgroups < 256 ? cgroups : 256;           // threads per row
+    const int lanes = 256 / tpr;                             // row lanes
+    const int lc = threadIdx.x % tpr, lr = threadIdx.x / tpr;
+    for (int cg0 = 0; cg0 < cgroups; cg0 += tpr) {
+        const int cg = cg0 + lc;
+        const bool live = lr < lanes && cg < cgroups;
+        float acc[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+        if (live) {
+            const bf16* xc = x + 8 * cg;
+            int i = i0 + lr;
+            for (; i + 3 * lanes < i1; i += 4 * lanes) {
+                float v0[8], v1[8], v2[8], v3[8];
+                ld8(xc + seg_row(sd, seg, i) * ldx, v0);
+                ld8(xc + seg_row(sd, seg, i + lanes) * ldx, v1);
+                ld8(xc + seg_row(sd, seg, i + 2 * lanes) * ldx, v2);
+                ld8(xc + seg_row(sd, seg, i + 3 * lanes) * ldx, v3);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) acc[q] += (v0[q] + v1[q]) + (v2[q] + v3[q]);
+            }
+            for (; i < i1; i += lanes) {
+                float v0[8];
+                ld8(xc + seg_row(sd, seg, i) * ldx, v0);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) acc[q] += v0[q];
+            }
         }
-        if (i < i1) {
-            const float2 a = ld_pair(x + seg_row(sd, seg, i) * ldx + c);
-            s0 += a.x; s1 += a.y;
-        }
-        s0 += t0; s1 += t1;
-        if (nchunk > 1) {
-            float* p = partial + ((size_t)chunk * sd.nseg + seg) * C + c;
-            p[0] = s0; p[1] = s1;
-        } else {
-            if (out_f32) st_pair(out_f32 + (size_t)seg * C + c, s0, s1);
-            if (out_bf16) st_pair(out_bf16 + (size_t)seg * C + c, s0, s1);
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) red[threadIdx.x * 8 + q] = acc[q];
+        __syncthreads();
+        if (lr == 0 && cg < cgroups) {
+            float sum[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) sum[q] = 0.f;
+            for (int r = 0; r < lanes; ++r)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) sum[q] += red[(r * tpr + lc) * 8 + q];
+            const int c = 8 * cg;
+            if (nchunk > 1) {
+                float* p = partial + ((size_t)chunk * sd.nseg + seg) * C + c;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) p[q] = sum[q];
+            } else {
+                if (out_f32) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) out_f32[(size_t)seg * C + c + q] = sum[q];
+                }
+                if (out_bf16) st8(out_bf16 + (size_t)seg * C + c, sum);
+            }
         }
     }
 }
@@ -197,33 +255,111 @@ __global__ void k_wide_segsum_final(const float* __restrict__ partial, int nchun
 // moments[fibre] = {mean, E[m^2], c2, c3, c4} (central moments about the mean, two passes), [S,5,C]
 // grid (S), C / 2 threads
 // ------------------------------------------------------------------------------------------------
-__global__ void k_wide_moments_fwd(const SegDesc sd, const bf16* __restrict__ m, int C, float* __restrict__ moments) {
+__global__ void __launch_bounds__(256) k_wide_moments_fwd(const SegDesc sd, const bf16* __restrict__ m, int C,
+                                                          float* __restrict__ moments) {
+    // same thread mapping as k_wide_segsum (8 columns x row lanes); pass 1: sum, sum of squares; pass 2: central moments
+    __shared__ float red[256 * 8 * 3];
+    __shared__ float mean_s[2048];
     const int seg = blockIdx.x;
     const int len = seg_len(sd, seg);
     const float inv = 1.f / (float)max(len, 1);
-    for (int c = 2 * threadIdx.x; c < C; c += 2 * blockDim.x) {
-        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-        for (int i = 0; i < len; ++i) {
-            const float2 a = ld_pair(m + seg_row(sd, seg, i) * C + c);
-            s0 += a.x; s1 += a.y;
-            q0 = fmaf(a.x, a.x, q0); q1 = fmaf(a.y, a.y, q1);
+    const int cgroups = C >> 3;
+    const int tpr = cgroups < 256 ? cgroups : 256;
+    const int lanes = 256 / tpr;
+    const int lc = threadIdx.x % tpr, lr = threadIdx.x / tpr;
+    for (int cg0 = 0; cg0 < cgroups; cg0 += tpr) {
+        const int cg = cg0 + lc;
+        const bool live = lr < lanes && cg < cgroups;
+        const bf16* xc = m + 8 * cg;
+        float s1[8], s2[8], s3[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s1[q] = s2[q] = s3[q] = 0.f;
+        if (live) {
+            int i = lr;
+            for (; i + lanes < len; i += 2 * lanes) {
+                float v0[8], v1[8];
+                ld8(xc + seg_row(sd, seg, i) * C, v0);
+                ld8(xc + seg_row(sd, seg, i + lanes) * C, v1);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    s1[q] += v0[q] + v1[q];
+                    s2[q] = fmaf(v0[q], v0[q], fmaf(v1[q], v1[q], s2[q]));
+                }
+            }
+            for (; i < len; i += lanes) {
+                float v0[8];
+                ld8(xc + seg_row(sd, seg, i) * C, v0);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    s1[q] += v0[q];
+                    s2[q] = fmaf(v0[q], v0[q], s2[q]);
+                }
+            }
         }
-        const float mean0 = s0 * inv, mean1 = s1 * inv;
-        float a20 = 0.f, a21 = 0.f, a30 = 0.f, a31 = 0.f, a40 = 0.f, a41 = 0.f;
-        for (int i = 0; i < len; ++i) {
-            const float2 a = ld_pair(m + seg_row(sd, seg, i) * C + c);
-            const float d0 = a.x - mean0, d1 = a.y - mean1;
-            const float d02 = d0 * d0, d12 = d1 * d1;
-            a20 += d02; a21 += d12;
-            a30 = fmaf(d02, d0, a30); a31 = fmaf(d12, d1, a31);
-            a40 = fmaf(d02, d02, a40); a41 = fmaf(d12, d12, a41);
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            red[threadIdx.x * 8 + q] = s1[q];
+            red[2048 + threadIdx.x * 8 + q] = s2[q];
         }
-        float* o = moments + (size_t)seg * 5 * C + c;
-        st_pair(o, mean0, mean1);
-        st_pair(o + C, q0 * inv, q1 * inv);
-        st_pair(o + 2 * C, a20 * inv, a21 * inv);
-        st_pair(o + 3 * C, a30 * inv, a31 * inv);
-        st_pair(o + 4 * C, a40 * inv, a41 * inv);
+        __syncthreads();
+        float* o = moments + (size_t)seg * 5 * C + 8 * cg;
+        if (lr == 0 && cg < cgroups) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                float a = 0.f, b = 0.f;
+                for (int r = 0; r < lanes; ++r) {
+                    a += red[(r * tpr + lc) * 8 + q];
+                    b += red[2048 + (r * tpr + lc) * 8 + q];
+                }
+                mean_s[lc * 8 + q] = a * inv;
+                o[q] = a * inv;
+                o[C + q] = b * inv;
+            }
+        }
+        __syncthreads();
+        float mean[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            mean[q] = mean_s[lc * 8 + q];
+            s1[q] = s2[q] = s3[q] = 0.f;
+        }
+        if (live) {
+            for (int i = lr; i < len; i += lanes) {
+                float v0[8];
+                ld8(xc + seg_row(sd, seg, i) * C, v0);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float d = v0[q] - mean[q], d2 = d * d;
+                    s1[q] += d2;
+                    s2[q] = fmaf(d2, d, s2[q]);
+                    s3[q] = fmaf(d2, d2, s3[q]);
+                }
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            red[threadIdx.x * 8 + q] = s1[q];
+            red[2048 + threadIdx.x * 8 + q] = s2[q];
+            red[4096 + threadIdx.x * 8 + q] = s3[q];
+        }
+        __syncthreads();
+        if (lr == 0 && cg < cgroups) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                float a = 0.f, b = 0.f, c = 0.f;
+                for (int r = 0; r < lanes; ++r) {
+                    a += red[(r * tpr + lc) * 8 + q];
+                    b += red[2048 + (r * tpr + lc) * 8 + q];
+                    c += red[4096 + (r * tpr + lc) * 8 + q];
+                }
+                o[2 * C + q] = a * inv;
+                o[3 * C + q] = b * inv;
+                o[4 * C + q] = c * inv;
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -317,35 +453,41 @@ __global__ void k_wide_source_coef(const SegDesc sd, const float* __restrict__ d
 __global__ void __launch_bounds__(256) k_wide_source_dm(const bf16* __restrict__ m, const float* __restrict__ moments,
                                                         const float* __restrict__ coef, const int* __restrict__ src, int T,
                                                         long long E, int C, bf16* __restrict__ dm) {
-    const int half = C >> 1;
-    const long long total = E * half;
+    const int groups = C >> 3;
+    const long long total = E * groups;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long e = i / half;
-        const int c = 2 * (int)(i - e * half);
+        const long long e = i / groups;
+        const int c = 8 * (int)(i - e * groups);
         const long long s = src ? src[e] : e / T;
-        const float2 mm = ld_pair(m + e * C + c);
-        const float2 mean = ld_pair(moments + s * 5 * C + c);
+        float mm[8], mean[8], a0[8], a1[8], a2[8], a3[8], o[8];
+        ld8(m + e * C + c, mm);
+        ld8f(moments + s * 5 * C + c, mean);
         const float* cf = coef + s * 4 * C + c;
-        const float2 a0 = ld_pair(cf), a1 = ld_pair(cf + C), a2 = ld_pair(cf + 2 * C), a3 = ld_pair(cf + 3 * C);
-        const float d0 = mm.x - mean.x, d1 = mm.y - mean.y;
-        const float o0 = a0.x + a1.x * mm.x + (a2.x + a3.x * d0) * d0 * d0;
-        const float o1 = a0.y + a1.y * mm.y + (a2.y + a3.y * d1) * d1 * d1;
-        st_pair(dm + e * C + c, o0, o1);
+        ld8f(cf, a0); ld8f(cf + C, a1); ld8f(cf + 2 * C, a2); ld8f(cf + 3 * C, a3);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float d = mm[q] - mean[q];
+            o[q] = a0[q] + a1[q] * mm[q] + (a2[q] + a3[q] * d) * d * d;
+        }
+        st8(dm + e * C + c, o);
     }
 }
 // out[e] = tab[idx[e]] * (act[e] > 0 ? 1 : slope)    (TModel backward: dht = dasum[tgt] . lrelu'(ht))
 __global__ void __launch_bounds__(256) k_wide_gather_mask(const float* __restrict__ tab, const int* __restrict__ idx, int mod,
                                                           const bf16* __restrict__ act, long long E, int C,
                                                           bf16* __restrict__ out) {
-    const int half = C >> 1;
-    const long long total = E * half;
+    const int groups = C >> 3;
+    const long long total = E * groups;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long e = i / half;
-        const int c = 2 * (int)(i - e * half);
+        const long long e = i / groups;
+        const int c = 8 * (int)(i - e * groups);
         const long long r = idx ? idx[e] : e % mod;
-        const float2 t = ld_pair(tab + r * C + c);
-        const float2 a = ld_pair(act + e * C + c);
-        st_pair(out + e * C + c, t.x * (a.x > 0.f ? 1.f : 0.1f), t.y * (a.y > 0.f ? 1.f : 0.1f));
+        float t[8], a[8], o[8];
+        ld8f(tab + r * C + c, t);
+        ld8(act + e * C + c, a);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) o[q] = t[q] * (a[q] > 0.f ? 1.f : 0.1f);
+        st8(out + e * C + c, o);
     }
 }
 
