@@ -1,0 +1,105 @@
+"""Fibre-range sharding of one graph over 2 GPUs (NCCL): every rank runs the wide Block on its fibre
+range inside shard.fibre_sharded(); outputs, input gradients and the (all-reduced) parameter
+gradients must match the single-GPU run of the whole graph.  Needs >= 2 CUDA devices
+(`gpurun --gpus 2`); skipped otherwise."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import block_oracle as bo
+
+pytestmark = pytest.mark.gpu
+F, S, T = 32, 128, 64
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _setup():
+    g = torch.Generator().manual_seed(21)
+    r = lambda *s: torch.randn(*s, generator=g).bfloat16()
+    ins = (r(S, F), r(T, F), r(S * T, F), r(1, F))
+    ups = (r(S, F), r(T, F), r(S * T, F), r(1, F))
+    state = {k: (v.bfloat16() if v.is_floating_point() else v) for k, v in bo.random_block_state(F, seed=2).items()}
+    return ins, ups, state
+
+
+def _run(dev, state, ins, ups, S_local, ctx):
+    from pfs_neural_net_b200 import gnn
+    blk = gnn.Block(F).to(torch.bfloat16)
+    blk.load_state_dict(state, strict=True)
+    blk = blk.to(dev).train()
+    ei = bo.complete_bipartite(S_local, T).to(dev)
+    x = [t.to(dev).requires_grad_(True) for t in ins]
+    with ctx():
+        _, o_s, o_t, o_e, o_u = blk((ei, *x))
+        torch.autograd.backward([o_s, o_t, o_e, o_u], [u.to(dev) for u in ups])
+    torch.cuda.synchronize(dev)
+    res = {"o_s": o_s, "o_t": o_t, "o_e": o_e, "o_u": o_u, "g_s": x[0].grad, "g_t": x[1].grad, "g_e": x[2].grad, "g_u": x[3].grad}
+    res.update({"p." + k: p.grad for k, p in blk.named_parameters()})
+    res.update({"b." + k: b for k, b in blk.named_buffers()})
+    return {k: v.detach().float().cpu() for k, v in res.items()}
+
+
+def _worker(rank, world, port, out):
+    import contextlib
+    from pfs_neural_net_b200 import shard
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    ins, ups, state = _setup()
+    h = S // world
+    sl, el = slice(rank * h, (rank + 1) * h), slice(rank * h * T, (rank + 1) * h * T)
+    loc_in = (ins[0][sl], ins[1], ins[2][el], ins[3])
+    loc_up = (ups[0][sl], ups[1], ups[2][el], ups[3])
+    res = _run(dev, state, loc_in, loc_up, h, shard.fibre_sharded)
+    out[rank] = res
+    if rank == 0:
+        out["full"] = _run(dev, state, ins, ups, S, contextlib.nullcontext)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_fibre_sharded_block_matches_single_gpu():
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 CUDA devices")
+    world = 2
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+        out = dict(out)
+    full = out["full"]
+    h = S // world
+
+    def close(a, b, what, tol=2e-2):
+        err = (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
+        assert err < tol, (what, err)
+
+    for r in range(world):
+        sl, el = slice(r * h, (r + 1) * h), slice(r * h * T, (r + 1) * h * T)
+        close(out[r]["o_s"], full["o_s"][sl], "x_s")
+        close(out[r]["o_e"], full["o_e"][el], "x_e")
+        close(out[r]["g_s"], full["g_s"][sl], "grad x_s")
+        close(out[r]["g_e"], full["g_e"][el], "grad x_e")
+        for k in ("o_t", "o_u", "g_t", "g_u"):
+            close(out[r][k], full[k], k)
+        for k in full:
+            if k.startswith("p."):
+                scale_key = k[:-4] + "weight" if k.endswith("bias") else k
+                den = max(full[k].abs().max().item(), 1e-3 * full[scale_key].abs().max().item())
+                err = (out[r][k] - full[k]).abs().max().item() / den
+                assert err < 3e-2, (k, err)
+            if k.startswith("b.") and not k.endswith("num_batches_tracked"):
+                close(out[r][k], full[k], k)
+    # every rank ends with the same (global) parameter gradients
+    for k in full:
+        if k.startswith("p."):
+            assert torch.equal(out[0][k], out[1][k]), k
