@@ -167,50 +167,64 @@ k_wide_gemm_nt(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int cq = ew >> 2;                          // which 32 of the block's 128 columns it drains
         const int trow = quarter * 32 + lane;            // accumulator row of this thread in phase 1
         constexpr int kRows = kGemmBM / kGemmEpiWarps;   // rows per warp in phase 2: ew, ew + 16, ...
-        // phase-1 / phase-2 staging addresses (16-byte chunks XOR-swizzled by the row; rows ew + 16 rr share ew's low bits)
-        float4* const p1row = reinterpret_cast<float4*>(stg + trow * kGemmEpiChunk);
+        constexpr int kChunks = (BN + kGemmEpiChunk - 1) / kGemmEpiChunk;
+        // staging addresses (16-byte chunks XOR-swizzled by the row; rows ew + 16 rr share ew's low bits)
+        float4* const p1row = reinterpret_cast<float4*>(stg + trow * kGemmEpiChunk) + 8 * cq;
+        const int t7 = trow & 7;
         const float4* const p2row = reinterpret_cast<const float4*>(stg + ew * kGemmEpiChunk) + ((lane & ~7) | ((lane ^ ew) & 7));
+        const size_t ostride = (size_t)kGemmEpiWarps * ldc, fstride = (size_t)kGemmEpiWarps * ep.ldf;
+        const size_t mstride = (size_t)kGemmEpiWarps * ep.ldmask;
         int it = 0;
         for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
             const int as = it & 1;
             const uint32_t aph = (it >> 1) & 1;
             const int m0 = (t / nt) * kGemmBM, n0 = (t % nt) * BN;
             const int ncols = min(BN, N - n0);
-            // per-row addressing, once per tile: rows beyond M are clamped for the loads and masked at the stores
-            int mrow[kRows];
+            const int mbase = m0 + ew;
+            const bool full = m0 + kGemmBM <= M;          // no row of this tile is out of range
+            // per-row gather offsets, once per tile (rows beyond M are clamped for the loads, masked at the stores)
             uint32_t off0[kRows], off1[kRows];
-#pragma unroll
-            for (int rr = 0; rr < kRows; ++rr) mrow[rr] = min(m0 + ew + kGemmEpiWarps * rr, M - 1);
             if constexpr (TABLES) {
                 if (ep.idx0) {
 #pragma unroll
-                    for (int rr = 0; rr < kRows; ++rr) off0[rr] = (uint32_t)__ldg(ep.idx0 + mrow[rr]) * (uint32_t)N;
+                    for (int rr = 0; rr < kRows; ++rr)
+                        off0[rr] = (uint32_t)__ldg(ep.idx0 + min(mbase + kGemmEpiWarps * rr, M - 1)) * (uint32_t)N;
                 } else {
+                    int q = mbase / ep.div0, rem = mbase - q * ep.div0;
 #pragma unroll
-                    for (int rr = 0; rr < kRows; ++rr) off0[rr] = (uint32_t)min(mrow[rr] / ep.div0, ep.rows0 - 1) * (uint32_t)N;
+                    for (int rr = 0; rr < kRows; ++rr) {
+                        off0[rr] = (uint32_t)min(q, ep.rows0 - 1) * (uint32_t)N;
+                        rem += kGemmEpiWarps;
+                        while (rem >= ep.div0) { rem -= ep.div0; ++q; }
+                    }
                 }
                 if (ep.idx1) {
 #pragma unroll
-                    for (int rr = 0; rr < kRows; ++rr) off1[rr] = (uint32_t)__ldg(ep.idx1 + mrow[rr]) * (uint32_t)N;
+                    for (int rr = 0; rr < kRows; ++rr)
+                        off1[rr] = (uint32_t)__ldg(ep.idx1 + min(mbase + kGemmEpiWarps * rr, M - 1)) * (uint32_t)N;
                 } else {
+                    int rem = mbase % ep.mod1;
 #pragma unroll
-                    for (int rr = 0; rr < kRows; ++rr) off1[rr] = (uint32_t)(mrow[rr] % ep.mod1) * (uint32_t)N;
+                    for (int rr = 0; rr < kRows; ++rr) {
+                        off1[rr] = (uint32_t)rem * (uint32_t)N;
+                        rem += kGemmEpiWarps;
+                        while (rem >= ep.mod1) rem -= ep.mod1;
+                    }
                 }
             }
-            const bool last_rows_ok = m0 + kGemmBM <= M;
             mbar_wait(tfull + as, aph);
             tc_fence_after();
-            for (int c0 = 0; c0 < ncols; c0 += kGemmEpiChunk) {
+#pragma unroll
+            for (int ch = 0; ch < kChunks; ++ch) {
+                const int c0 = ch * kGemmEpiChunk;
+                if (c0 >= ncols) break;
                 named_bar_sync(1, 32 * kGemmEpiWarps);   // phase 2 of the previous block has left the staging tile
                 // ---- phase 1: TMEM -> staging ----
                 if (c0 + 32 * cq < ncols) {
                     float v[32];
                     tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + as * BN + c0 + 32 * cq, v);
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const int chunk = 8 * cq + q;
-                        p1row[(chunk & ~7) | ((chunk ^ trow) & 7)] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                    }
+                    for (int q = 0; q < 8; ++q) p1row[q ^ t7] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                 }
                 if (c0 + kGemmEpiChunk >= ncols) {       // accumulator fully drained: hand it back to the MMA warp
                     tc_fence_before();
@@ -227,17 +241,24 @@ k_wide_gemm_nt(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int rr = 0; rr < kRows; ++rr) acc[rr] = p2row[rr * (kGemmEpiWarps * kGemmEpiChunk / 4)];
                     uint2 mkv[kRows];
                     if constexpr (MASK) {
-                        const __nv_bfloat16* mp = ep.mask + n;
+                        const __nv_bfloat16* mp = ep.mask + (size_t)mbase * ep.ldmask + n;
+                        if (full) {
 #pragma unroll
-                        for (int rr = 0; rr < kRows; ++rr)
-                            mkv[rr] = __ldg(reinterpret_cast<const uint2*>(mp + (size_t)mrow[rr] * ep.ldmask));
+                            for (int rr = 0; rr < kRows; ++rr) mkv[rr] = __ldg(reinterpret_cast<const uint2*>(mp + rr * mstride));
+                        } else {
+#pragma unroll
+                            for (int rr = 0; rr < kRows; ++rr) {
+                                mkv[rr] = make_uint2(0u, 0u);
+                                if (mbase + kGemmEpiWarps * rr < M) mkv[rr] = __ldg(reinterpret_cast<const uint2*>(mp + rr * mstride));
+                            }
+                        }
                     }
                     if (ep.bias) {
                         const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
                         if (ep.bias_rowscale) {
 #pragma unroll
                             for (int rr = 0; rr < kRows; ++rr) {
-                                const float rs = __ldg(ep.bias_rowscale + mrow[rr]);
+                                const float rs = __ldg(ep.bias_rowscale + min(mbase + kGemmEpiWarps * rr, M - 1));
                                 acc[rr].x = fmaf(b.x, rs, acc[rr].x); acc[rr].y = fmaf(b.y, rs, acc[rr].y);
                                 acc[rr].z = fmaf(b.z, rs, acc[rr].z); acc[rr].w = fmaf(b.w, rs, acc[rr].w);
                             }
@@ -285,19 +306,25 @@ k_wide_gemm_nt(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                     if (out_bf16) {
-                        __nv_bfloat16* op = out_bf16 + (size_t)(m0 + ew) * ldc + n;
+                        __nv_bfloat16* op = out_bf16 + (size_t)mbase * ldc + n;
+                        if (full) {
 #pragma unroll
-                        for (int rr = 0; rr < kRows; ++rr)
-                            if (last_rows_ok || m0 + ew + kGemmEpiWarps * rr < M)
-                                *reinterpret_cast<uint2*>(op + (size_t)rr * kGemmEpiWarps * ldc) =
+                            for (int rr = 0; rr < kRows; ++rr)
+                                *reinterpret_cast<uint2*>(op + rr * ostride) =
                                     make_uint2(pack_bf16(acc[rr].x, acc[rr].y), pack_bf16(acc[rr].z, acc[rr].w));
+                        } else {
+#pragma unroll
+                            for (int rr = 0; rr < kRows; ++rr)
+                                if (mbase + kGemmEpiWarps * rr < M)
+                                    *reinterpret_cast<uint2*>(op + rr * ostride) =
+                                        make_uint2(pack_bf16(acc[rr].x, acc[rr].y), pack_bf16(acc[rr].z, acc[rr].w));
+                        }
                     }
                     if (ep.out_f32) {
-                        float* op = ep.out_f32 + (size_t)(m0 + ew) * ep.ldf + n;
+                        float* op = ep.out_f32 + (size_t)mbase * ep.ldf + n;
 #pragma unroll
                         for (int rr = 0; rr < kRows; ++rr)
-                            if (last_rows_ok || m0 + ew + kGemmEpiWarps * rr < M)
-                                *reinterpret_cast<float4*>(op + (size_t)rr * kGemmEpiWarps * ep.ldf) = acc[rr];
+                            if (full || mbase + kGemmEpiWarps * rr < M) *reinterpret_cast<float4*>(op + rr * fstride) = acc[rr];
                     }
                 }
             }
