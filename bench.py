@@ -59,9 +59,10 @@ def parse_args():
     ap.add_argument("--classes", type=int, default=12)
     ap.add_argument("--fdim", type=int, default=10)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget of the cpu_baseline sample")
-    ap.add_argument("--workload", default="c3", choices=["c3", "c4", "c5"],
+    ap.add_argument("--workload", default="c3", choices=["c3", "c4", "c5", "c5a"],
                     help="c3: 256 x 2394x12 graphs, Fdim 10 fp32 (headline); c4: one 12500*N x 512 graph, Fdim 128 bf16, "
-                         "fibre-sharded over the N GPUs; c5: 10%% sparse 100000x512 edge list, Fdim 128 bf16 (CSR/CSC path)")
+                         "fibre-sharded over the N GPUs; c5: 10%% sparse 100000x512 edge list, Fdim 128 bf16 (CSR/CSC path); "
+                         "c5a: the same edge list at Fdim 10 fp32 through the narrow kernels")
     ap.add_argument("--wide-fibres", type=int, default=12500, help="c4: fibres per GPU")
     ap.add_argument("--wide-classes", type=int, default=512)
     ap.add_argument("--wide-fdim", type=int, default=128)
@@ -231,7 +232,16 @@ def run_ours(args):
     bucket = dp.GradBucket(blk.parameters())
     if world > 1:
         dp.broadcast_parameters(blk)
-    ei = torch.cartesian_prod(torch.arange(S), torch.arange(T)).T.contiguous().to(dev)   # reference src/train.py:94
+    if args.workload == "c5a":
+        # BASELINE configs[4]: general sparse edge_index, 10% density, shuffled (SURVEY.md 8d "C5")
+        G, S, T = 1, 100000, 512
+        gsp = torch.Generator().manual_seed(7)
+        e = torch.nonzero(torch.rand(S * T, generator=gsp) < 0.1).flatten()
+        e = e[torch.randperm(e.numel(), generator=gsp)]
+        ei = torch.stack([e // T, e % T]).contiguous().to(dev)
+        E = int(e.numel())
+    else:
+        ei = torch.cartesian_prod(torch.arange(S), torch.arange(T)).T.contiguous().to(dev)   # reference src/train.py:94
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     shapes = [(G, S, F), (G, T, F), (G, E, F), (G, 1, F)]
     ins = [torch.randn(s, generator=gen, device=dev) for s in shapes]
@@ -306,7 +316,7 @@ def run_ours(args):
                         "frac": achieved / hbm_gbs, "traffic": None, "peak_source": peak_src,
                         "avg_launch_ms": tms / n, "algorithmic_bytes_per_launch": bytes_per_launch,
                         "share_of_step": tms / tot, "binding": "fp32_fma (see fma)"}
-    step_bytes = (5.0 * F * 4 * E + 6.0 * (S + T) * F * 4) * G
+    step_bytes = ((5.0 * F * 4 + (16 if args.workload == "c5a" else 0)) * E + 6.0 * (S + T) * F * 4) * G
     flops = 2.0 * F * F * (MAC_PER_EDGE_F2 * E + MAC_PER_FIBRE_F2 * S) * G
     clk = (clocks.get("sm_mhz") or sm_max)
     fma_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
@@ -345,7 +355,7 @@ def run_ours(args):
 
     # ---- CPU baseline (rank 0, N = 1) ------------------------------------------------------------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "c3":
         eps, ncores, sample, _ = cpu_reference(args, seconds=args.cpu_seconds)
         cpu = {"value": eps, "unit": UNIT, "cores": ncores, "kind": "port", "sample": sample}
 
@@ -354,8 +364,10 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C3: %d x complete bipartite %dx%d per GPU, Fdim %d, one Block fwd+bwd, train mode"
-                                   % (G, S, T, F),
+            "config": {"workload": ("C3: %d x complete bipartite %dx%d per GPU, Fdim %d, one Block fwd+bwd, train mode"
+                                    % (G, S, T, F)) if args.workload == "c3" else
+                                   ("C5a: 10%% Bernoulli edge list of %d x %d (%d edges, shuffled; CSR/CSC segmented "
+                                    "reductions), Fdim %d fp32, one Block fwd+bwd" % (S, T, E, F)),
                        "graphs_per_gpu": G, "global_graphs": G * world, "fibres": S, "classes": T, "fdim": F,
                        "edges_per_step": edges_total, "parallelism": "dp%d" % world,
                        "l2": "inputs larger than L2 (x_e %.0f MB per step)" % (G * E * F * 4 / 1e6)},
@@ -582,7 +594,7 @@ def run_wide(args):
 
 def main():
     args = parse_args()
-    if args.workload != "c3":
+    if args.workload in ("c4", "c5"):
         run_wide(args)
     elif args.impl == "reference":
         run_reference(args)

@@ -294,14 +294,34 @@ int outer_rows(const float* D, const float* X, long long N, float* scratch_parti
     return PFS_OK;
 }
 // class-side sums: dense -> second stage over per-tile partials; CSR -> class-sorted segment sums
-int class_sums(const Topo& tp, const float* part_or_rows, int J, float* out, cudaStream_t st) {
+// chunks per class segment of the CSC sums: enough blocks to fill the device when there are few classes
+int csc_chunks(const Topo& tp) {
+    const long long blocks = (long long)tp.T * tp.G;
+    long long n = (4LL * num_sms() + blocks - 1) / blocks;
+    const long long avg = tp.E / (tp.T > 0 ? tp.T : 1);
+    if (n > avg / 64) n = avg / 64;
+    if (n > 64) n = 64;
+    return (int)(n < 1 ? 1 : n);
+}
+size_t csc_scratch_floats(const Topo& tp, int J) {
+    return tp.layout == PFS_LAYOUT_DENSE ? 0 : (size_t)tp.G * csc_chunks(tp) * tp.T * J;
+}
+int class_sums(const Topo& tp, const float* part_or_rows, int J, float* out, float* scratch, cudaStream_t st) {
     if (tp.layout == PFS_LAYOUT_DENSE) {
         const int TJ = tp.T * J;
         k_class_reduce<<<dim3((TJ + 127) / 128, tp.G), 128, 0, st>>>(part_or_rows, tp.ntiles, TJ, out);
         PFS_LAUNCH_CHECK("k_class_reduce");
     } else {
-        k_csc_segment_sum<<<dim3((tp.T + 3) / 4, tp.G), 128, 0, st>>>(part_or_rows, tp.colptr, tp.cscq, tp.E, tp.T, J, out);
+        if (J > kCscThreads) return fail(PFS_ERR_UNSUPPORTED, "class sums of %d features per row", J);
+        const int nchunk = csc_chunks(tp);
+        k_csc_segment_sum<<<dim3(tp.T, nchunk, tp.G), kCscThreads, 0, st>>>(part_or_rows, tp.colptr, tp.cscq, tp.E, tp.T, J,
+                                                                            nchunk, out, scratch);
         PFS_LAUNCH_CHECK("k_csc_segment_sum");
+        if (nchunk > 1) {
+            const int TJ = tp.T * J;
+            k_csc_segment_final<<<dim3((TJ + 127) / 128, tp.G), 128, 0, st>>>(scratch, nchunk, TJ, out);
+            PFS_LAUNCH_CHECK("k_csc_segment_final");
+        }
     }
     return PFS_OK;
 }
@@ -428,6 +448,8 @@ int edge_bwd_impl(const pfs_edge_args& a, const Topo& tp) {
     float* dgb = ws.f((size_t)tp.G * 2 * F);
     float* dPs = ws.f((size_t)tp.G * tp.S * H);
     float* stage = ws.f(class_stage_floats(tp, H));
+    float* cscs = ws.f(csc_scratch_floats(tp, H) + 1);
+    double* statsum = (double*)ws.f((size_t)tp.G * 4 * F + 2);
     float* dPt = ws.f((size_t)tp.G * tp.T * H);
     float* tot = ws.f((size_t)tp.G * H);
     float* wpart = ws.f((size_t)grid * pstride);
@@ -446,15 +468,17 @@ int edge_bwd_impl(const pfs_edge_args& a, const Topo& tp) {
     }
     const int n = tp.G * F;
     k_edge_bn_bwd_coef<<<(n + 127) / 128, 128, 0, st>>>(0, mode, F, tp.G, tp.ntiles, tp.E, a.bn_save, a.gamma, a.beta,
-                                                         a.running_mean, a.running_var, a.eps, statp, coef, dgb);
+                                                         a.running_mean, a.running_var, a.eps, statsum, coef, dgb);
     PFS_LAUNCH_CHECK("k_edge_bn_bwd_coef/0");
     if (mode != 0) {
         EdgeBnStatParams sp{tp, a.x_e_out, a.g_out, coef, statp};
         const int g2 = persistent_grid(k_edge_bn_bwd_stats<F>, 0, total);
         k_edge_bn_bwd_stats<F><<<g2, kThreads, 0, st>>>(sp);
         PFS_LAUNCH_CHECK("k_edge_bn_bwd_stats");
+        k_tile_partial_sums<<<tp.G, 256, 0, st>>>(statp, tp.ntiles, 2 * F, statsum);
+        PFS_LAUNCH_CHECK("k_tile_partial_sums");
         k_edge_bn_bwd_coef<<<(n + 127) / 128, 128, 0, st>>>(1, mode, F, tp.G, tp.ntiles, tp.E, a.bn_save, a.gamma,
-                                                             a.beta, a.running_mean, a.running_var, a.eps, statp, coef,
+                                                             a.beta, a.running_mean, a.running_var, a.eps, statsum, coef,
                                                              dgb);
         PFS_LAUNCH_CHECK("k_edge_bn_bwd_coef/1");
         PFS_TRY(colsum_all(dgb, tp.G, 2 * F, 0, F, a.g_gamma, st));
@@ -472,7 +496,7 @@ int edge_bwd_impl(const pfs_edge_args& a, const Topo& tp) {
         rd.add(2 * H * F, F, F, a.g_b2, F, 0);
         PFS_TRY(rd.run(wpart, grid, pstride, st));
     }
-    PFS_TRY(class_sums(tp, stage, H, dPt, st));
+    PFS_TRY(class_sums(tp, stage, H, dPt, cscs, st));
     PFS_TRY((node_linear_bwd<F, H>(dPs, (long long)tp.G * tp.S, a.w1, H, 0, a.g_x_s, st)));
     PFS_TRY((node_linear_bwd<F, H>(dPt, (long long)tp.G * tp.T, a.w1, H, F, a.g_x_t, st)));
     PFS_TRY((outer_rows<H, F, 8, F / 2>(dPs, a.x_s, (long long)tp.G * tp.S, opart, a.g_w1, H, 0, nullptr, st)));
@@ -586,6 +610,7 @@ int source_bwd_impl(const pfs_source_args& a, const Topo& tp) {
     float* tot3 = ws.f((size_t)tp.G * J);
     float* wpn = ws.f((size_t)gridn * pstride_n);
     float* stage = ws.f(class_stage_floats(tp, M));
+    float* cscs = ws.f(csc_scratch_floats(tp, M) + 1);
     float* dQt = ws.f((size_t)tp.G * tp.T * M);
     float* wpe = ws.f((size_t)gride * pstride_e);
     float* opart = ws.f((size_t)kMaxCtas * (M * F + M));
@@ -641,7 +666,7 @@ int source_bwd_impl(const pfs_source_args& a, const Topo& tp) {
         rd.add(M * F + M * M, M, M, a.g_b2, M, 0);
         PFS_TRY(rd.run(wpe, gride, pstride_e, st));
     }
-    PFS_TRY(class_sums(tp, stage, M, dQt, st));
+    PFS_TRY(class_sums(tp, stage, M, dQt, cscs, st));
     PFS_TRY((node_linear_bwd<F, M>(dQt, (long long)tp.G * tp.T, a.w1, M, 0, a.g_x_t, st)));
     PFS_TRY((outer_rows<M, F, 4, F / 2>(dQt, a.x_t, (long long)tp.G * tp.T, opart, a.g_w1, M, 0, a.g_b1, st)));
     return PFS_OK;
@@ -674,6 +699,7 @@ int target_fwd_impl(const pfs_target_args& a, const Topo& tp) {
     Bump ws(a.workspace, a.workspace_bytes);
     float* Rs = ws.f((size_t)tp.G * tp.S * M);
     float* stage = ws.f(class_stage_floats(tp, M));
+    float* cscs = ws.f(csc_scratch_floats(tp, M) + 1);
     if (!ws.ok) return fail(PFS_ERR_WORKSPACE, "target_fwd: workspace too small (%zu B)", a.workspace_bytes);
     if (a.normed) PFS_REQUIRE(a.gamma && a.beta && a.bn_save, "normed target model needs gamma, beta, bn_save");
     if (a.normed && a.training && tp.T <= 1)
@@ -687,7 +713,7 @@ int target_fwd_impl(const pfs_target_args& a, const Topo& tp) {
         k_target_edge_fwd<F><<<grid, kThreads, 0, st>>>(p);
         PFS_LAUNCH_CHECK("k_target_edge_fwd");
     }
-    PFS_TRY(class_sums(tp, stage, M, a.act_sum, st));
+    PFS_TRY(class_sums(tp, stage, M, a.act_sum, cscs, st));
     {
         TargetTailParams p = make_tail(a, tp);
         const size_t smem = sizeof(float) * ((size_t)tp.T * 8 * F + 4 * F);
@@ -728,7 +754,7 @@ int target_bwd_impl(const pfs_target_args& a, const Topo& tp) {
         TargetTailParams p = make_tail(a, tp);
         p.dasum = dasum;
         p.gpartial = gpart;
-        const size_t smem = sizeof(float) * ((size_t)tp.T * 12 * F + 6 * F);
+        const size_t smem = sizeof(float) * ((size_t)tp.T * 8 * F + 6 * F);
         if (smem > 200 * 1024) return fail(PFS_ERR_UNSUPPORTED, "target tail: T*F too large for one CTA (%zu B)", smem);
         PFS_TRY(allow_smem(k_target_tail_bwd, smem));
         k_target_tail_bwd<<<tp.G, kThreads, smem, st>>>(p);
@@ -928,7 +954,7 @@ size_t pfs_workspace_bytes(const pfs_topology* t) {
     fl += G * T * 16 * F;
     fl += G * ntiles * (T * 4 * F + 4 * F + 8);         // per-tile class partials and BatchNorm partials
     fl += G * ntn * (12 * F + 8);
-    if (t->layout != PFS_LAYOUT_DENSE) fl += G * E * 4 * F;
+    if (t->layout != PFS_LAYOUT_DENSE) fl += G * E * 4 * F + G * 64 * T * 4 * F;   // materialised rows + CSC chunk partials
     fl += (size_t)kMaxCtas * (100 * F * F + 32 * F + 64) * 2;   // per-CTA weight-gradient partials
     fl += 2 * kConstFloats;                                       // weight staging for the constant bank
     fl += G * (36 * F * F + 128 * F);

@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(kThreads) k_edge_bn_bwd_stats(const EdgeBnStat
 __global__ void k_edge_bn_bwd_coef(int stage, int mode, int F, int G, int ntiles, long long n_rows,
                                    const float* __restrict__ save, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, const float* __restrict__ rm,
-                                   const float* __restrict__ rv, float eps, const float* __restrict__ partial,
+                                   const float* __restrict__ rv, float eps, const double* __restrict__ sums,
                                    float* __restrict__ coef, float* __restrict__ dgb) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= G * F) return;
@@ -162,11 +162,7 @@ __global__ void k_edge_bn_bwd_coef(int stage, int mode, int F, int G, int ntiles
             c[4 * F + f] = s[3 * F + f];
         } else {
             // sum g and sum g * z come from the statistics pass (xhat == z here)
-            double sg = 0.0, sgz = 0.0;
-            for (int t = 0; t < ntiles; ++t) {
-                sg += partial[((size_t)g * ntiles + t) * 2 * F + f];
-                sgz += partial[((size_t)g * ntiles + t) * 2 * F + F + f];
-            }
+            const double sg = sums[(size_t)g * 2 * F + f], sgz = sums[(size_t)g * 2 * F + F + f];
             // dgamma = sum g c [(y1 - m) + a (z - m)] = c [ 2a (sgz - m sg) + (bt - m) sg ]
             dgb[(size_t)g * 2 * F + f] = (float)(cc * (2.0 * a * (sgz - m * sg) + (bt - m) * sg));
             dgb[(size_t)g * 2 * F + F + f] = (float)((a + 1.0) * sg);
@@ -185,11 +181,7 @@ __global__ void k_edge_bn_bwd_coef(int stage, int mode, int F, int G, int ntiles
         c[4 * F + f] = (float)bt;
         return;
     }
-    double sg = 0.0, sgx = 0.0;
-    for (int t = 0; t < ntiles; ++t) {
-        sg += partial[((size_t)g * ntiles + t) * 2 * F + f];
-        sgx += partial[((size_t)g * ntiles + t) * 2 * F + F + f];
-    }
+    const double sg = sums[(size_t)g * 2 * F + f], sgx = sums[(size_t)g * 2 * F + F + f];
     const double n = (double)n_rows;
     const double gbar = sg / n, mgx = sgx / n;
     const double sc = gm * r2, q = var * r1 * r1;

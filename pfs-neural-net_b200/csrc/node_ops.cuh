@@ -213,18 +213,64 @@ __global__ void k_class_reduce(const float* __restrict__ part, int ntiles, int T
 }
 
 // general layout: out[g][c][j] = sum over the class's edges (class-sorted order) of rows[g][q][j]
-__global__ void k_csc_segment_sum(const float* __restrict__ rows, const int* __restrict__ colptr,
-                                  const int* __restrict__ cscq, int E, int T, int J, float* __restrict__ out) {
-    // one warp per (graph, class): lanes stride over features, fixed edge order
-    const int g = blockIdx.y;
-    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (c >= T) return;
-    const int lane = threadIdx.x & 31;
-    const int a = colptr[c], b = colptr[c + 1];
-    for (int j = lane; j < J; j += 32) {
+// grid (T, nchunk, G), 128 threads: a block sums one chunk of one class's edge list; thread = (row lane,
+// feature), row lanes summed in a fixed order through shared memory.  nchunk > 1 writes partials
+// [g][chunk][c][J] for k_csc_segment_final (a few hundred long class segments must fill the device).
+constexpr int kCscThreads = 128;
+__global__ void __launch_bounds__(kCscThreads) k_csc_segment_sum(const float* __restrict__ rows, const int* __restrict__ colptr,
+                                                                 const int* __restrict__ cscq, int E, int T, int J, int nchunk,
+                                                                 float* __restrict__ out, float* __restrict__ partial) {
+    __shared__ float red[kCscThreads];
+    const int c = blockIdx.x, chunk = blockIdx.y, g = blockIdx.z;
+    const int a = colptr[c], len = colptr[c + 1] - a;
+    const int i0 = a + (int)((long long)len * chunk / nchunk), i1 = a + (int)((long long)len * (chunk + 1) / nchunk);
+    const int lanes = kCscThreads / J;                       // J <= 128
+    const int lr = threadIdx.x / J, j = threadIdx.x - lr * J;
+    const float* base = rows + (size_t)g * E * J + j;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (lr < lanes) {
+        int k = i0 + lr;
+        for (; k + 3 * lanes < i1; k += 4 * lanes) {         // four gathers in flight per thread
+            const int q0 = cscq[k], q1 = cscq[k + lanes], q2 = cscq[k + 2 * lanes], q3 = cscq[k + 3 * lanes];
+            s0 += base[(size_t)q0 * J]; s1 += base[(size_t)q1 * J];
+            s2 += base[(size_t)q2 * J]; s3 += base[(size_t)q3 * J];
+        }
+        for (; k < i1; k += lanes) s0 += base[(size_t)cscq[k] * J];
+    }
+    red[threadIdx.x] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (lr == 0) {
         float s = 0.f;
-        for (int k = a; k < b; ++k) s += rows[((size_t)g * E + cscq[k]) * J + j];
-        out[((size_t)g * T + c) * J + j] = s;
+        for (int r = 0; r < lanes; ++r) s += red[r * J + j];
+        if (nchunk > 1) partial[(((size_t)g * nchunk + chunk) * T + c) * J + j] = s;
+        else out[((size_t)g * T + c) * J + j] = s;
+    }
+}
+__global__ void k_csc_segment_final(const float* __restrict__ partial, int nchunk, int TJ, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, g = blockIdx.y;
+    if (i >= TJ) return;
+    float s = 0.f;
+    for (int q = 0; q < nchunk; ++q) s += partial[((size_t)g * nchunk + q) * TJ + i];
+    out[(size_t)g * TJ + i] = s;
+}
+
+// sums of the per-tile BatchNorm-backward partials of a graph: out[g][0..2F) in double, fixed order
+// (one CTA per graph, threads stride over the tiles: a single large graph has tens of thousands of tiles)
+__global__ void __launch_bounds__(256) k_tile_partial_sums(const float* __restrict__ partial, int ntiles, int F2,
+                                                           double* __restrict__ out) {
+    __shared__ double red[256];
+    const int g = blockIdx.x;
+    const int lanes = 256 / F2;
+    const int lr = threadIdx.x / F2, f = threadIdx.x - lr * F2;
+    double s = 0.0;
+    if (lr < lanes)
+        for (int t = lr; t < ntiles; t += lanes) s += (double)partial[((size_t)g * ntiles + t) * F2 + f];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    if (lr == 0) {
+        double tot = 0.0;
+        for (int r = 0; r < lanes; ++r) tot += red[r * F2 + f];
+        out[(size_t)g * F2 + f] = tot;
     }
 }
 

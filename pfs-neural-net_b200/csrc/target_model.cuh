@@ -188,9 +188,9 @@ __global__ void __launch_bounds__(kThreads) k_target_tail_bwd(const TargetTailPa
     const int F = p.F, T = p.T, M = 2 * F, H = 4 * F, K3 = 3 * F;
     const int g = blockIdx.x;
     float* HC = sm;               // [T][3F]  hcat, later dhcat
-    float* A3 = HC + T * K3;      // [T][4F]
-    float* DH = A3 + T * H;       // [T][4F]
-    float* DY = DH + T * H;       // [T][F]
+    float* A3 = HC + T * K3;      // [T][4F]  hidden activations, overwritten in place by dh3
+    float* DH = A3;
+    float* DY = A3 + T * H;       // [T][F]
     float* b3e = DY + T * F;      // [4F]
     float* st = b3e + H;          // [2F] sum g, sum g xhat
     tail_forward_core(p, g, HC, A3, b3e);
@@ -255,7 +255,8 @@ __global__ void __launch_bounds__(kThreads) k_target_tail_bwd(const TargetTailPa
         for (int r = 0; r < T; ++r) s += DY[r * F + threadIdx.x];
         gp[tail_off_b4(F) + threadIdx.x] = s;
     }
-    // dh3
+    __syncthreads();              // dW4 has read every activation: dh3 may overwrite them
+    // dh3 (in place over the activations: only their sign is needed)
     for (int i = threadIdx.x; i < T * H; i += blockDim.x) {
         const int r = i / H, j = i - r * H;
         float s = 0.f;
@@ -290,7 +291,7 @@ __global__ void __launch_bounds__(kThreads) k_target_tail_bwd(const TargetTailPa
     }
     __syncthreads();
     // dhcat = dh3 . W3[:, :3F]  (overwrites HC after everyone is done with it)
-    float* DHC = A3;   // A3 is dead: reuse as [T][3F]
+    float* DHC = HC;   // hcat is dead after dW3: reuse as [T][3F]
     for (int i = threadIdx.x; i < T * K3; i += blockDim.x) {
         const int r = i / K3, k = i - r * K3;
         float s = 0.f;
