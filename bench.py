@@ -43,6 +43,10 @@ KERNEL_ROWS = {
     "k_source_edge_fwd": (1, 10), "k_source_edge_bwd": (2, 18), "k_target_edge_fwd": (1, 2),
     "k_target_edge_bwd": (2, 2), "k_source_node_fwd": (0, 22), "k_source_node_bwd": (0, 32),
 }
+# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` captures of
+# the default C3 workload (profiles/r01_ncu_full_fma_path.txt); reported as `roofline.traffic` for that workload only
+KERNEL_TRAFFIC_C3 = {"k_edge_bwd": 1404.3e6, "k_source_node_bwd": 766.2e6, "k_edge_fwd": 655.6e6,
+                     "k_source_edge_fwd": 502.8e6, "k_target_edge_bwd": 644.9e6}
 # executed multiply-accumulates per edge / per fibre, forward + backward, in units of F^2
 MAC_PER_EDGE_F2 = 60
 MAC_PER_FIBRE_F2 = 318
@@ -366,7 +370,10 @@ def run_ours(args):
             dur_s = tms / n * 1e-3
             achieved = bytes_per_launch / dur_s / 1e9
             roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s",
-                        "frac": achieved / hbm_gbs, "traffic": None, "peak_source": peak_src,
+                        "frac": achieved / hbm_gbs,
+                        "traffic": KERNEL_TRAFFIC_C3.get(top) if (args.workload == "c3" and (G, S, T, F) == (256, 2394, 12, 10))
+                        else None,
+                        "traffic_source": "ncu --set full capture under profiles/ (bytes per launch)", "peak_source": peak_src,
                         "avg_launch_ms": tms / n, "algorithmic_bytes_per_launch": bytes_per_launch,
                         "share_of_step": tms / tot, "binding": "fp32_fma (see fma)"}
     step_bytes = ((5.0 * F * 4 + (16 if args.workload == "c5a" else 0)) * E + 6.0 * (S + T) * F * 4) * G

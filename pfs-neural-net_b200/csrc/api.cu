@@ -605,6 +605,7 @@ int source_bwd_impl(const pfs_source_args& a, const Topo& tp) {
     Bump ws(a.workspace, a.workspace_bytes);
     float* Qt = ws.f((size_t)tp.G * tp.T * M);
     float* bnstat = ws.f((size_t)tp.G * 2 * F);
+    float* bnpart = ws.f((size_t)tp.G * 64 * 2 * F);
     float* coefA = ws.f((size_t)tp.G * tp.S * 4 * M);
     float* tot3p = ws.f((size_t)tp.G * ntn * J);
     float* tot3 = ws.f((size_t)tp.G * J);
@@ -617,9 +618,15 @@ int source_bwd_impl(const pfs_source_args& a, const Topo& tp) {
     float* wstage = ws.f(kConstFloats);
     if (!ws.ok) return fail(PFS_ERR_WORKSPACE, "source_bwd: workspace too small (%zu B)", a.workspace_bytes);
     if (mode != 0) {
-        k_bn_bwd_stats_rows<<<tp.G, kThreads, sizeof(float) * kWarps * 2 * F, st>>>(a.g_out, a.y_pre, a.bn_save, tp.S, F,
-                                                                                    a.eps, bnstat);
+        int nchunk = (tp.S + 4095) / 4096;           // one CTA per 4096 fibres of a graph (1 for the C3 graphs)
+        if (nchunk > 64) nchunk = 64;
+        k_bn_bwd_stats_rows<<<dim3(nchunk, tp.G), kThreads, sizeof(float) * 2 * kThreads, st>>>(
+            a.g_out, a.y_pre, a.bn_save, tp.S, F, a.eps, nchunk, nchunk > 1 ? bnpart : bnstat);
         PFS_LAUNCH_CHECK("k_bn_bwd_stats_rows");
+        if (nchunk > 1) {
+            k_bn_bwd_stats_final<<<(tp.G * 2 * F + 127) / 128, 128, 0, st>>>(bnpart, nchunk, 2 * F, tp.G, bnstat);
+            PFS_LAUNCH_CHECK("k_bn_bwd_stats_final");
+        }
         PFS_TRY(colsum_all(bnstat, tp.G, 2 * F, F, F, a.g_gamma, st));
         PFS_TRY(colsum_all(bnstat, tp.G, 2 * F, 0, F, a.g_beta, st));
     }
@@ -958,6 +965,7 @@ size_t pfs_workspace_bytes(const pfs_topology* t) {
     fl += (size_t)kMaxCtas * (100 * F * F + 32 * F + 64) * 2;   // per-CTA weight-gradient partials
     fl += 2 * kConstFloats;                                       // weight staging for the constant bank
     fl += G * (36 * F * F + 128 * F);
+    fl += G * 64 * 2 * F + 64;                                   // chunk partials of the node BatchNorm backward sums
     fl += 4096;
     return fl * sizeof(float) + 64 * 256;
 }
@@ -1091,7 +1099,7 @@ int pfs_global_fwd(const pfs_global_args* a) {
     PFS_REQUIRE(a->u_out, "null pointer");
     cudaStream_t st = (cudaStream_t)a->stream;
     prof_mark(nullptr, st);
-    const size_t smem = sizeof(float) * (22 * (size_t)a->F + 2);
+    const size_t smem = sizeof(float) * (kThreads + 14 * (size_t)a->F + 2);
     k_global_fwd<<<a->G, kThreads, smem, st>>>(p);
     PFS_LAUNCH_CHECK("k_global_fwd");
     return PFS_OK;
@@ -1108,7 +1116,7 @@ int pfs_global_bwd(const pfs_global_args* a) {
     float* gpart = ws.f((size_t)a->G * pg);
     if (!ws.ok) return fail(PFS_ERR_WORKSPACE, "global_bwd: workspace too small");
     p.gpartial = gpart;
-    const size_t smem = sizeof(float) * (22 * (size_t)F + 2);
+    const size_t smem = sizeof(float) * (kThreads + 14 * (size_t)F + 2);
     k_global_bwd<<<a->G, kThreads, smem, st>>>(p);
     PFS_LAUNCH_CHECK("k_global_bwd");
     {

@@ -444,35 +444,53 @@ __global__ void k_affine_rows(const float* __restrict__ in, const float* __restr
 // BatchNorm backward statistics over node rows: per graph sum_r g and sum_r g * xhat,
 // xhat = (y - mean) * rsqrt(var + eps).  One CTA per graph (rows <= a few thousand per graph).
 // out[g][0][f] = sum g, out[g][1][f] = sum g * xhat
+// grid (nchunk, G): chunk c of graph g covers rows [rows*c/nchunk, rows*(c+1)/nchunk); nchunk == 1 writes
+// out[g][2F] directly, otherwise partial[g][chunk][2F] for k_bn_bwd_stats_final
 __global__ void k_bn_bwd_stats_rows(const float* __restrict__ gout, const float* __restrict__ y,
-                                    const float* __restrict__ save, int rows, int F, float eps,
+                                    const float* __restrict__ save, int rows, int F, float eps, int nchunk,
                                     float* __restrict__ out) {
-    extern __shared__ float red[];  // [nwarp][2F]
-    const int g = blockIdx.x;
-    const int nw = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // thread = (row lane, feature): coalesced single pass over the rows, row lanes summed in order
+    extern __shared__ float red[];  // [2][blockDim.x]
+    const int chunk = blockIdx.x, g = blockIdx.y;
+    const int lanes = blockDim.x / F;
+    const int lr = threadIdx.x / F, f = threadIdx.x - lr * F;
     const float* s = save + (size_t)g * 4 * F;
-    for (int f = 0; f < F; ++f) {
+    const int r_begin = (int)((long long)rows * chunk / nchunk), r_end = (int)((long long)rows * (chunk + 1) / nchunk);
+    float a0 = 0.f, b0 = 0.f, a1 = 0.f, b1 = 0.f;
+    if (lr < lanes) {
         const float mean = s[f], r = rsqrtf(s[F + f] + eps);
-        float a = 0.f, b = 0.f;
-        for (int rr = threadIdx.x; rr < rows; rr += blockDim.x) {
-            const size_t idx = ((size_t)g * rows + rr) * F + f;
-            const float gv = gout[idx];
-            a += gv;
-            b += gv * ((y[idx] - mean) * r);
+        int rr = r_begin + lr;
+        for (; rr + lanes < r_end; rr += 2 * lanes) {
+            const size_t i0 = ((size_t)g * rows + rr) * F + f, i1 = i0 + (size_t)lanes * F;
+            const float g0 = gout[i0], g1 = gout[i1], y0 = y[i0], y1 = y[i1];
+            a0 += g0; a1 += g1;
+            b0 += g0 * ((y0 - mean) * r);
+            b1 += g1 * ((y1 - mean) * r);
         }
-        a = warp_sum(a);
-        b = warp_sum(b);
-        if (lane == 0) {
-            red[w * 2 * F + f] = a;
-            red[w * 2 * F + F + f] = b;
+        if (rr < r_end) {
+            const size_t i0 = ((size_t)g * rows + rr) * F + f;
+            const float g0 = gout[i0];
+            a0 += g0;
+            b0 += g0 * ((y[i0] - mean) * r);
         }
     }
+    red[threadIdx.x] = a0 + a1;
+    red[blockDim.x + threadIdx.x] = b0 + b1;
     __syncthreads();
     if (threadIdx.x < 2 * F) {
+        const int which = threadIdx.x / F, ff = threadIdx.x - which * F;
         float t = 0.f;
-        for (int i = 0; i < nw; ++i) t += red[i * 2 * F + threadIdx.x];
-        out[(size_t)g * 2 * F + threadIdx.x] = t;
+        for (int i = 0; i < lanes; ++i) t += red[which * blockDim.x + i * F + ff];
+        out[((size_t)g * nchunk + chunk) * 2 * F + threadIdx.x] = t;
     }
+}
+__global__ void k_bn_bwd_stats_final(const float* __restrict__ partial, int nchunk, int F2, int G, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= G * F2) return;
+    const int g = i / F2, f = i - g * F2;
+    float s = 0.f;
+    for (int c = 0; c < nchunk; ++c) s += partial[((size_t)g * nchunk + c) * F2 + f];
+    out[i] = s;
 }
 
 }  // namespace pfs

@@ -419,20 +419,28 @@ __host__ __device__ constexpr int glob_off_b2(int F) { return 12 * F * F + 3 * F
 __host__ __device__ constexpr int glob_off_rms(int F) { return 12 * F * F + 4 * F; }      // [F]
 __host__ __device__ constexpr int global_partial_floats(int F) { return 12 * F * F + 5 * F; }
 
-// column means of x [rows, F] of graph g into out[0..F) (fixed order); blockDim.x threads
+// column means of x [rows, F] of graph g into out[0..F) (fixed order); blockDim.x threads.
+// thread = (row lane, feature): consecutive threads read consecutive addresses, one pass over the rows
+// (a single large graph has 1e5 rows here); scratch: blockDim.x floats
 __device__ __forceinline__ void column_means(const float* x, int rows, int F, float* scratch, float* out) {
-    // scratch: [blockDim.x / 32][F]
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int f = 0; f < F; ++f) {
-        float s = 0.f;
-        for (int r = threadIdx.x; r < rows; r += blockDim.x) s += x[(size_t)r * F + f];
-        s = warp_sum(s);
-        if (lane == 0) scratch[w * F + f] = s;
+    const int lanes = blockDim.x / F;
+    const int lr = threadIdx.x / F, f = threadIdx.x - lr * F;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (lr < lanes) {
+        int r = lr;
+        for (; r + 3 * lanes < rows; r += 4 * lanes) {      // four loads in flight per thread
+            s0 += x[(size_t)r * F + f];
+            s1 += x[(size_t)(r + lanes) * F + f];
+            s2 += x[(size_t)(r + 2 * lanes) * F + f];
+            s3 += x[(size_t)(r + 3 * lanes) * F + f];
+        }
+        for (; r < rows; r += lanes) s0 += x[(size_t)r * F + f];
     }
+    scratch[threadIdx.x] = (s0 + s1) + (s2 + s3);
     __syncthreads();
     if (threadIdx.x < F) {
         float s = 0.f;
-        for (int i = 0; i < nw; ++i) s += scratch[i * F + threadIdx.x];
+        for (int i = 0; i < lanes; ++i) s += scratch[i * F + threadIdx.x];
         out[threadIdx.x] = s / (float)rows;
     }
     __syncthreads();
@@ -479,12 +487,12 @@ __device__ __forceinline__ void global_core(const GlobalParams& p, int g, float*
     __syncthreads();
 }
 
-// dynamic shared memory: (8 * F) scratch + 3F + 3F + F + F + F + 2 + 3F + F floats
+// dynamic shared memory: kThreads scratch + 3F + 3F + F + F + F + 2 (+ 3F + F + F in the backward) floats
 __global__ void __launch_bounds__(kThreads) k_global_fwd(const GlobalParams p) {
     extern __shared__ __align__(16) float sm[];
     const int F = p.F;
     float* scratch = sm;
-    float* hc = scratch + kWarps * F;
+    float* hc = scratch + kThreads;
     float* h = hc + 3 * F;
     float* y = h + 3 * F;
     float* o1 = y + F;
@@ -499,7 +507,7 @@ __global__ void __launch_bounds__(kThreads) k_global_bwd(const GlobalParams p) {
     extern __shared__ __align__(16) float sm[];
     const int F = p.F, K = 3 * F;
     float* scratch = sm;
-    float* hc = scratch + kWarps * F;
+    float* hc = scratch + kThreads;
     float* h = hc + 3 * F;
     float* y = h + 3 * F;
     float* o1 = y + F;
