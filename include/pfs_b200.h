@@ -319,6 +319,16 @@ int pfs_wide_source_dm(const void* m_bf16, const float* moments, const float* co
 /* out[e] = tab[idx ? idx[e] : e % mod] * (act[e] > 0 ? 1 : 0.1)   (TModel backward, src/gnn.py:188-190) */
 int pfs_wide_gather_mask(const float* tab, const int32_t* idx, int32_t mod, const void* act_bf16, int64_t E, int32_t C,
                          void* out_bf16, void* stream);
+/* Time head on the wide path (src/gnn.py:307-312): a [E,F] = lrelu(x_e W1^T + b1) from pfs_wide_gemm_nt;
+ * pred = a . w2 + b2, time = softplus(pred) * scale; optional integer outputs (NULL to skip):
+ * visits = rint(time / class_hours[tgt]), time_int = visits * class_hours[tgt] (tgt NULL: e % T).
+ * Backward: gp[e] = g_time[e] sigmoid(pred[e]) scale and da = gp w2 lrelu'(a) (bf16 [E,F]); the weight
+ * gradients follow from pfs_wide_colstats (roww = gp) and pfs_wide_gemm_tn / _nt on da. */
+int pfs_wide_head_fwd(const void* a_bf16, const float* w2, const float* b2, float scale, int64_t E, int32_t F,
+                      const float* class_hours, const int32_t* tgt, int32_t T, float* pred, float* time, float* visits,
+                      float* time_int, void* stream);
+int pfs_wide_head_bwd(const void* a_bf16, const float* w2, const float* pred, const float* g_time, float scale, int64_t E,
+                      int32_t F, float* gp, void* da_bf16, void* stream);
 /* dtype conversion (0 = bf16, 1 = fp32) and bf16 transpose out[c][r] = in[r][c] */
 int pfs_wide_cast(const void* in, int32_t in_dtype, void* out, int32_t out_dtype, int64_t n, void* stream);
 int pfs_wide_transpose(const void* in_bf16, int32_t R, int32_t C, int64_t ld, void* out_bf16, void* stream);

@@ -382,6 +382,31 @@ int pfs_wide_gather_mask(const float* tab, const int32_t* idx, int32_t mod, cons
     return PFS_OK;
 }
 
+int pfs_wide_head_fwd(const void* a_bf16, const float* w2, const float* b2, float scale, int64_t E, int32_t F,
+                      const float* class_hours, const int32_t* tgt, int32_t T, float* pred, float* time, float* visits,
+                      float* time_int, void* stream) {
+    W_REQUIRE(a_bf16 && w2 && b2 && pred && time && E >= 1, "bad arguments");
+    W_REQUIRE(F >= 8 && F % 8 == 0 && F <= 256 && ((F >> 3) & ((F >> 3) - 1)) == 0, "time head: Fdim must be 8 * a power of two, <= 256");
+    if (visits || time_int) W_REQUIRE(visits && time_int && class_hours && (tgt || T >= 1), "integer outputs need hours and classes");
+    cudaStream_t st = (cudaStream_t)stream;
+    pfs_host::mark_launch(nullptr, st);
+    const int rows_per_block = 8 * (32 / (F >> 3));
+    k_wide_head_fwd<<<grid_for(E, rows_per_block), 256, 0, st>>>((const bf16*)a_bf16, w2, b2, scale, E, F, class_hours, tgt, T,
+                                                                  pred, time, visits, time_int);
+    W_LAUNCH_CHECK("k_wide_head_fwd");
+    return PFS_OK;
+}
+
+int pfs_wide_head_bwd(const void* a_bf16, const float* w2, const float* pred, const float* g_time, float scale, int64_t E,
+                      int32_t F, float* gp, void* da_bf16, void* stream) {
+    W_REQUIRE(a_bf16 && w2 && pred && g_time && gp && da_bf16 && E >= 1 && F >= 8 && F % 8 == 0, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    pfs_host::mark_launch(nullptr, st);
+    k_wide_head_bwd<<<grid_for(E * (F / 8)), 256, 0, st>>>((const bf16*)a_bf16, w2, pred, g_time, scale, E, F, gp, (bf16*)da_bf16);
+    W_LAUNCH_CHECK("k_wide_head_bwd");
+    return PFS_OK;
+}
+
 int pfs_wide_cast(const void* in, int32_t in_dtype, void* out, int32_t out_dtype, int64_t n, void* stream) {
     W_REQUIRE(in && out && n >= 1, "bad arguments");
     cudaStream_t st = (cudaStream_t)stream;

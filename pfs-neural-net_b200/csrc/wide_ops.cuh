@@ -492,6 +492,71 @@ __global__ void __launch_bounds__(256) k_wide_gather_mask(const float* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
+// time head (reference src/gnn.py:307-312): pred = a . w2 + b2 over the hidden activation a [E,F] (bf16),
+// time = softplus(pred) * scale; optional integer outputs visits = rint(time / hours[tgt]), time_int = visits * hours
+// (DESIGN.md section 8).  A group of F/8 lanes owns a row (16-byte loads), dot product by shuffles.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float wide_softplus(float x) { return x > 20.f ? x : log1pf(expf(x)); }   // torch threshold 20
+__global__ void __launch_bounds__(256) k_wide_head_fwd(const bf16* __restrict__ a, const float* __restrict__ w2,
+                                                       const float* __restrict__ b2, float scale, long long E, int F,
+                                                       const float* __restrict__ hours, const int* __restrict__ tgt, int T,
+                                                       float* __restrict__ pred_out, float* __restrict__ time,
+                                                       float* __restrict__ visits, float* __restrict__ time_int) {
+    const int gl = F >> 3;                       // lanes per row (power of two <= 32 is required by the host)
+    const int rows_per_warp = 32 / gl;
+    const int lane = threadIdx.x & 31, sub = lane / gl, lc = lane - sub * gl;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    float w[8];
+    ld8f(w2 + 8 * lc, w);
+    const float bias = b2[0];
+    for (long long r0 = warp0 * rows_per_warp; r0 < E; r0 += nwarps * rows_per_warp) {
+        const long long e = r0 + sub;
+        float s = 0.f;
+        if (e < E) {
+            float v[8];
+            ld8(a + e * F + 8 * lc, v);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) s = fmaf(v[q], w[q], s);
+        }
+        for (int o = gl >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (e < E && lc == 0) {
+            const float p = s + bias;
+            const float t = wide_softplus(p) * scale;
+            pred_out[e] = p;
+            time[e] = t;
+            if (visits) {
+                const float h = hours[tgt ? tgt[e] : (int)(e % T)];
+                const float vs = rintf(t / h);
+                visits[e] = vs;
+                time_int[e] = vs * h;
+            }
+        }
+    }
+}
+// backward: gp[e] = g[e] * sigmoid(pred[e]) * scale; da[e][:] = gp[e] * w2[:] * lrelu'(a[e][:])  (bf16 [E,F])
+__global__ void __launch_bounds__(256) k_wide_head_bwd(const bf16* __restrict__ a, const float* __restrict__ w2,
+                                                       const float* __restrict__ pred, const float* __restrict__ g, float scale,
+                                                       long long E, int F, float* __restrict__ gp, bf16* __restrict__ da) {
+    const int groups = F >> 3;
+    const long long total = E * groups;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long e = i / groups;
+        const int c = 8 * (int)(i - e * groups);
+        const float p = pred[e];
+        const float sg = p > 20.f ? 1.f : 1.f / (1.f + expf(-p));
+        const float coeff = g[e] * sg * scale;
+        if (c == 0) gp[e] = coeff;
+        float v[8], w[8], o[8];
+        ld8(a + e * F + c, v);
+        ld8f(w2 + c, w);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) o[q] = coeff * w[q] * (v[q] > 0.f ? 1.f : 0.1f);
+        st8(da + e * F + c, o);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // layout helpers
 // ------------------------------------------------------------------------------------------------
 template <class TI, class TO>

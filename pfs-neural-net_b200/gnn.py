@@ -290,10 +290,14 @@ class GNN(torch.nn.Module):
     def edge_prediction(self, x_e, scale=1, edge_index=None):
         """softplus(decoder_e(x_e)) * scale, [E, 1] (reference src/gnn.py:307-312; `round` is the
         identity there, see `round`).  The time head does not depend on the topology."""
+        d = self.decoder_e
+        if pw.supported(x_e.shape[-1], x_e.dtype):
+            if x_e.dim() != 2:
+                raise RuntimeError("the bf16 wide path takes one graph per call (2-D tensors)")
+            return pw.WideTimeHeadFunction.apply(scale, x_e, d[0].weight, d[0].bias, d[2].weight, d[2].bias).unsqueeze(-1)
         single = x_e.dim() == 2
         xe3 = x_e.unsqueeze(0) if single else x_e
         topo = _FlatTopology(xe3.shape[1], x_e.device)
-        d = self.decoder_e
         time = pf.TimeHeadFunction.apply(topo, scale, xe3, d[0].weight, d[0].bias, d[2].weight, d[2].bias)
         time = time.unsqueeze(-1)
         return time[0] if single else time
@@ -301,10 +305,13 @@ class GNN(torch.nn.Module):
     def integer_times(self, x_e, class_hours, scale=1, edge_index=None):
         """(time, visits, time_int): visits = round-half-even(time / T_i[tgt]), time_int = visits * T_i.
         This is the "rounded integer time" this build defines (reference src/train.py:257)."""
+        d = self.decoder_e
+        if pw.supported(x_e.shape[-1], x_e.dtype):
+            topo = self._head_topology(x_e.unsqueeze(0), edge_index)
+            return pw.integer_times(topo.wide(), x_e, d[0].weight, d[0].bias, d[2].weight, d[2].bias, scale, class_hours)
         single = x_e.dim() == 2
         xe3 = x_e.unsqueeze(0) if single else x_e
         topo = self._head_topology(xe3, edge_index)
-        d = self.decoder_e
         out = pf.integer_times(topo, xe3, d[0].weight, d[0].bias, d[2].weight, d[2].bias, scale,
                                class_hours.to(torch.float32))
         return tuple(o[0] for o in out) if single else out

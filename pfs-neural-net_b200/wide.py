@@ -452,3 +452,41 @@ class WideGlobalFunction(torch.autograd.Function):
         g_x_t = _bf((dcat[:, 2 * F:] / T).expand(T, F))
         return (None, g_x_s, g_x_t, g_u, _like(g_w1, w1), _like(dh.float()[0], b1), _like(g_w2, w2), _like(dy[0], b2),
                 g_rms, None)
+
+
+# ------------------------------------------------------------------------------------------------ time head
+class WideTimeHeadFunction(torch.autograd.Function):
+    """GNN.edge_prediction (reference src/gnn.py:307-312) on the wide path: the first layer is a tcgen05 GEMM with
+    the LeakyReLU in its epilogue, the F -> 1 layer, softplus and scale are one streaming kernel."""
+
+    @staticmethod
+    def forward(ctx, scale, x_e, w1, b1, w2, b2):
+        x_e, w1 = x_e.contiguous(), w1.contiguous()
+        a = wo.gemm_nt(x_e, w1, bias=_f32(b1), act=True)                     # [E,F] bf16
+        w2f, b2f = _f32(w2.reshape(-1)), _f32(b2.reshape(-1))
+        pred, time, _, _ = wo.head_fwd(a, w2f, b2f, scale)
+        ctx.scale = float(scale)
+        ctx.save_for_backward(x_e, w1, b1, w2, b2, a, w2f, pred)
+        return wo.cast(time, x_e.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        x_e, w1, b1, w2, b2, a, w2f, pred = ctx.saved_tensors
+        E = x_e.shape[0]
+        gp, da = wo.head_bwd(a, w2f, pred, _f32(g.reshape(-1)), ctx.scale)
+        g_w2 = wo.colstats(1, a, roww=gp[:E])[0]                              # sum_e gp[e] a[e]
+        g_b2 = _colsum(gp.view(-1, 2)).sum().reshape(1)
+        g_w1 = wo.gemm_tn(da, x_e)
+        g_b1 = _colsum(da)
+        g_x_e = wo.gemm_nt(da, wo.transpose(w1))
+        g_w1, g_b1, g_w2, g_b2 = (_shard.allreduce_sum(t) for t in (g_w1, g_b1, g_w2, g_b2))
+        return None, g_x_e, _like(g_w1, w1), _like(g_b1, b1), _like(g_w2.reshape(w2.shape), w2), _like(g_b2.reshape(b2.shape), b2)
+
+
+def integer_times(wt, x_e, w1, b1, w2, b2, scale, class_hours):
+    """(time, visits, time_int), fp32 [E] each: the integer definition of DESIGN.md section 8 on the wide path."""
+    with torch.no_grad():
+        a = wo.gemm_nt(x_e.contiguous(), w1.contiguous(), bias=_f32(b1), act=True)
+        _, time, visits, time_int = wo.head_fwd(a, _f32(w2.reshape(-1)), _f32(b2.reshape(-1)), scale,
+                                                class_hours=class_hours.float().contiguous(), tgt=wt.tgt, T=wt.T)
+    return time, visits, time_int

@@ -257,3 +257,36 @@ def transpose(w):
         _abi.check(_abi.load_library().pfs_wide_transpose(w.data_ptr(), R, C, w.stride(0), out.data_ptr(), _stream(w.device)),
                    "pfs_wide_transpose")
     return out
+
+
+def head_fwd(a, w2, b2, scale, class_hours=None, tgt=None, T=0):
+    """Time head tail: pred = a . w2 + b2, time = softplus(pred) * scale (+ integer visits / times)."""
+    _chk(a, BF16, "a"), _chk(w2, F32, "w2"), _chk(b2, F32, "b2")
+    a = a.contiguous()
+    E, F = a.shape
+    dev = a.device
+    pred = torch.empty(E, dtype=F32, device=dev)
+    time = torch.empty(E, dtype=F32, device=dev)
+    visits = time_int = None
+    if class_hours is not None:
+        _chk(class_hours, F32, "class_hours")
+        visits, time_int = torch.empty(E, dtype=F32, device=dev), torch.empty(E, dtype=F32, device=dev)
+    with torch.cuda.device(dev):
+        _abi.check(_abi.load_library().pfs_wide_head_fwd(
+            a.data_ptr(), w2.data_ptr(), b2.data_ptr(), float(scale), E, F, _abi.ptr(class_hours), _abi.ptr(tgt), int(T),
+            pred.data_ptr(), time.data_ptr(), _abi.ptr(visits), _abi.ptr(time_int), _stream(dev)), "pfs_wide_head_fwd")
+    return pred, time, visits, time_int
+
+
+def head_bwd(a, w2, pred, g_time, scale):
+    """(gp [E] fp32 padded to an even length with zeros, da [E,F] bf16) of the time head."""
+    _chk(a, BF16, "a"), _chk(g_time, F32, "g_time")
+    E, F = a.shape
+    dev = a.device
+    gp = torch.zeros(E + (E & 1), dtype=F32, device=dev)
+    da = torch.empty(E, F, dtype=BF16, device=dev)
+    with torch.cuda.device(dev):
+        _abi.check(_abi.load_library().pfs_wide_head_bwd(a.data_ptr(), w2.data_ptr(), pred.data_ptr(), g_time.data_ptr(),
+                                                         float(scale), E, F, gp.data_ptr(), da.data_ptr(), _stream(dev)),
+                   "pfs_wide_head_bwd")
+    return gp, da

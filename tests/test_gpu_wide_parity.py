@@ -145,3 +145,63 @@ def test_wide_rejects_cpu_and_batches():
     blk = blk.to(dev)
     with pytest.raises(RuntimeError):
         blk.edge_model(ins[0].to(dev)[None], ins[1].to(dev)[None], ei.to(dev), ins[2].to(dev)[None], ins[3].to(dev))
+
+
+@pytest.mark.parametrize("kind,F,S,T", [("dense", 32, 40, 16), ("csr", 128, 30, 12)])
+def test_wide_gnn_time_head(kind, F, S, T):
+    """GNN in bf16 end to end (encoders, Blocks, time head): edge times and their gradients against the fp64 oracle,
+    integer times exact against the same formula on the kernel's own times."""
+    from pfs_neural_net_b200 import gnn
+    dev = _dev()
+    ei = _graph(kind, S, T, seed=3)
+    E = ei.shape[1]
+    torch.manual_seed(4)
+    model = gnn.GNN(B=1, Fdim=F, T=T, F_s=1, F_t=2).to(torch.bfloat16).to(dev).train()
+    g = torch.Generator().manual_seed(8)
+    x_e = torch.randn(E, F, generator=g).bfloat16()
+    xe_dev = x_e.to(dev).requires_grad_(True)
+    time = model.edge_prediction(xe_dev, scale=3.5)
+    assert time.shape == (E, 1) and time.dtype == torch.bfloat16
+    up = torch.randn(E, 1, generator=g).bfloat16()
+    time.backward(up.to(dev))
+    sd = {k: v.detach().double().cpu() for k, v in model.state_dict().items() if k.startswith("decoder_e")}
+    sd = {k: v.requires_grad_(True) for k, v in sd.items()}
+    x64 = x_e.double().requires_grad_(True)
+    ref = bo.edge_prediction(sd, x64, 3.5)
+    ref.backward(up.double())
+    assert _err(time, ref) < TOL
+    assert _err(xe_dev.grad, x64.grad) < 2e-2
+    for k, p in model.decoder_e.named_parameters():
+        r = sd["decoder_e." + k].grad
+        assert _err(p.grad, r, max(r.abs().max().item(), 1e-6)) < 2e-2, k
+    hours = torch.rand(T, generator=g) * 2 + 0.5
+    t32, visits, t_int = model.integer_times(xe_dev.detach(), hours.to(dev), scale=3.5, edge_index=ei.to(dev))
+    assert _err(t32, ref.reshape(-1)) < TOL
+    per = hours.to(dev)[ei[1].to(dev)]
+    assert torch.equal(visits, torch.round(t32 / per))
+    assert torch.equal(t_int, visits * per)
+
+
+def test_wide_gnn_forward_backward_runs_in_bf16():
+    """The whole reference surface in bf16: GNN.forward (torch encoders + wide Blocks) -> BipartiteData -> time head."""
+    from pfs_neural_net_b200 import gnn
+    dev = _dev()
+    F, S, T = 32, 48, 16
+    ei = _graph("dense", S, T, seed=1).to(dev)
+    torch.manual_seed(0)
+    model = gnn.GNN(B=2, Fdim=F, T=T, F_s=1, F_t=2).to(torch.bfloat16).to(dev).train()
+    g = torch.Generator().manual_seed(2)
+    graph = gnn.BipartiteData(ei, torch.randn(S, 1, generator=g).bfloat16(), torch.randn(T, 2, generator=g).bfloat16(),
+                              torch.randn(S * T, F, generator=g).bfloat16(), torch.zeros(1, F).bfloat16())
+    out = model(graph)
+    assert out.x_e.shape == (S * T, F) and out.x_s.shape == (S, F) and out.x_t.shape == (T, F) and out.x_u.shape == (1, F)
+    time = model.edge_prediction(out.x_e, scale=3.5)
+    time.float().sum().backward()
+    # the last Block's node / global models do not feed the edge times (29 of 109 tensors stay without a gradient
+    # with the reference loss too, SURVEY.md section 3a)
+    for name, p in model.named_parameters():
+        expect = not (name.startswith("decoder_s") or name.startswith(("mpb.1.s_model", "mpb.1.t_model", "mpb.1.global_model")))
+        assert (p.grad is not None) == expect, name
+        if expect:
+            assert torch.isfinite(p.grad.float()).all(), name
+    assert int(model.mpb[0].edge_model.norm.num_batches_tracked) == 2      # the double BatchNorm (SURVEY.md 0.2)
