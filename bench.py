@@ -63,10 +63,11 @@ def parse_args():
     ap.add_argument("--classes", type=int, default=12)
     ap.add_argument("--fdim", type=int, default=10)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget of the cpu_baseline sample")
-    ap.add_argument("--workload", default="c3", choices=["c3", "c4", "c5", "c5a"],
+    ap.add_argument("--workload", default="c3", choices=["c3", "c4", "c5", "c5a", "n1"],
                     help="c3: 256 x 2394x12 graphs, Fdim 10 fp32 (headline); c4: one 12500*N x 512 graph, Fdim 128 bf16, "
                          "fibre-sharded over the N GPUs; c5: 10%% sparse 100000x512 edge list, Fdim 128 bf16 (CSR/CSC path); "
-                         "c5a: the same edge list at Fdim 10 fp32 through the narrow kernels")
+                         "c5a: the same edge list at Fdim 10 fp32 through the narrow kernels; "
+                         "n1: the training loss (softfloor + loss_function) forward+backward on 612864 x 12 edge times")
     ap.add_argument("--wide-fibres", type=int, default=12500, help="c4: fibres per GPU")
     ap.add_argument("--wide-classes", type=int, default=512)
     ap.add_argument("--wide-fdim", type=int, default=128)
@@ -639,8 +640,82 @@ def run_wide(args):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------
+# N1: the training loss that follows the path (reference src/train.py:21-80), forward + backward
+# ---------------------------------------------------------------------------------------------
+def run_loss(args):
+    from pfs_neural_net_b200 import _abi, loss as pl
+    from oracle import block_oracle as bo, loss_oracle as lo
+    S, T = args.fibres * args.graphs, args.classes            # one graph with the edge count of the C3 batch
+    E = S * T
+    g = torch.Generator().manual_seed(1)
+    class_info = torch.stack([0.5 + 3 * torch.rand(T, generator=g), 50 + 400 * torch.rand(T, generator=g)], 1)
+    if args.impl == "reference":
+        Sc = 20000
+        ncores = os.cpu_count() or 1
+        torch.set_num_threads(ncores)
+        ei = bo.complete_bipartite(Sc, T)
+        time_c, noise_c = 6 * torch.rand(Sc * T, generator=g), torch.rand(Sc * T, generator=g)
+        ts = []
+        for _ in range(args.warmup + args.steps):
+            tt = time_c.clone().requires_grad_(True)
+            t0 = time.perf_counter()
+            lo.loss_terms(tt, noise_c, class_info, ei, Sc, T)["loss"].backward()
+            ts.append(time.perf_counter() - t0)
+        ts = ts[args.warmup:]
+        eps = Sc * T * len(ts) / sum(ts)
+        print(json.dumps({"impl": "reference", "metric": "edges_per_sec_loss_fwd_bwd", "value": eps, "unit": UNIT, "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(ts) / len(ts), "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": "N1 loss fwd+bwd, CPU oracle port on %d x %d edge times" % (Sc, T)},
+                          "cpu_baseline": {"value": eps, "unit": UNIT, "cores": ncores, "kind": "port", "sample": "%d steps" % len(ts)},
+                          "e2e": {"value": eps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        return
+    dev = torch.device("cuda", 0)
+    lib = _abi.load_library()
+    ci = class_info.to(dev)
+    gen = torch.Generator(device=dev).manual_seed(2)
+    time_d = 6 * torch.rand(E, generator=gen, device=dev)
+    noise = torch.rand(E, generator=gen, device=dev)
+
+    def step():
+        t = time_d.detach().requires_grad_(True)
+        loss = pl.loss_from_times(t, ci, S, T, noise=noise)[0]
+        loss.backward()
+        return loss
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    torch.cuda.synchronize(dev)
+    sampler = ClockSampler(0)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = lib.pfs_launch_count()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = lib.pfs_launch_count() - n0
+    hbm_gbs, peak_src, _ = measured_peaks()
+    alg = 12.0 * E                                            # read time + noise, write g_time
+    print(json.dumps({"metric": "edges_per_sec_loss_fwd_bwd", "value": E / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+                      "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": "N1: training loss (softfloor + loss_function) forward+backward on %d x %d edge times"
+                                             % (S, T), "l2": "inputs larger than L2 (%.0f MB per tensor)" % (E * 4 / 1e6)},
+                      "roofline": {"kernel": "whole loss step (5 kernels)", "bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9,
+                                   "peak": hbm_gbs, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / hbm_gbs, "traffic": None,
+                                   "peak_source": peak_src, "algorithmic_bytes_per_step": alg},
+                      "gpu_launches": int(launches), "clocks": clocks}))
+
+
 def main():
     args = parse_args()
+    if args.workload == "n1":
+        return run_loss(args)
     if args.workload in ("c4", "c5"):
         run_wide(args)
     elif args.impl == "reference":

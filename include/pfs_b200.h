@@ -333,6 +333,40 @@ int pfs_wide_head_bwd(const void* a_bf16, const float* w2, const float* pred, co
 int pfs_wide_cast(const void* in, int32_t in_dtype, void* out, int32_t out_dtype, int64_t n, void* stream);
 int pfs_wide_transpose(const void* in_bf16, int32_t R, int32_t C, int64_t ld, void* out_bf16, void* stream);
 
+/* -------------------------------------------------------------------------------------------
+ * Training loss that consumes the edge times (reference src/train.py:21-80: softfloor + loss_function
+ * from `time = gnn.edge_prediction(...)` on).  fp32, one graph, dense
+ * canonical edge order e = k*T + i (the reference reshapes the times to [NFIBERS, NCLASSES],
+ * src/train.py:67).  `noise` is the uniform [0,1) draw of softfloor (torch.rand_like, src/train.py:22),
+ * supplied by the caller so the result is reproducible.
+ *   forward : galaxies = max(0, softfloor(time / T_i)), time2 = galaxies T_i, n'_i, fibre times, and
+ *             scalars = {loss, totutils (min completeness), class_penalty, fibre_penalty, variance, #minima}
+ *   backward: g_time = dloss/dtime * g_loss (g_loss: device scalar, NULL = 1)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct pfs_loss_args {
+    int32_t S, T;                                /* fibres, classes */
+    const float* time;                           /* [S*T] */
+    const float* noise;                          /* [S*T] uniform [0,1) */
+    const float* hours;                          /* [T] T_i = class_info[:,0] */
+    const float* counts;                         /* [T] N_i = class_info[:,1] / NFIELDS */
+    float total_time, wutils, wvar, pclass, pfiber, sharpness, noiselevel;   /* src/config.py:19,27-28; train.py:21,29 */
+    float* galaxies;                             /* [S*T] */
+    float* time2;                                /* [S*T] galaxies * T_i (the `time` of finaloutput) */
+    float* fibre_time;                           /* [S] */
+    float* n_prime;                              /* [T] */
+    float* class_mean;                           /* [T] mean over fibres of time2 */
+    float* class_coef;                           /* [T] dloss/dn'_i */
+    float* scalars;                              /* [8] */
+    const float* g_loss;                         /* backward: device scalar or NULL */
+    float* g_time;                               /* backward: [S*T] */
+    void* workspace; size_t workspace_bytes;     /* pfs_loss_workspace_bytes(S, T) */
+    void* stream;
+} pfs_loss_args;
+size_t pfs_sizeof_loss_args(void);
+size_t pfs_loss_workspace_bytes(int32_t S, int32_t T);
+int pfs_loss_fwd(const pfs_loss_args* a);
+int pfs_loss_bwd(const pfs_loss_args* a);
+
 #ifdef __cplusplus
 }
 #endif

@@ -116,6 +116,13 @@ class WideGemmArgs(ct.Structure):
     ]
 
 
+class LossArgs(ct.Structure):
+    _fields_ = [("S", ct.c_int32), ("T", ct.c_int32), ("time", _P), ("noise", _P), ("hours", _P), ("counts", _P)] + \
+        [(n, ct.c_float) for n in "total_time wutils wvar pclass pfiber sharpness noiselevel".split()] + \
+        [(n, _P) for n in "galaxies time2 fibre_time n_prime class_mean class_coef scalars g_loss g_time workspace".split()] + \
+        [("workspace_bytes", ct.c_size_t), ("stream", _P)]
+
+
 class WideSegments(ct.Structure):
     _fields_ = [("mode", ct.c_int32), ("nseg", ct.c_int32), ("S", ct.c_int32), ("T", ct.c_int32),
                 ("ptr", _P), ("list", _P)]
@@ -169,12 +176,18 @@ SYMBOLS = {
     "pfs_wide_head_fwd": (ct.c_int, [_P, _P, _P, ct.c_float, _I64, _I32, _P, _P, _I32, _P, _P, _P, _P, _P]),
     "pfs_wide_head_bwd": (ct.c_int, [_P, _P, _P, _P, ct.c_float, _I64, _I32, _P, _P, _P]),
     "pfs_wide_cast": (ct.c_int, [_P, _I32, _P, _I32, _I64, _P]),
+    # training loss (reference src/train.py:21-80)
+    "pfs_sizeof_loss_args": (ct.c_size_t, []),
+    "pfs_loss_workspace_bytes": (ct.c_size_t, [_I32, _I32]),
+    "pfs_loss_fwd": (ct.c_int, [ct.POINTER(LossArgs)]),
+    "pfs_loss_bwd": (ct.c_int, [ct.POINTER(LossArgs)]),
     "pfs_wide_transpose": (ct.c_int, [_P, _I32, _I32, _I64, _P, _P]),
 }
 _SIZEOF_CHECKS = {
     "pfs_sizeof_topology": TopologyStruct, "pfs_sizeof_edge_args": EdgeArgs, "pfs_sizeof_source_args": SourceArgs,
     "pfs_sizeof_target_args": TargetArgs, "pfs_sizeof_global_args": GlobalArgs, "pfs_sizeof_head_args": HeadArgs,
     "pfs_sizeof_wide_gemm_args": WideGemmArgs, "pfs_sizeof_wide_segments": WideSegments,
+    "pfs_sizeof_loss_args": LossArgs,
 }
 
 
@@ -190,6 +203,7 @@ _WIDE_HEADERS = ("wide_gemm.cuh", "wide_ops.cuh", "tc_ptx.cuh")
 _UNITS = {
     "api.cu": lambda f: f.endswith(".cuh") and not f.startswith("wide_"),
     "wide.cu": lambda f: f in _WIDE_HEADERS,
+    "loss.cu": lambda f: False,
 }
 
 

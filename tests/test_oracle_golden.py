@@ -89,3 +89,37 @@ def test_integer_time_definition():
     visits, t_int = bo.integer_times(time, hours, tgt)
     assert visits.tolist() == [2.0, 2.0, 2.0, 0.0]      # 1.5 -> 2 and 2.5 -> 2: round-half-even
     assert t_int.tolist() == [4.0, 4.0, 12.0, 0.0]
+
+
+# ---------------------------------------------------------------------------------------------
+# training loss: oracle/loss_oracle.py against the unmodified reference
+# ---------------------------------------------------------------------------------------------
+def _loss_cases():
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "loss_cases.pt")
+    return torch.load(path)
+
+
+def test_loss_oracle_matches_reference():
+    from oracle import loss_oracle as lo
+    cases = _loss_cases()
+    assert len(cases) == 8
+    for c in cases:
+        S, T = c["S"], c["T"]
+        tol = 1e-10 if c["time"].dtype == torch.float64 else 2e-5
+        time = c["time"].clone().requires_grad_(True)
+        r = lo.loss_terms(time, c["noise"], c["class_info"], bo.complete_bipartite(S, T), S, T, nfields=c["nfields"],
+                          total_time=c["total_time"], wutils=c["wutils"], wvar=c["wvar"])
+        r["loss"].backward()
+
+        def close(a, b, what):
+            err = (a.detach().double() - b.double()).abs().max().item() / max(b.double().abs().max().item(), 1e-30)
+            assert err < tol, (what, S, T, str(time.dtype), err)
+
+        close(r["loss"], c["loss"], "loss")
+        close(r["totutils"], c["totutils"], "totutils")
+        close(r["n_prime"], c["n_prime"], "n_prime")
+        close(r["fiber_time"], c["fiber_time"], "fiber_time")
+        close(r["time"], c["time2"], "time")
+        close(r["variance"], c["variance"], "variance")
+        close(time.grad, c["g_time"], "grad time")
