@@ -361,6 +361,8 @@ typedef struct pfs_loss_args {
     float* g_time;                               /* backward: [S*T] */
     void* workspace; size_t workspace_bytes;     /* pfs_loss_workspace_bytes(S, T) */
     void* stream;
+    const float* sharpness_dev;                  /* optional device scalar overriding `sharpness` (a sharpness schedule
+                                                    under CUDA-graph replay, src/train.py:139) */
 } pfs_loss_args;
 size_t pfs_sizeof_loss_args(void);
 size_t pfs_loss_workspace_bytes(int32_t S, int32_t T);

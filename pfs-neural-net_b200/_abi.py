@@ -120,7 +120,7 @@ class LossArgs(ct.Structure):
     _fields_ = [("S", ct.c_int32), ("T", ct.c_int32), ("time", _P), ("noise", _P), ("hours", _P), ("counts", _P)] + \
         [(n, ct.c_float) for n in "total_time wutils wvar pclass pfiber sharpness noiselevel".split()] + \
         [(n, _P) for n in "galaxies time2 fibre_time n_prime class_mean class_coef scalars g_loss g_time workspace".split()] + \
-        [("workspace_bytes", ct.c_size_t), ("stream", _P)]
+        [("workspace_bytes", ct.c_size_t), ("stream", _P), ("sharpness_dev", _P)]
 
 
 class WideSegments(ct.Structure):

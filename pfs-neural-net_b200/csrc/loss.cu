@@ -42,7 +42,15 @@ struct LossConst {
     int S, T;
     float total_time, wutils, wvar, pclass, pfiber, noiselevel;
     float r, atan_r;      // r = exp(-1 / sharpness) (0 when sharpness == 0), atan(r / (1 - r))
+    const float* sharp_dev;   // optional device scalar overriding the sharpness (CUDA-graph replays with a schedule)
 };
+__device__ __forceinline__ void resolve_sharpness(LossConst& c) {
+    if (c.sharp_dev) {
+        const float sh = *c.sharp_dev;
+        c.r = sh == 0.f ? 0.f : expf(-1.f / sh);
+        c.atan_r = atanf(c.r / (1.f - c.r));
+    }
+}
 
 // softfloor (reference src/train.py:21-27) of the noisy visit count and its derivative
 __device__ __forceinline__ void softfloor_eval(float visited, float u, const LossConst& c, float& sf, float& dsf) {
@@ -55,9 +63,10 @@ __device__ __forceinline__ void softfloor_eval(float visited, float u, const Los
 }
 
 // per edge: galaxies = max(0, softfloor(time / T_i)), time2 = galaxies * T_i      (src/train.py:43-49)
-__global__ void __launch_bounds__(256) k_loss_edge_fwd(const LossConst c, const float* __restrict__ time,
+__global__ void __launch_bounds__(256) k_loss_edge_fwd(LossConst c, const float* __restrict__ time,
                                                        const float* __restrict__ noise, const float* __restrict__ hours,
                                                        float* __restrict__ galaxies, float* __restrict__ time2) {
+    resolve_sharpness(c);
     const long long E = (long long)c.S * c.T;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (long long)gridDim.x * blockDim.x) {
         const float h = hours[e % c.T];
@@ -198,11 +207,12 @@ __global__ void __launch_bounds__(1024) k_loss_scalars(const LossConst c, const 
 }
 
 // g_time[e] = gL * [softfloor > 0] * softfloor' / T_i * (dL/dn'_i + T_i * (dL/dfibre_time_k - 2 wvar (time2 - mean_i) / (S - 1)))
-__global__ void __launch_bounds__(256) k_loss_edge_bwd(const LossConst c, const float* __restrict__ time,
+__global__ void __launch_bounds__(256) k_loss_edge_bwd(LossConst c, const float* __restrict__ time,
                                                        const float* __restrict__ noise, const float* __restrict__ hours,
                                                        const float* __restrict__ time2, const float* __restrict__ fibre_time,
                                                        const float* __restrict__ class_mean, const float* __restrict__ class_coef,
                                                        const float* __restrict__ g_loss, float* __restrict__ g_time) {
+    resolve_sharpness(c);
     const long long E = (long long)c.S * c.T;
     const float gl = g_loss ? g_loss[0] : 1.f;
     const float vscale = 2.f * c.wvar / (float)(c.S - 1);
@@ -230,6 +240,7 @@ int make_const(const pfs_loss_args& a, LossConst& c) {
     c.noiselevel = a.noiselevel;
     c.r = a.sharpness == 0.f ? 0.f : expf(-1.f / a.sharpness);
     c.atan_r = atanf(c.r / (1.f - c.r));
+    c.sharp_dev = a.sharpness_dev;
     return PFS_OK;
 }
 int class_row_blocks(int S) {

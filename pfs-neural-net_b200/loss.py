@@ -43,8 +43,11 @@ class LossFunction(torch.autograd.Function):
         ws = torch.empty(lib.pfs_loss_workspace_bytes(S, T), dtype=torch.uint8, device=dev)
         for k, v in dict(time=time, noise=noise, hours=hours, counts=counts, **out).items():
             setattr(a, k, v.data_ptr())
+        sharp_dev = consts.get("sharpness_dev")
         for k, v in consts.items():
-            setattr(a, k, float(v))
+            if k != "sharpness_dev":
+                setattr(a, k, float(v))
+        a.sharpness_dev = _abi.ptr(sharp_dev)
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
         with torch.cuda.device(dev):
             a.stream = torch.cuda.current_stream(dev).cuda_stream
@@ -67,7 +70,9 @@ class LossFunction(torch.autograd.Function):
                          class_mean=class_mean, class_coef=class_coef, g_loss=gl, g_time=g_time).items():
             setattr(a, k, v.data_ptr())
         for k, v in ctx.consts.items():
-            setattr(a, k, float(v))
+            if k != "sharpness_dev":
+                setattr(a, k, float(v))
+        a.sharpness_dev = _abi.ptr(ctx.consts.get("sharpness_dev"))
         with torch.cuda.device(dev):
             a.stream = torch.cuda.current_stream(dev).cuda_stream
             _abi.check(_abi.load_library().pfs_loss_bwd(ct.byref(a)), "pfs_loss_bwd")
@@ -85,8 +90,11 @@ def loss_from_times(time, class_info, nfibers, nclasses, nfields=10, total_time=
         noise = torch.rand_like(time)             # the draw of softfloor, reference src/train.py:22
     hours = class_info[:, 0].to(torch.float32)
     counts = (class_info[:, 1] / nfields).to(torch.float32)
-    consts = dict(total_time=total_time, wutils=wutils, wvar=wvar, pclass=pclass, pfiber=pfiber, sharpness=sharpness,
-                  noiselevel=NOISELEVEL)
+    consts = dict(total_time=total_time, wutils=wutils, wvar=wvar, pclass=pclass, pfiber=pfiber, noiselevel=NOISELEVEL)
+    if torch.is_tensor(sharpness):                # device scalar: the value is read by the kernels (CUDA-graph replays)
+        consts.update(sharpness=0.0, sharpness_dev=sharpness.to(torch.float32).reshape(1))
+    else:
+        consts.update(sharpness=sharpness)
     return LossFunction.apply(time, noise.reshape(-1).to(torch.float32), hours, counts, int(nfibers), int(nclasses), consts)
 
 
