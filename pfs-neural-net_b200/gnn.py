@@ -72,6 +72,32 @@ class Loader(torch.utils.data.Dataset):
     def __getitem__(self, idx):
         return self.graphs_list[idx]
 
+    @staticmethod
+    def collate(graphs):
+        """Batch graphs that share one `edge_index` into leading-dimension tensors x_s [G,S,F], x_t [G,T,F],
+        x_e [G,E,F], x_u [G,1,F] -- the form every module of this file accepts.  Unlike
+        the reference's PyG collation (`__inc__`, src/gnn.py:32-47, which concatenates nodes and cannot carry one
+        global row per graph through `u.expand`, src/gnn.py:100), every graph keeps its own global features and its
+        own BatchNorm statistics, exactly as if the graphs were run one after the other."""
+        if not graphs:
+            raise ValueError("no graphs to collate")
+        ei = graphs[0].edge_index
+        for g in graphs[1:]:
+            if g.edge_index.shape != ei.shape or not torch.equal(g.edge_index, ei):
+                raise ValueError("collate() batches graphs with identical edge_index; shard different topologies "
+                                 "over separate calls")
+        out = BipartiteData.__new__(BipartiteData)
+        out.edge_index = ei
+        for k in ("x_s", "x_t", "x_e", "x_u"):
+            setattr(out, k, torch.stack([getattr(g, k) for g in graphs]))
+        out.num_nodes = graphs[0].x_t.shape[0]
+        return out
+
+    def batches(self, batch_size):
+        """Collated batches in list order (the last one may be smaller)."""
+        for i in range(0, len(self.graphs_list), batch_size):
+            yield Loader.collate(self.graphs_list[i:i + batch_size])
+
 
 class MLP(torch.nn.Sequential):
     """Linear -> LeakyReLU(0.1) -> Linear with children '0', '1', '2' (reference src/gnn.py:65-71)."""

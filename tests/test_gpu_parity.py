@@ -371,3 +371,45 @@ def test_unsupported_fdim_fails_loudly():
     with pytest.raises(RuntimeError, match="Fdim"):
         blk((ei, torch.randn(5, 6, device=dev), torch.randn(3, 6, device=dev), torch.randn(15, 6, device=dev),
              torch.randn(1, 6, device=dev)))
+
+
+@pytest.mark.gpu
+def test_loader_collate_batches_graphs_like_sequential_runs():
+    """N4: Loader.collate -> one batched GNN forward/backward == the graphs one after the other (own BatchNorm
+    statistics and global row per graph; parameter gradients summed)."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from pfs_neural_net_b200 import gnn
+    dev = torch.device("cuda:0")
+    S, T, F, G = 30, 6, 10, 3
+    torch.manual_seed(0)
+    model = gnn.GNN(B=2, Fdim=F, T=T, F_s=1, F_t=2).to(dev).train()
+    ei = bo.complete_bipartite(S, T)
+    g = torch.Generator().manual_seed(1)
+    graphs = [gnn.BipartiteData(ei, torch.randn(S, 1, generator=g), torch.randn(T, 2, generator=g),
+                                torch.randn(S * T, F, generator=g), torch.randn(1, F, generator=g)) for _ in range(G)]
+    import copy
+    ref = copy.deepcopy(model)
+    outs = []
+    for gr in graphs:
+        o = ref(gr)
+        outs.append(o)
+        (o.x_e.sum() + ref.edge_prediction(o.x_e).square().sum()).backward()
+    loader = gnn.Loader(graphs)
+    batch = next(loader.batches(G))
+    ob = model(batch)
+    assert ob.x_e.shape == (G, S * T, F) and ob.x_u.shape == (G, 1, F)
+    (ob.x_e.sum() + model.edge_prediction(ob.x_e).square().sum()).backward()
+    for i in range(G):
+        for a, b in ((ob.x_e[i], outs[i].x_e), (ob.x_s[i], outs[i].x_s), (ob.x_t[i], outs[i].x_t), (ob.x_u[i], outs[i].x_u)):
+            assert (a - b).abs().max().item() < 1e-4 * b.abs().max().item()       # norm-wise, like the other parity tests
+    for (n, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
+        if q.grad is None:
+            assert p.grad is None, n
+            continue
+        scale = max(q.grad.abs().max().item(), 1e-6)
+        if n.endswith("bias"):      # a bias in front of a train-mode BatchNorm: analytically zero, judge on the weight's scale
+            scale = max(scale, dict(ref.named_parameters())[n[:-4] + "weight"].grad.abs().max().item())
+        assert (p.grad - q.grad).abs().max().item() < 2e-3 * scale + 1e-5, n
+    with pytest.raises(ValueError):
+        gnn.Loader.collate([graphs[0], gnn.BipartiteData(ei[:, :-1], graphs[0].x_s, graphs[0].x_t, graphs[0].x_e[:-1], graphs[0].x_u)])
