@@ -254,7 +254,7 @@ int pfs_time_head_bwd(const pfs_head_args* a);
  * (row0 = idx0 ? idx0[m] : m / div0, row1 = idx1 ? idx1[m] : m % mod1 -- the gathered first-layer
  * node tables replacing the concatenations of src/gnn.py:100,136,188); LeakyReLU(0.1) if act;
  * * (mask[m][n] > 0 ? 1 : 0.1) if mask (LeakyReLU derivative from the saved activation).
- * Outputs: bf16 [M,ldc] and/or fp32 [M,ldf]. */
+ * Outputs: bf16 [M,ldc] and/or fp32 [M,ldf].  Optional dense-layout operands: see the last fields. */
 typedef struct pfs_wide_gemm_args {
     const void* A; int64_t lda;                  /* bf16 [M,K] */
     const void* B; int64_t ldb;                  /* bf16 [N,K] */
@@ -268,6 +268,11 @@ typedef struct pfs_wide_gemm_args {
     void* out_bf16; int64_t ldc;                 /* or NULL */
     float* out_f32; int64_t ldf;                 /* or NULL */
     void* stream;
+    /* dense-layout fast path (canonical order, T % 128 == 0), replacing the gathered tables:
+     * K-concatenation C = [A2[m % a2_mod] | A[m]] . B^T with B [N, K2 + K] (x_t[tgt] as a second operand), and
+     * per-tile bias rows + bias_rows[m / bias_rows_div][n] (P_s[src] is constant over a 128-row tile) */
+    const void* A2; int64_t lda2; int32_t K2; int32_t a2_mod;     /* bf16 [a2_mod, K2] or NULL */
+    const float* bias_rows; int32_t bias_rows_div;                /* fp32 [*, N] or NULL */
 } pfs_wide_gemm_args;
 size_t pfs_sizeof_wide_gemm_args(void);
 int pfs_wide_gemm_nt(const pfs_wide_gemm_args* a);

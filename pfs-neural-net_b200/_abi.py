@@ -113,6 +113,8 @@ class WideGemmArgs(ct.Structure):
         ("out_bf16", _P), ("ldc", ct.c_int64),
         ("out_f32", _P), ("ldf", ct.c_int64),
         ("stream", _P),
+        ("A2", _P), ("lda2", ct.c_int64), ("K2", ct.c_int32), ("a2_mod", ct.c_int32),
+        ("bias_rows", _P), ("bias_rows_div", ct.c_int32),
     ]
 
 

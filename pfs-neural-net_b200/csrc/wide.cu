@@ -93,19 +93,40 @@ int allow_smem(Kern kern, size_t smem) {
     return PFS_OK;
 }
 
-template <int BN, int STAGES, bool TABLES, bool MASK>
+template <int BN, int STAGES, bool TABLES, bool MASK, bool BSTAT = false>
 int launch_nt_impl(const pfs_wide_gemm_args& a, const GemmEpilogue& ep, cudaStream_t st) {
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmA2;
     W_TRY(make_map(&tmA, a.A, a.M, a.K, a.lda, kGemmBM));
-    W_TRY(make_map(&tmB, a.B, a.N, a.K, a.ldb, BN));
-    auto kern = k_wide_gemm_nt<BN, STAGES, TABLES, MASK>;
-    constexpr size_t smem = GemmNtSmem<BN, STAGES>::bytes;
+    W_TRY(make_map(&tmB, a.B, a.N, (long long)a.K + a.K2, a.ldb, BN));
+    if (a.A2) W_TRY(make_map(&tmA2, a.A2, a.a2_mod, a.K2, a.lda2, kGemmBM));
+    else tmA2 = tmA;
+    auto kern = k_wide_gemm_nt<BN, STAGES, TABLES, MASK, BSTAT>;
+    constexpr size_t smem = GemmNtSmem<BN, STAGES, BSTAT>::bytes;
     W_TRY(allow_smem(kern, smem));
-    const long long tiles = (long long)((a.M + kGemmBM - 1) / kGemmBM) * ((a.N + BN - 1) / BN);
-    const int grid = (int)(tiles < pfs_host::sm_count() ? tiles : pfs_host::sm_count());
-    kern<<<grid, kGemmNtThreads, smem, st>>>(tmA, tmB, ep, (__nv_bfloat16*)a.out_bf16, (int)a.ldc, a.M, a.N, a.K);
+    const int nt = (a.N + BN - 1) / BN;
+    const long long tiles = (long long)((a.M + kGemmBM - 1) / kGemmBM) * nt;
+    int grid = (int)(tiles < pfs_host::sm_count() ? tiles : pfs_host::sm_count());
+    if (BSTAT) grid -= grid % nt;            // every tile of a CTA must share its n block
+    kern<<<grid, kGemmNtThreads, smem, st>>>(tmA, tmB, tmA2, ep, (__nv_bfloat16*)a.out_bf16, (int)a.ldc, a.M, a.N, a.K);
     W_LAUNCH_CHECK("k_wide_gemm_nt");
     return PFS_OK;
+}
+
+// B-stationary variant (128-column tiles, weight tile resident): large-M layers with K_total <= 256
+int launch_nt_bstat(const pfs_wide_gemm_args& a, const GemmEpilogue& ep, cudaStream_t st) {
+    const bool tables = ep.tab0 != nullptr, mask = ep.mask != nullptr;
+    if (tables && mask) return launch_nt_impl<128, 4, true, true, true>(a, ep, st);
+    if (tables) return launch_nt_impl<128, 4, true, false, true>(a, ep, st);
+    if (mask) return launch_nt_impl<128, 4, false, true, true>(a, ep, st);
+    return launch_nt_impl<128, 4, false, false, true>(a, ep, st);
+}
+bool bstat_applies(const pfs_wide_gemm_args& a) {
+    const long long ktot = (long long)a.K + a.K2;
+    const int kb = (a.K + kGemmBK - 1) / kGemmBK + (a.K2 + kGemmBK - 1) / kGemmBK;
+    const int nt = (a.N + 127) / 128;
+    const long long mt = (a.M + kGemmBM - 1) / kGemmBM;
+    return ktot <= 256 && kb <= kGemmBsTiles && a.N >= 128 && mt * nt >= 4LL * pfs_host::sm_count() &&
+           pfs_host::sm_count() % nt == 0;
 }
 
 // FULL = gathered tables / derivative mask in the epilogue; the plain variant carries no code for them
@@ -215,9 +236,19 @@ int pfs_wide_gemm_nt(const pfs_wide_gemm_args* a) {
     }
     ep.mask = (const __nv_bfloat16*)a->mask; ep.ldmask = (int)a->ldmask;
     ep.act = a->act;
+    ep.brow = a->bias_rows; ep.brow_div = a->bias_rows_div > 0 ? a->bias_rows_div : 1;
+    ep.k1 = 0; ep.a2_mod = 1;
+    if (a->bias_rows) W_REQUIRE(a->bias_rows_div % kGemmBM == 0 && ((uintptr_t)a->bias_rows & 15) == 0,
+                                "bias_rows: tiles of 128 rows must not straddle a row block (div % 128 == 0)");
+    if (a->A2) {
+        W_REQUIRE(a->K2 >= 8 && a->K2 % 8 == 0 && a->a2_mod >= kGemmBM && a->a2_mod % kGemmBM == 0,
+                  "A2: K2 multiple of 8, a2_mod a multiple of 128 (dense layout with T % 128 == 0)");
+        ep.k1 = a->K2; ep.a2_mod = a->a2_mod;
+    }
     ep.out_f32 = a->out_f32; ep.ldf = (int)a->ldf;
     ep.out_bf16 = a->out_bf16 ? 1 : 0;
     if (a->out_bf16) W_REQUIRE(a->ldc % 4 == 0 && ((uintptr_t)a->out_bf16 & 7) == 0, "bf16 output alignment");
+    if (bstat_applies(*a)) return launch_nt_bstat(*a, ep, st);
     if (a->N > 128) return launch_nt<256, 3>(*a, ep, st);
     if (a->N > 64) return launch_nt<128, 5>(*a, ep, st);
     return launch_nt<64, 6>(*a, ep, st);

@@ -41,6 +41,10 @@ struct GemmEpilogue {
     int mod1;
     const __nv_bfloat16* mask;     // [M, ldmask] saved activation: multiply by (mask > 0 ? 1 : slope)
     int ldmask;
+    const float* brow;             // [R, N] fp32 rows added per TILE: row = m0 / brow_div (tiles never straddle a row), or null
+    int brow_div;
+    int k1;                        // columns of the second A operand (tmA2), contracted FIRST against B[:, 0:k1); 0 = none
+    int a2_mod;                    // its row for tile m0 is m0 % a2_mod (dense layout: x_t[tgt], tgt = e % T)
     int act;                       // 1: LeakyReLU(0.1)
     float* out_f32;                // optional fp32 output [M, ldf]
     int ldf;
@@ -51,13 +55,16 @@ constexpr int kGemmEpiWarps = 16;
 constexpr int kGemmNtThreads = 64 + 32 * kGemmEpiWarps;      // warp 0 = TMA, warp 1 = MMA, warps 2..17 = epilogue
 constexpr int kGemmEpiChunk = 128;       // accumulator columns staged per epilogue round
 
-template <int BN, int STAGES>
+constexpr int kGemmBsTiles = 4;          // B-stationary variant: the whole [BN, K <= 256] weight tile stays in shared memory
+
+template <int BN, int STAGES, bool BSTAT = false>
 struct GemmNtSmem {
     static constexpr int kA = kGemmBM * kGemmBK * 2;     // 16 KB
     static constexpr int kB = BN * kGemmBK * 2;
+    static constexpr int kBT = BSTAT ? kGemmBsTiles : STAGES;   // B tiles held in shared memory
     static constexpr int kC = kGemmBM * kGemmEpiChunk * 4;   // fp32 staging of a 128 x 128 accumulator block
     static constexpr int kBars = 256;
-    static constexpr size_t bytes = (size_t)STAGES * (kA + kB) + kC + kBars;
+    static constexpr size_t bytes = (size_t)STAGES * kA + (size_t)kBT * kB + kC + kBars;
 };
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -70,25 +77,31 @@ __device__ __forceinline__ bool bf16_bits_positive(uint32_t h) { return (h & 0x8
 // (thread = accumulator row) while every global access is coalesced (warp = one row, lane = 4 columns):
 //   phase 1: tcgen05.ld -> fp32 staging tile in shared memory (16-byte chunks XOR-swizzled by row)
 //   phase 2: staging -> registers, + bias / gathered table rows, LeakyReLU, derivative mask, bf16 / fp32 stores
-template <int BN, int STAGES, bool TABLES, bool MASK>
+// BSTAT: every tile of a CTA has the same n block (gridDim.x % nt == 0) and K_total <= 256, so the weight tile is loaded
+// once per CTA and only A streams through the ring -- the L2 -> SM traffic per output tile halves for the K <= 256 layers.
+template <int BN, int STAGES, bool TABLES, bool MASK, bool BSTAT = false>
 __global__ void __launch_bounds__(kGemmNtThreads, 1)
-k_wide_gemm_nt(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmEpilogue ep,
+k_wide_gemm_nt(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmA2, const GemmEpilogue ep,
                __nv_bfloat16* __restrict__ out_bf16, int ldc, int M, int N, int K) {
-    using SM = GemmNtSmem<BN, STAGES>;
+    using SM = GemmNtSmem<BN, STAGES, BSTAT>;
     extern __shared__ __align__(1024) uint8_t gemm_smem[];   // no static shared memory: the window starts 1024-aligned
     uint8_t* sA = gemm_smem;
     uint8_t* sB = sA + STAGES * SM::kA;
-    float* stg = reinterpret_cast<float*>(sB + STAGES * SM::kB);
+    float* stg = reinterpret_cast<float*>(sB + SM::kBT * SM::kB);
     uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stg) + SM::kC);
     uint64_t* empty = full + STAGES;
     uint64_t* tfull = empty + STAGES;
     uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* bfull = tempty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mt = (M + kGemmBM - 1) / kGemmBM, nt = (N + BN - 1) / BN;
     const int tiles = mt * nt;
-    const int KB = (K + kGemmBK - 1) / kGemmBK;
+    // K-concatenation: [A2 | A] . B^T with A2 [*, k1] (rows m0 % a2_mod) and A [M, K]; B is [N, k1 + K]
+    const int KB1 = (ep.k1 + kGemmBK - 1) / kGemmBK;
+    const int KB = KB1 + (K + kGemmBK - 1) / kGemmBK;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -99,6 +112,7 @@ k_wide_gemm_nt(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(tfull + s, 1);
             mbar_init(tempty + s, kGemmEpiWarps);
         }
+        mbar_init(bfull, 1);
         fence_barrier_init();
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
@@ -114,13 +128,25 @@ k_wide_gemm_nt(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             int stage = 0;
             uint32_t ph = 0;
+            if constexpr (BSTAT) {      // the CTA's weight tile, once
+                const int n0 = (blockIdx.x % nt) * BN;
+                mbar_expect_tx(bfull, KB * SM::kB);
+                for (int kb = 0; kb < KB; ++kb)
+                    tma_load_2d(sB + kb * SM::kB, &tmB, bfull, kb < KB1 ? kb * kGemmBK : ep.k1 + (kb - KB1) * kGemmBK, n0);
+            }
             for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
                 const int m0 = (t / nt) * kGemmBM, n0 = (t % nt) * BN;
                 for (int kb = 0; kb < KB; ++kb) {
                     mbar_wait(empty + stage, ph ^ 1);
-                    mbar_expect_tx(full + stage, SM::kA + SM::kB);
-                    tma_load_2d(sA + stage * SM::kA, &tmA, full + stage, kb * kGemmBK, m0);
-                    tma_load_2d(sB + stage * SM::kB, &tmB, full + stage, kb * kGemmBK, n0);
+                    mbar_expect_tx(full + stage, BSTAT ? SM::kA : SM::kA + SM::kB);
+                    if (kb < KB1) {     // columns beyond k1 are zero-filled in A2, so the extra B columns contribute nothing
+                        tma_load_2d(sA + stage * SM::kA, &tmA2, full + stage, kb * kGemmBK, m0 % ep.a2_mod);
+                        if constexpr (!BSTAT) tma_load_2d(sB + stage * SM::kB, &tmB, full + stage, kb * kGemmBK, n0);
+                    } else {
+                        tma_load_2d(sA + stage * SM::kA, &tmA, full + stage, (kb - KB1) * kGemmBK, m0);
+                        if constexpr (!BSTAT)
+                            tma_load_2d(sB + stage * SM::kB, &tmB, full + stage, ep.k1 + (kb - KB1) * kGemmBK, n0);
+                    }
                     if (++stage == STAGES) {
                         stage = 0;
                         ph ^= 1;
@@ -135,6 +161,7 @@ k_wide_gemm_nt(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int stage = 0;
             uint32_t ph = 0;
             int it = 0;
+            if constexpr (BSTAT) mbar_wait(bfull, 0);
             for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
                 const int as = it & 1;
                 const uint32_t aph = (it >> 1) & 1;
@@ -144,7 +171,7 @@ k_wide_gemm_nt(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int kb = 0; kb < KB; ++kb) {
                     mbar_wait(full + stage, ph);
                     tc_fence_after();
-                    const uint32_t a0 = smem_u32(sA + stage * SM::kA), b0 = smem_u32(sB + stage * SM::kB);
+                    const uint32_t a0 = smem_u32(sA + stage * SM::kA), b0 = smem_u32(sB + (BSTAT ? kb : stage) * SM::kB);
 #pragma unroll
                     for (int k = 0; k < kGemmBK / 16; ++k) {
                         const uint64_t da = umma_desc_sw128(a0 + k * 32, 16, 1024);
@@ -267,6 +294,13 @@ k_wide_gemm_nt(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             for (int rr = 0; rr < kRows; ++rr) {
                                 acc[rr].x += b.x; acc[rr].y += b.y; acc[rr].z += b.z; acc[rr].w += b.w;
                             }
+                        }
+                    }
+                    if (ep.brow) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(ep.brow + (size_t)(m0 / ep.brow_div) * N + n));
+#pragma unroll
+                        for (int rr = 0; rr < kRows; ++rr) {
+                            acc[rr].x += b.x; acc[rr].y += b.y; acc[rr].z += b.z; acc[rr].w += b.w;
                         }
                     }
                     if constexpr (TABLES) {

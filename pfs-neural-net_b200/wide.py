@@ -54,6 +54,9 @@ class WideTopology:
             cp = a["csc_colptr"]
             self.class_count = (cp[1:] - cp[:-1]).to(F32)
         self.div = self.T      # dense: src = e // T, tgt = e % T
+        # canonical order with whole 128-edge tiles inside one fibre: the class rows of a tile are contiguous, so
+        # x_t[tgt] is a second GEMM operand and P_s[src] a per-tile bias row -- no gathered tables at all
+        self.tiled_dense = bool(topo.canonical and self.T % 128 == 0)
 
 
 # ------------------------------------------------------------------------------------------------ helpers
@@ -132,10 +135,15 @@ class WideEdgeFunction(torch.autograd.Function):
         F = x_e.shape[1]
         E = x_e.shape[0]
         uvec = wo.gemm_nt(u, w1[:, 3 * F:], bias=_f32(b1), want="f32")                          # W1_u.u + b1
-        Pt = wo.gemm_nt(x_t, w1[:, F:2 * F], bias=uvec[0].contiguous(), want="f32")             # [T,4F] fp32
         Ps = wo.gemm_nt(x_s, w1[:, :F], want="f32")                                             # [S,4F] fp32
-        a1 = wo.gemm_nt(x_e, w1[:, 2 * F:3 * F], tab0=Ps, idx0=wt.src, div0=wt.div, tab1=Pt, idx1=wt.tgt, mod1=wt.div,
-                        act=True)                                                               # [E,4F] bf16
+        if wt.tiled_dense:
+            # [x_t[tgt] | x_e] . [W1_t | W1_e]^T + P_s[src] (tile-constant) + (W1_u.u + b1)
+            a1 = wo.gemm_nt(x_e, w1[:, F:3 * F], A2=x_t, a2_mod=wt.T, bias=uvec[0].contiguous(), bias_rows=Ps,
+                            bias_rows_div=wt.T, act=True)
+        else:
+            Pt = wo.gemm_nt(x_t, w1[:, F:2 * F], bias=uvec[0].contiguous(), want="f32")         # [T,4F] fp32
+            a1 = wo.gemm_nt(x_e, w1[:, 2 * F:3 * F], tab0=Ps, idx0=wt.src, div0=wt.div, tab1=Pt, idx1=wt.tgt,
+                            mod1=wt.div, act=True)                                              # [E,4F] bf16
         z = wo.gemm_nt(a1, w2, bias=_f32(b2))                                                   # [E,F] bf16
         saved_small = {}
         if normed:
@@ -243,8 +251,11 @@ class WideSourceFunction(torch.autograd.Function):
         wt = topo.wide()
         x_s, x_t, x_e, u, w1, w2, w3, w4 = (t.contiguous() for t in (x_s, x_t, x_e, u, w1, w2, w3, w4))
         S, F = x_s.shape
-        Qt = wo.gemm_nt(x_t, w1[:, :F], bias=_f32(b1), want="f32")                              # [T,2F] fp32
-        a_s = wo.gemm_nt(x_e, w1[:, F:], tab1=Qt, idx1=wt.tgt, mod1=wt.div, act=True)           # [E,2F]
+        if wt.tiled_dense:
+            a_s = wo.gemm_nt(x_e, w1, A2=x_t, a2_mod=wt.T, bias=_f32(b1), act=True)             # [x_t[tgt] | x_e] . W1^T + b1
+        else:
+            Qt = wo.gemm_nt(x_t, w1[:, :F], bias=_f32(b1), want="f32")                          # [T,2F] fp32
+            a_s = wo.gemm_nt(x_e, w1[:, F:], tab1=Qt, idx1=wt.tgt, mod1=wt.div, act=True)       # [E,2F]
         m = wo.gemm_nt(a_s, w2, bias=_f32(b2))                                                  # messages [E,2F]
         moments = wo.moments_fwd(wt.fibres, m)                                                  # [S,5,2F] fp32
         hcat = wo.source_hcat(x_s, moments)                                                     # [S,9F] bf16
@@ -320,7 +331,10 @@ class WideTargetFunction(torch.autograd.Function):
         x_s, x_t, x_e, u, w1, w2, w3, w4 = (t.contiguous() for t in (x_s, x_t, x_e, u, w1, w2, w3, w4))
         T, F = x_t.shape
         Rs = wo.gemm_nt(x_s, w1[:, :F], bias=_f32(b1), want="f32")                              # [S,2F] fp32
-        a_t = wo.gemm_nt(x_e, w1[:, F:], tab0=Rs, idx0=wt.src, div0=wt.div, act=True)           # [E,2F] bf16
+        if wt.tiled_dense:
+            a_t = wo.gemm_nt(x_e, w1[:, F:], bias_rows=Rs, bias_rows_div=wt.T, act=True)        # R_s[src] is tile-constant
+        else:
+            a_t = wo.gemm_nt(x_e, w1[:, F:], tab0=Rs, idx0=wt.src, div0=wt.div, act=True)       # [E,2F] bf16
         asum32 = _shard.allreduce_sum(wo.segsum(wt.classes, a_t, want="f32"))                   # [T,2F]
         asum = _bf(asum32)
         cnt = _shard.allreduce_sum(wt.class_count)

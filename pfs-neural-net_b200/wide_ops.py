@@ -56,14 +56,25 @@ class Segments:
 
 
 def gemm_nt(A, B, bias=None, bias_rowscale=None, tab0=None, idx0=None, div0=0, tab1=None, idx1=None, mod1=0,
-            mask=None, act=False, out_bf16=None, out_f32=None, want="bf16"):
-    """epilogue(A[M,K] @ B[N,K]^T) on tcgen05; returns the bf16 and/or fp32 result (want in {'bf16','f32','both'})."""
+            mask=None, act=False, out_bf16=None, out_f32=None, want="bf16", A2=None, a2_mod=0, bias_rows=None,
+            bias_rows_div=0):
+    """epilogue(A[M,K] @ B[N,K]^T) on tcgen05; returns the bf16 and/or fp32 result (want in {'bf16','f32','both'}).
+    Dense-layout operands: A2 [a2_mod, K2] contracted first ([A2[m % a2_mod] | A[m]] @ B^T with B [N, K2 + K]) and
+    bias_rows [*, N] added per 128-row tile (row m // bias_rows_div)."""
     A, B = _rows2d(A, "A"), _rows2d(B, "B")
     _chk(A, BF16, "A"), _chk(B, BF16, "B")
     M, K = A.shape
     N = B.shape[0]
-    if B.shape[1] != K:
-        raise _abi.PfsError("gemm_nt: A %s vs B %s" % (tuple(A.shape), tuple(B.shape)))
+    K2 = 0
+    if A2 is not None:
+        A2 = _rows2d(A2, "A2")
+        _chk(A2, BF16, "A2")
+        K2 = A2.shape[1]
+        if A2.shape[0] != a2_mod:
+            raise _abi.PfsError("gemm_nt: A2 has %d rows, a2_mod is %d" % (A2.shape[0], a2_mod))
+    _chk(bias_rows, F32, "bias_rows")
+    if B.shape[1] != K + K2:
+        raise _abi.PfsError("gemm_nt: A %s (+ A2 %d columns) vs B %s" % (tuple(A.shape), K2, tuple(B.shape)))
     dev = A.device
     for t, n in ((bias, "bias"), (bias_rowscale, "bias_rowscale"), (tab0, "tab0"), (tab1, "tab1")):
         _chk(t, F32, n)
@@ -83,6 +94,10 @@ def gemm_nt(A, B, bias=None, bias_rowscale=None, tab0=None, idx0=None, div0=0, t
         mask = _rows2d(mask, "mask")
         a.mask, a.ldmask = mask.data_ptr(), mask.stride(0)
     a.act = int(bool(act))
+    if A2 is not None:
+        a.A2, a.lda2, a.K2, a.a2_mod = A2.data_ptr(), A2.stride(0), K2, int(a2_mod)
+    if bias_rows is not None:
+        a.bias_rows, a.bias_rows_div = bias_rows.contiguous().data_ptr(), int(bias_rows_div)
     if out_bf16 is not None:
         out_bf16 = _rows2d(out_bf16, "out_bf16")
         a.out_bf16, a.ldc = out_bf16.data_ptr(), out_bf16.stride(0)

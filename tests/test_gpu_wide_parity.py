@@ -56,6 +56,8 @@ CASES = [
     ("dense", 16, 64, 300, True, True),      # T > 256: canonical order beyond the fp32 kernels' tile
     ("csr", 32, 150, 64, True, True),        # shuffled edge list, an empty fibre and an empty class
     ("dense", 128, 96, 64, True, True),
+    ("dense", 32, 40, 128, True, True),      # T % 128 == 0: K-concatenated x_t[tgt] operand + per-tile bias rows
+    ("dense", 128, 12, 256, True, True),
     ("csr", 64, 100, 64, False, True),       # eval mode
     ("dense", 32, 200, 64, True, False),     # un-normed
 ]
