@@ -321,6 +321,9 @@ int pfs_wide_source_coef(const pfs_wide_segments* sd, const float* dh, const flo
                          void* dx_s_bf16, float* coef, void* stream);
 int pfs_wide_source_dm(const void* m_bf16, const float* moments, const float* coef, const int32_t* src, int32_t T,
                        int64_t E, int32_t C, void* dm_bf16, void* stream);
+/* the same, one CTA per fibre segment (coefficients stay in registers over the fibre's edges) */
+int pfs_wide_source_dm_seg(const pfs_wide_segments* fibres, const void* m_bf16, const float* moments, const float* coef,
+                           int32_t C, void* dm_bf16, void* stream);
 /* out[e] = tab[idx ? idx[e] : e % mod] * (act[e] > 0 ? 1 : 0.1)   (TModel backward, src/gnn.py:188-190) */
 int pfs_wide_gather_mask(const float* tab, const int32_t* idx, int32_t mod, const void* act_bf16, int64_t E, int32_t C,
                          void* out_bf16, void* stream);

@@ -174,6 +174,7 @@ SYMBOLS = {
     "pfs_wide_source_hcat": (ct.c_int, [_P, _P, _I32, _I32, _P, _P]),
     "pfs_wide_source_coef": (ct.c_int, [ct.POINTER(WideSegments), _P, _P, _I32, _I32, _P, _P, _P]),
     "pfs_wide_source_dm": (ct.c_int, [_P, _P, _P, _P, _I32, _I64, _I32, _P, _P]),
+    "pfs_wide_source_dm_seg": (ct.c_int, [ct.POINTER(WideSegments), _P, _P, _P, _I32, _P, _P]),
     "pfs_wide_gather_mask": (ct.c_int, [_P, _P, _I32, _P, _I64, _I32, _P, _P]),
     "pfs_wide_head_fwd": (ct.c_int, [_P, _P, _P, ct.c_float, _I64, _I32, _P, _P, _I32, _P, _P, _P, _P, _P]),
     "pfs_wide_head_bwd": (ct.c_int, [_P, _P, _P, _P, ct.c_float, _I64, _I32, _P, _P, _P]),

@@ -184,7 +184,6 @@ int check_seg(const pfs_wide_segments* s) {
     else W_REQUIRE(s->S >= 1 && s->T >= 1, "dense segments need S and T");
     return PFS_OK;
 }
-long long seg_rows(const pfs_wide_segments& s) { return s.mode == 2 ? -1 : (long long)s.S * s.T; }
 int segsum_chunks(const pfs_wide_segments& s, int C) {
     // few long segments (classes): split them so that the grid fills the device
     const long long blocks = s.nseg;
@@ -319,10 +318,18 @@ int pfs_wide_rowmap(int32_t kind, const void* x, int32_t x_dtype, int64_t ldx, c
     if (kind == 1) W_REQUIRE(v && p0 && p1 && c2, "kind 1 needs v, p0, p1, c2");
     cudaStream_t st = (cudaStream_t)stream;
     pfs_host::mark_launch(nullptr, st);
-    const int grid = grid_for(R * (C / 2));
+    // 8 columns per thread (16-byte accesses, coefficients in registers) when the rows allow it
+    const bool vec = C % 8 == 0 && C <= 2048 && ldx % 8 == 0 && ldo % 8 == 0 && (!v || ldv % 8 == 0) &&
+                     ((uintptr_t)x & 15) == 0 && ((uintptr_t)out_bf16 & 15) == 0 && (!v || ((uintptr_t)v & 15) == 0) &&
+                     ((uintptr_t)a & 15) == 0 && ((uintptr_t)b & 15) == 0;
+    const int grid = vec ? grid_for(R, 256 / (C / 8 > 256 ? 256 : C / 8)) : grid_for(R * (C / 2));
 #define PFS_ROWMAP(TX, TV)                                                                                            \
-    k_wide_rowmap<TX, TV><<<grid, 256, 0, st>>>(kind, (const TX*)x, (int)ldx, (const TV*)v, (int)ldv, a, b, p0, p1, c2, R, C, \
-                                                (bf16*)out_bf16, (int)ldo)
+    if (vec)                                                                                                          \
+        k_wide_rowmap8<TX, TV><<<grid, 256, 0, st>>>(kind, (const TX*)x, (int)ldx, (const TV*)v, (int)ldv, a, b, p0, p1, c2, R, \
+                                                     C, (bf16*)out_bf16, (int)ldo);                                   \
+    else                                                                                                              \
+        k_wide_rowmap<TX, TV><<<grid, 256, 0, st>>>(kind, (const TX*)x, (int)ldx, (const TV*)v, (int)ldv, a, b, p0, p1, c2, R, \
+                                                    C, (bf16*)out_bf16, (int)ldo)
     if (x_dtype == 0 && (v_dtype == 0 || !v)) PFS_ROWMAP(bf16, bf16);
     else if (x_dtype == 0 && v_dtype == 1) PFS_ROWMAP(bf16, float);
     else if (x_dtype == 1 && (v_dtype == 1 || !v)) PFS_ROWMAP(float, float);
@@ -399,6 +406,17 @@ int pfs_wide_source_dm(const void* m_bf16, const float* moments, const float* co
     cudaStream_t st = (cudaStream_t)stream;
     pfs_host::mark_launch(nullptr, st);
     k_wide_source_dm<<<grid_for(E * (C / 8)), 256, 0, st>>>((const bf16*)m_bf16, moments, coef, src, T, E, C, (bf16*)dm_bf16);
+    W_LAUNCH_CHECK("k_wide_source_dm");
+    return PFS_OK;
+}
+
+int pfs_wide_source_dm_seg(const pfs_wide_segments* sd, const void* m_bf16, const float* moments, const float* coef, int32_t C,
+                           void* dm_bf16, void* stream) {
+    W_TRY(check_seg(sd));
+    W_REQUIRE(m_bf16 && moments && coef && dm_bf16 && C >= 8 && C % 8 == 0 && C <= 2048, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    pfs_host::mark_launch(nullptr, st);
+    k_wide_source_dm_seg<<<sd->nseg, 256, 0, st>>>(make_seg(*sd), (const bf16*)m_bf16, moments, coef, C, (bf16*)dm_bf16);
     W_LAUNCH_CHECK("k_wide_source_dm");
     return PFS_OK;
 }

@@ -171,6 +171,47 @@ __global__ void __launch_bounds__(256) k_wide_rowmap(int kind, const TX* __restr
     }
 }
 
+__device__ __forceinline__ void ld8_any(const bf16* p, float (&v)[8]) { ld8(p, v); }
+__device__ __forceinline__ void ld8_any(const float* p, float (&v)[8]) { ld8f(p, v); }
+// the same maps with 8 columns per thread (16-byte accesses) and the per-column coefficients held in registers:
+// a thread keeps its column group and strides over the rows
+template <class TX, class TV>
+__global__ void __launch_bounds__(256) k_wide_rowmap8(int kind, const TX* __restrict__ x, int ldx, const TV* __restrict__ v, int ldv,
+                                                      const float* __restrict__ a, const float* __restrict__ b,
+                                                      const float* __restrict__ p0, const float* __restrict__ p1,
+                                                      const float* __restrict__ c2, long long R, int C,
+                                                      bf16* __restrict__ out, int ldo) {
+    const int groups = C >> 3;
+    const int lanes = blockDim.x / groups;
+    const int lr = threadIdx.x / groups, c = 8 * (threadIdx.x - lr * groups);
+    if (lr >= lanes) return;
+    float ca[8], cb[8], cs[8], cq[8];       // kind 1: out = ca (x - cb - (v - cq) cs), cs = p1 c2
+    ld8f(a + c, ca);
+    ld8f(b + c, cb);
+    if (kind == 1) {
+        float t1[8], t2[8];
+        ld8f(p0 + c, cq);
+        ld8f(p1 + c, t1);
+        ld8f(c2 + c, t2);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) cs[q] = t1[q] * t2[q];
+    }
+    for (long long r = (long long)blockIdx.x * lanes + lr; r < R; r += (long long)gridDim.x * lanes) {
+        float xv[8], o[8];
+        ld8_any(x + r * ldx + c, xv);
+        if (kind == 0) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) o[q] = fmaf(ca[q], xv[q], cb[q]);
+        } else {
+            float vv[8];
+            ld8_any(v + r * ldv + c, vv);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) o[q] = ca[q] * (xv[q] - cb[q] - (vv[q] - cq[q]) * cs[q]);
+        }
+        st8(out + r * ldo + c, o);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // segmented sums: out[seg][c] = sum over the segment's rows of x[row][c]
 // grid (nseg, nchunk), 256 threads, thread = column pair (loops when C > 512);
@@ -464,6 +505,33 @@ __global__ void __launch_bounds__(256) k_wide_source_dm(const bf16* __restrict__
         ld8f(moments + s * 5 * C + c, mean);
         const float* cf = coef + s * 4 * C + c;
         ld8f(cf, a0); ld8f(cf + C, a1); ld8f(cf + 2 * C, a2); ld8f(cf + 3 * C, a3);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float d = mm[q] - mean[q];
+            o[q] = a0[q] + a1[q] * mm[q] + (a2[q] + a3[q] * d) * d * d;
+        }
+        st8(dm + e * C + c, o);
+    }
+}
+// the same per fibre: a block owns a fibre, a thread keeps the fibre's five coefficient rows of its 8 columns in
+// registers and strides over the fibre's edges (the gathers by src otherwise dominate the L1/L2 traffic)
+__global__ void __launch_bounds__(256) k_wide_source_dm_seg(const SegDesc sd, const bf16* __restrict__ m,
+                                                            const float* __restrict__ moments, const float* __restrict__ coef,
+                                                            int C, bf16* __restrict__ dm) {
+    const int seg = blockIdx.x;
+    const int len = seg_len(sd, seg);
+    const int groups = C >> 3;
+    const int lanes = blockDim.x / groups;
+    const int lr = threadIdx.x / groups, c = 8 * (threadIdx.x - lr * groups);
+    if (lr >= lanes || len == 0) return;
+    float mean[8], a0[8], a1[8], a2[8], a3[8];
+    ld8f(moments + (size_t)seg * 5 * C + c, mean);
+    const float* cf = coef + (size_t)seg * 4 * C + c;
+    ld8f(cf, a0); ld8f(cf + C, a1); ld8f(cf + 2 * C, a2); ld8f(cf + 3 * C, a3);
+    for (int i = lr; i < len; i += lanes) {
+        const long long e = seg_row(sd, seg, i);
+        float mm[8], o[8];
+        ld8(m + e * C + c, mm);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const float d = mm[q] - mean[q];

@@ -298,7 +298,7 @@ class WideSourceFunction(torch.autograd.Function):
         g_u = wo.gemm_nt(tot3_16, w3t[K9:], want="f32")
         dh = wo.gemm_nt(dh3, w3t[:K9], want="f32")               # gradient of hcat [S,9F] fp32
         g_x_s, coef = wo.source_coef(wt.fibres, dh, moments, F)  # dx_s bf16, cubic coefficients [S,4,2F]
-        dm = wo.source_dm(m, moments, coef, wt.src, wt.div)      # [E,2F] bf16
+        dm = wo.source_dm_seg(wt.fibres, m, moments, coef) if 2 * F <= 2048 else wo.source_dm(m, moments, coef, wt.src, wt.div)
         w2t, w1t = wo.transpose(w2), wo.transpose(w1)            # [2F,2F], [2F(in), 2F(out)]
         g_w2 = wo.gemm_tn(dm, a_s)
         g_b2 = _colsum(dm)

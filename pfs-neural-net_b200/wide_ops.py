@@ -237,6 +237,18 @@ def source_dm(m, moments, coef, src, T):
     return out
 
 
+def source_dm_seg(seg, m, moments, coef):
+    """source_dm with one CTA per fibre segment."""
+    _chk(m, BF16, "m")
+    E, C = m.shape
+    out = torch.empty(E, C, dtype=BF16, device=m.device)
+    with torch.cuda.device(m.device):
+        _abi.check(_abi.load_library().pfs_wide_source_dm_seg(ct.byref(seg.struct), m.data_ptr(), moments.data_ptr(),
+                                                              coef.data_ptr(), C, out.data_ptr(), _stream(m.device)),
+                   "pfs_wide_source_dm_seg")
+    return out
+
+
 def gather_mask(tab, idx, mod, act):
     _chk(tab, F32, "tab"), _chk(act, BF16, "act")
     E, C = act.shape
