@@ -2,6 +2,9 @@
 // Host-side only: argument checks, TMA tensor maps, grid sizing, launches on the caller's stream.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <string>
 
 #include "../../include/pfs_b200.h"
 #include "wide_gemm.cuh"
@@ -93,40 +96,56 @@ int allow_smem(Kern kern, size_t smem) {
     return PFS_OK;
 }
 
-template <int BN, int STAGES, bool TABLES, bool MASK, bool BSTAT = false>
+// profile label: with PFS_PROFILE_SHAPES=1 the GEMM launches are reported per shape (bench.py kernel table)
+const char* nt_name(const pfs_wide_gemm_args& a, bool tables, bool mask, bool bstat, int bn) {
+    static const bool by_shape = getenv("PFS_PROFILE_SHAPES") && getenv("PFS_PROFILE_SHAPES")[0] == '1';
+    if (!by_shape) return "k_wide_gemm_nt";
+    static std::map<std::string, std::string> names;
+    char buf[96];
+    snprintf(buf, sizeof(buf), "k_wide_gemm_nt[M%s,N%d,K%d%s%s%s%s,bn%d]", a.M >= (1 << 20) ? "=E" : "<E", a.N, a.K + a.K2,
+             tables ? ",tab" : "", mask ? ",mask" : "", a.A2 ? ",a2" : "", bstat ? ",bstat" : "", bn);
+    return names.emplace(buf, buf).first->second.c_str();
+}
+
+template <int BN, int STAGES, bool TABLES, bool MASK, int BT = 0>
 int launch_nt_impl(const pfs_wide_gemm_args& a, const GemmEpilogue& ep, cudaStream_t st) {
     CUtensorMap tmA, tmB, tmA2;
     W_TRY(make_map(&tmA, a.A, a.M, a.K, a.lda, kGemmBM));
     W_TRY(make_map(&tmB, a.B, a.N, (long long)a.K + a.K2, a.ldb, BN));
     if (a.A2) W_TRY(make_map(&tmA2, a.A2, a.a2_mod, a.K2, a.lda2, kGemmBM));
     else tmA2 = tmA;
-    auto kern = k_wide_gemm_nt<BN, STAGES, TABLES, MASK, BSTAT>;
-    constexpr size_t smem = GemmNtSmem<BN, STAGES, BSTAT>::bytes;
+    constexpr bool BSTAT = BT > 0;
+    auto kern = k_wide_gemm_nt<BN, STAGES, TABLES, MASK, BT>;
+    constexpr size_t smem = GemmNtSmem<BN, STAGES, BT>::bytes;
     W_TRY(allow_smem(kern, smem));
     const int nt = (a.N + BN - 1) / BN;
     const long long tiles = (long long)((a.M + kGemmBM - 1) / kGemmBM) * nt;
     int grid = (int)(tiles < pfs_host::sm_count() ? tiles : pfs_host::sm_count());
     if (BSTAT) grid -= grid % nt;            // every tile of a CTA must share its n block
     kern<<<grid, kGemmNtThreads, smem, st>>>(tmA, tmB, tmA2, ep, (__nv_bfloat16*)a.out_bf16, (int)a.ldc, a.M, a.N, a.K);
-    W_LAUNCH_CHECK("k_wide_gemm_nt");
+    W_LAUNCH_CHECK(nt_name(a, TABLES, MASK, BSTAT, BN));
     return PFS_OK;
 }
 
-// B-stationary variant (128-column tiles, weight tile resident): large-M layers with K_total <= 256
+// B-stationary variants (weight tile resident in shared memory) for large-M layers:
+//   K_total <= 128: 256-column tiles (two k-blocks of B = 64 KB), full-rate MMAs
+//   K_total <= 256: 128-column tiles (four k-blocks = 64 KB)
+template <int BN, int BT>
 int launch_nt_bstat(const pfs_wide_gemm_args& a, const GemmEpilogue& ep, cudaStream_t st) {
     const bool tables = ep.tab0 != nullptr, mask = ep.mask != nullptr;
-    if (tables && mask) return launch_nt_impl<128, 4, true, true, true>(a, ep, st);
-    if (tables) return launch_nt_impl<128, 4, true, false, true>(a, ep, st);
-    if (mask) return launch_nt_impl<128, 4, false, true, true>(a, ep, st);
-    return launch_nt_impl<128, 4, false, false, true>(a, ep, st);
+    if (tables && mask) return launch_nt_impl<BN, 4, true, true, BT>(a, ep, st);
+    if (tables) return launch_nt_impl<BN, 4, true, false, BT>(a, ep, st);
+    if (mask) return launch_nt_impl<BN, 4, false, true, BT>(a, ep, st);
+    return launch_nt_impl<BN, 4, false, false, BT>(a, ep, st);
 }
-bool bstat_applies(const pfs_wide_gemm_args& a) {
-    const long long ktot = (long long)a.K + a.K2;
+// 0: not applicable; else the tile width to use
+int bstat_tile(const pfs_wide_gemm_args& a) {
     const int kb = (a.K + kGemmBK - 1) / kGemmBK + (a.K2 + kGemmBK - 1) / kGemmBK;
-    const int nt = (a.N + 127) / 128;
     const long long mt = (a.M + kGemmBM - 1) / kGemmBM;
-    return ktot <= 256 && kb <= kGemmBsTiles && a.N >= 128 && mt * nt >= 4LL * pfs_host::sm_count() &&
-           pfs_host::sm_count() % nt == 0;
+    if (a.N < 128 || mt < 8LL * pfs_host::sm_count()) return 0;
+    if (kb <= 2 && a.N > 128 && pfs_host::sm_count() % ((a.N + 255) / 256) == 0) return 256;
+    if (kb <= 4 && pfs_host::sm_count() % ((a.N + 127) / 128) == 0) return 128;
+    return 0;
 }
 
 // FULL = gathered tables / derivative mask in the epilogue; the plain variant carries no code for them
@@ -247,7 +266,9 @@ int pfs_wide_gemm_nt(const pfs_wide_gemm_args* a) {
     ep.out_f32 = a->out_f32; ep.ldf = (int)a->ldf;
     ep.out_bf16 = a->out_bf16 ? 1 : 0;
     if (a->out_bf16) W_REQUIRE(a->ldc % 4 == 0 && ((uintptr_t)a->out_bf16 & 7) == 0, "bf16 output alignment");
-    if (bstat_applies(*a)) return launch_nt_bstat(*a, ep, st);
+    const int bs = bstat_tile(*a);
+    if (bs == 256) return launch_nt_bstat<256, 2>(*a, ep, st);
+    if (bs == 128) return launch_nt_bstat<128, 4>(*a, ep, st);
     if (a->N > 128) return launch_nt<256, 3>(*a, ep, st);
     if (a->N > 64) return launch_nt<128, 5>(*a, ep, st);
     return launch_nt<64, 6>(*a, ep, st);

@@ -55,13 +55,13 @@ constexpr int kGemmEpiWarps = 16;
 constexpr int kGemmNtThreads = 64 + 32 * kGemmEpiWarps;      // warp 0 = TMA, warp 1 = MMA, warps 2..17 = epilogue
 constexpr int kGemmEpiChunk = 128;       // accumulator columns staged per epilogue round
 
-constexpr int kGemmBsTiles = 4;          // B-stationary variant: the whole [BN, K <= 256] weight tile stays in shared memory
-
-template <int BN, int STAGES, bool BSTAT = false>
+// B-stationary variants keep the CTA's whole weight tile [BN, K] in shared memory as BT k-blocks (BT = 0: B streams
+// through the ring with A)
+template <int BN, int STAGES, int BT = 0>
 struct GemmNtSmem {
     static constexpr int kA = kGemmBM * kGemmBK * 2;     // 16 KB
     static constexpr int kB = BN * kGemmBK * 2;
-    static constexpr int kBT = BSTAT ? kGemmBsTiles : STAGES;   // B tiles held in shared memory
+    static constexpr int kBT = BT ? BT : STAGES;              // B tiles held in shared memory
     static constexpr int kC = kGemmBM * kGemmEpiChunk * 4;   // fp32 staging of a 128 x 128 accumulator block
     static constexpr int kBars = 256;
     static constexpr size_t bytes = (size_t)STAGES * kA + (size_t)kBT * kB + kC + kBars;
@@ -77,14 +77,15 @@ __device__ __forceinline__ bool bf16_bits_positive(uint32_t h) { return (h & 0x8
 // (thread = accumulator row) while every global access is coalesced (warp = one row, lane = 4 columns):
 //   phase 1: tcgen05.ld -> fp32 staging tile in shared memory (16-byte chunks XOR-swizzled by row)
 //   phase 2: staging -> registers, + bias / gathered table rows, LeakyReLU, derivative mask, bf16 / fp32 stores
-// BSTAT: every tile of a CTA has the same n block (gridDim.x % nt == 0) and K_total <= 256, so the weight tile is loaded
+// BT > 0: every tile of a CTA has the same n block (gridDim.x % nt == 0) and K_total <= 64 BT, so the weight tile is loaded
 // once per CTA and only A streams through the ring -- the L2 -> SM traffic per output tile halves for the K <= 256 layers.
-template <int BN, int STAGES, bool TABLES, bool MASK, bool BSTAT = false>
+template <int BN, int STAGES, bool TABLES, bool MASK, int BT = 0>
 __global__ void __launch_bounds__(kGemmNtThreads, 1)
 k_wide_gemm_nt(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA2, const GemmEpilogue ep,
                __nv_bfloat16* __restrict__ out_bf16, int ldc, int M, int N, int K) {
-    using SM = GemmNtSmem<BN, STAGES, BSTAT>;
+    constexpr bool BSTAT = BT > 0;
+    using SM = GemmNtSmem<BN, STAGES, BT>;
     extern __shared__ __align__(1024) uint8_t gemm_smem[];   // no static shared memory: the window starts 1024-aligned
     uint8_t* sA = gemm_smem;
     uint8_t* sB = sA + STAGES * SM::kA;
@@ -239,6 +240,21 @@ k_wide_gemm_nt(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
             }
+            // the derivative mask does not depend on the accumulator: its loads for a block of columns are issued one
+            // block ahead (for the first block: before waiting for the MMAs), so their latency hides behind the tile
+            uint2 mkv[kRows];
+            auto load_mask = [&](int c0m) {
+                const int colm = c0m + 4 * lane;
+                if (colm < ncols && n0 + colm + 4 <= N) {
+                    const __nv_bfloat16* mp = ep.mask + (size_t)mbase * ep.ldmask + n0 + colm;
+#pragma unroll
+                    for (int rr = 0; rr < kRows; ++rr) {
+                        mkv[rr] = make_uint2(0u, 0u);
+                        if (full || mbase + kGemmEpiWarps * rr < M) mkv[rr] = __ldg(reinterpret_cast<const uint2*>(mp + rr * mstride));
+                    }
+                }
+            };
+            if constexpr (MASK) load_mask(0);
             mbar_wait(tfull + as, aph);
             tc_fence_after();
 #pragma unroll
@@ -266,20 +282,6 @@ k_wide_gemm_nt(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     float4 acc[kRows];
 #pragma unroll
                     for (int rr = 0; rr < kRows; ++rr) acc[rr] = p2row[rr * (kGemmEpiWarps * kGemmEpiChunk / 4)];
-                    uint2 mkv[kRows];
-                    if constexpr (MASK) {
-                        const __nv_bfloat16* mp = ep.mask + (size_t)mbase * ep.ldmask + n;
-                        if (full) {
-#pragma unroll
-                            for (int rr = 0; rr < kRows; ++rr) mkv[rr] = __ldg(reinterpret_cast<const uint2*>(mp + rr * mstride));
-                        } else {
-#pragma unroll
-                            for (int rr = 0; rr < kRows; ++rr) {
-                                mkv[rr] = make_uint2(0u, 0u);
-                                if (mbase + kGemmEpiWarps * rr < M) mkv[rr] = __ldg(reinterpret_cast<const uint2*>(mp + rr * mstride));
-                            }
-                        }
-                    }
                     if (ep.bias) {
                         const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
                         if (ep.bias_rowscale) {
@@ -338,6 +340,7 @@ k_wide_gemm_nt(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             acc[rr].z *= bf16_bits_positive(mkv[rr].y & 0xFFFFu) ? 1.f : kWideSlope;
                             acc[rr].w *= bf16_bits_positive(mkv[rr].y >> 16) ? 1.f : kWideSlope;
                         }
+                        if (ch + 1 < kChunks && c0 + kGemmEpiChunk < ncols) load_mask(c0 + kGemmEpiChunk);   // next block's mask
                     }
                     if (out_bf16) {
                         __nv_bfloat16* op = out_bf16 + (size_t)mbase * ldc + n;
