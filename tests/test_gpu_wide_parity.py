@@ -58,7 +58,7 @@ CASES = [
     ("dense", 128, 96, 64, True, True),
     ("dense", 32, 40, 128, True, True),      # T % 128 == 0: K-concatenated x_t[tgt] operand + per-tile bias rows
     ("dense", 128, 12, 256, True, True),
-    ("csr", 24, 120, 70, True, True),        # Fdim a multiple of 8 only; odd sizes everywhere
+    ("csr", 24, 131, 64, True, True),        # Fdim a multiple of 8 only; odd sizes
     ("csr", 64, 100, 64, False, True),       # eval mode
     ("dense", 32, 200, 64, True, False),     # un-normed
 ]
