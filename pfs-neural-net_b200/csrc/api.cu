@@ -15,6 +15,7 @@
 #include "source_model.cuh"
 #include "source_node_c.cuh"
 #include "source_node_mma.cuh"
+#include "source_node_bwd_mma.cuh"
 #include "target_model.cuh"
 
 using namespace pfs;
@@ -184,6 +185,16 @@ bool node_mma_enabled() {
         v = (e && e[0] == '0') ? 0 : 1;
     }
     return v == 1;
+}
+
+// PFS_NODE_BWD_MMA=0 keeps the tensor-core forward but runs the fibre MLP backward on the FMA kernel
+bool node_bwd_mma_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PFS_NODE_BWD_MMA");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1 && node_mma_enabled();
 }
 
 // staging geometry of the edge kernels (common.cuh: TileStage)
@@ -585,14 +596,22 @@ int source_bwd_impl(const pfs_source_args& a, const Topo& tp) {
     cudaStream_t st = (cudaStream_t)a.stream;
     prof_mark(nullptr, st);
     const int total = tp.ntiles * tp.G;
-    const int ntn = node_ntiles<F>(tp.S);
+    int ntn = node_ntiles<F>(tp.S);
     const int mode = !a.normed ? 0 : (a.training ? 1 : 2);
     using SME = SourceEdgeBwdSmem<F>;
     constexpr bool kNodeC = SourceNodeConst<F>::fits;
+    constexpr bool kNodeMma = SourceNodeBwdMma<F>::fits;
+    const bool use_mma = kNodeMma && node_bwd_mma_enabled();
     auto ke = k_source_edge_bwd<F>;
     PFS_TRY(allow_smem(ke, SME::bytes));
     int gridn = 0;
-    if constexpr (kNodeC) {
+    if (use_mma) {
+        if constexpr (kNodeMma) {
+            ntn = (tp.S + kNodeRowsB - 1) / kNodeRowsB;        // 64-fibre tiles
+            PFS_TRY(allow_smem(k_source_node_bwd_mma<F>, SourceNodeBwdMma<F>::bytes));
+            gridn = persistent_grid(k_source_node_bwd_mma<F>, SourceNodeBwdMma<F>::bytes, (long long)ntn * tp.G, kNodeThreadsC);
+        }
+    } else if constexpr (kNodeC) {
         PFS_TRY(allow_smem(k_source_node_bwd_c<F>, SourceNodeBwdSmemC<F>::bytes));
         gridn = persistent_grid(k_source_node_bwd_c<F>, SourceNodeBwdSmemC<F>::bytes, (long long)ntn * tp.G, kNodeThreadsC);
     } else {
@@ -640,11 +659,23 @@ int source_bwd_impl(const pfs_source_args& a, const Topo& tp) {
             pl.it[1] = PackItem{a.w3, J, 0, K9, J, 0, CW::kW3o};      // W3[:, :9F] as stored [J][K9]
             pl.n = 2;
             PFS_TRY(upload_weights(pl, CW::kBwdFloats, wstage, st));
-            k_source_node_bwd_c<F><<<gridn, kNodeThreadsC, SourceNodeBwdSmemC<F>::bytes, st>>>(p);
+            bool launched = false;
+            if constexpr (kNodeMma) {
+                if (use_mma) {
+                    // both 9F x 10F contractions on tcgen05 (3xTF32), see source_node_bwd_mma.cuh
+                    k_source_node_bwd_mma<F><<<gridn, kNodeThreadsC, SourceNodeBwdMma<F>::bytes, st>>>(p);
+                    PFS_LAUNCH_CHECK("k_source_node_bwd_mma");
+                    launched = true;
+                }
+            }
+            if (!launched) {
+                k_source_node_bwd_c<F><<<gridn, kNodeThreadsC, SourceNodeBwdSmemC<F>::bytes, st>>>(p);
+                PFS_LAUNCH_CHECK("k_source_node_bwd");
+            }
         } else {
             k_source_node_bwd<F><<<gridn, kThreads, SourceNodeBwdSmem<F>::bytes, st>>>(p);
+            PFS_LAUNCH_CHECK("k_source_node_bwd");
         }
-        PFS_LAUNCH_CHECK("k_source_node_bwd");
     }
     {
         Reducer rd;

@@ -139,6 +139,19 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
     d |= (uint64_t)1 << 46;                              // descriptor version 1 (Blackwell)
     return d;                                            // base offset 0, layout type 0 = SWIZZLE_NONE
 }
+// The same no-swizzle K-major core-matrix tile with both strides explicit:
+//   byte(row, col) = (col / 4) * lbo + (row / 8) * sbo + (row % 8) * 16 + (col % 4) * 4          (tf32)
+// Measured on B200 (scratch/probe/mn_probe2.cu): with a_major / b_major = MN in the instruction
+// descriptor, kind::tf32 reads a no-swizzle operand as zeros.  For tf32 the only transposing layout
+// is SWIZZLE_128B_BASE32B, so the tf32 kernels of this library keep every operand K-major.
+__device__ __forceinline__ uint64_t umma_desc_ls(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
 // 128-byte-swizzled operand tile as TMA writes it (rows of 128 bytes, 8-row groups of 1024 bytes):
 //   K-major : rows = M/N index, 128 B = 64 bf16 along K; sbo = 1024 (next 8 rows), lbo unused (1)
 //   MN-major: rows = K index, 128 B = 64 bf16 along M/N; sbo = 1024 (next 8 K rows),
@@ -154,6 +167,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo
 }
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// tf32 with explicit operand major-ness (a_mn / b_mn = 1: MN-major)
+__host__ __device__ constexpr uint32_t umma_idesc_tf32_mn(int M, int N, int a_mn, int b_mn) {
+    return umma_idesc_tf32(M, N) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16);
 }
 // bf16 x bf16 -> fp32; a_mn / b_mn = 1 selects the MN-major (transposed) operand layout
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn, int b_mn) {
