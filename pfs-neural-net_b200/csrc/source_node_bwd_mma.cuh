@@ -58,6 +58,24 @@ struct SourceNodeBwdMma {
                                  AccW4::kScratchFloats <= 2 * D1_FLOATS + 2 * D2_FLOATS && SourceNodeConst<F>::fits;
 };
 
+// dh3 accumulation of one warp-uniform chunk: d[c] += dy[f] * W4[f][CH * 2F + c], weights read as
+// constant-bank operands of the FFMA2s (the offset is a compile-time constant per chunk)
+template <int F, int CH>
+__device__ __forceinline__ void dh3_chunk(const float* y, float (&d)[2 * F]) {
+    using CW = SourceNodeConst<F>;
+    constexpr int C = 2 * F, J = 10 * F, OFF = CW::kW4o + CH * C;
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+        const float2 v = make_float2(y[f], y[f]);
+#pragma unroll
+        for (int c = 0; c < C; c += 2) {
+            const float2 w = make_float2(c_w[OFF + f * J + c], c_w[OFF + f * J + c + 1]);
+            const float2 e = __ffma2_rn(w, v, make_float2(d[c], d[c + 1]));
+            d[c] = e.x; d[c + 1] = e.y;
+        }
+    }
+}
+
 template <int F>
 __global__ void __launch_bounds__(kNodeThreadsC) k_source_node_bwd_mma(const SourceNodeBwdParams p) {
     using MM = SourceNodeBwdMma<F>;
@@ -119,6 +137,37 @@ __global__ void __launch_bounds__(kNodeThreadsC) k_source_node_bwd_mma(const Sou
     // dh3 mapping: warp = (row set, chunk of 2F hidden units), lane = fibre; rows >= R of the second row set idle
     const int chunk = warp % 5, r = (warp / 5) * 32 + lane;
     const int off = chunk * C;
+    // Tile-invariant work items of the scalar phases.  Moment items (fibre rr, message feature j) and x_s items
+    // (rr, c) are numbered so that consecutive lanes take rr % 4 fastest, then the feature: the 4-byte operand
+    // stores of a warp then fill whole 16-byte core-matrix rows (no bank conflicts) and the global reads touch
+    // 4 rows x 32 contiguous bytes.  What the forward pass of an item computes (1 / std, the nan_to_num masks)
+    // stays in registers for its backward half after the MMAs.
+    constexpr int NI = (R * M + kNodeThreadsC - 1) / kNodeThreadsC;      // moment items per thread
+    constexpr int NX = (R * F + kNodeThreadsC - 1) / kNodeThreadsC;      // x_s / dy items per thread
+    int it_rr[NI], it_j[NI];
+#pragma unroll
+    for (int n = 0; n < NI; ++n) {
+        const int i = threadIdx.x + n * kNodeThreadsC;
+        const int q = i / (4 * M), rem = i - q * (4 * M);
+        it_rr[n] = i < R * M ? 4 * q + (rem & 3) : R;                    // R = no item
+        it_j[n] = rem >> 2;
+    }
+    int ix_rr[NX], ix_c[NX], iy_rr[NX], iy_f[NX];
+#pragma unroll
+    for (int n = 0; n < NX; ++n) {
+        const int i = threadIdx.x + n * kNodeThreadsC;
+        const int q = i / (4 * F), rem = i - q * (4 * F);
+        ix_rr[n] = i < R * F ? 4 * q + (rem & 3) : R;
+        ix_c[n] = rem >> 2;
+        iy_rr[n] = i < R * F ? i / F : R;
+        iy_f[n] = i % F;
+    }
+    auto put = [&](int rr, int k, float v) {
+        const float hi = to_tf32(v);
+        const int o = ((rr >> 2) * MM::CS_H + k * 16 + (rr & 3) * 4) >> 2;
+        Hhi[o] = hi;
+        Hlo[o] = to_tf32(v - hi);
+    };
     const int total = p.ntiles * p.G;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
         const int g = tile / p.ntiles, lt = tile - g * p.ntiles;
@@ -129,43 +178,53 @@ __global__ void __launch_bounds__(kNodeThreadsC) k_source_node_bwd_mma(const Sou
         float a[C];
         load_row<C>(p.hidden + (row0 + (r < rows ? r : 0)) * J + off, a);   // rows beyond the tile: any valid row
         // ---- hcat = [x_s | mean | std | skew | kurt], split hi/lo (rows beyond the tile are zero) ----
-        auto put = [&](int rr, int k, float v) {
-            const float hi = to_tf32(v);
-            const int o = ((rr >> 2) * MM::CS_H + k * 16 + (rr & 3) * 4) >> 2;
-            Hhi[o] = hi;
-            Hlo[o] = to_tf32(v - hi);
-        };
-        for (int i = threadIdx.x; i < R * F; i += blockDim.x) {
-            const int c = i / R, rr = i - c * R;
-            put(rr, c, rr < rows ? __ldg(p.x_s + (row0 + rr) * F + c) : 0.f);
-        }
-        for (int i = threadIdx.x; i < R * M; i += blockDim.x) {
-            const int j = i / R, rr = i - j * R;
+        float m_mean[NI], m_vr[NI], m_c2[NI], m_c3[NI], m_c4[NI], m_i1[NI], m_is1[NI];
+        unsigned m_fin[NI];      // bit 0..3: mean, var, skew, kurt were finite (nan_to_num passes their gradient)
+#pragma unroll
+        for (int n = 0; n < NI; ++n) {
+            const int rr = it_rr[n], j = it_j[n];
             float mean_o = 0.f, std_o = 0.f, skew_o = 0.f, kurt_o = 0.f;
+            m_fin[n] = 0u;
+            m_mean[n] = m_vr[n] = m_c2[n] = m_c3[n] = m_c4[n] = m_i1[n] = m_is1[n] = 0.f;
             if (rr < rows) {
                 const float* mo = p.moments + (row0 + rr) * 5 * M + j;
-                const float mean = __ldg(mo), ex2 = __ldg(mo + M), c3 = __ldg(mo + 3 * M), c4 = __ldg(mo + 4 * M);
+                const float mean = __ldg(mo), ex2 = __ldg(mo + M), c2 = __ldg(mo + 2 * M), c3 = __ldg(mo + 3 * M),
+                            c4 = __ldg(mo + 4 * M);
                 const float vr = ex2 - mean * mean;
                 const float var = vr > 0.f ? vr : kSlopeVar * vr;
-                const float std0 = sqrtf(var + kStdEps);
-                const float s3 = std0 * std0 * std0;
+                const float i1 = rsqrtf(var + kStdEps);          // 1 / std (NaN for var + eps < 0, like the sqrt)
+                const float i2 = i1 * i1;
+                const float skew = c3 * (i2 * i1), kurt = c4 * (i2 * i2);
+                const bool fv = finite_f(var);
+                std_o = fv ? (var + kStdEps) * i1 : sqrtf(nan_to_num(var) + kStdEps);
                 mean_o = nan_to_num(mean);
-                std_o = sqrtf(nan_to_num(var) + kStdEps);
-                skew_o = nan_to_num(c3 / s3);
-                kurt_o = nan_to_num(c4 / (s3 * std0));
+                skew_o = nan_to_num(skew);
+                kurt_o = nan_to_num(kurt);
+                m_fin[n] = (finite_f(mean) ? 1u : 0u) | (fv ? 2u : 0u) | (finite_f(skew) ? 4u : 0u) | (finite_f(kurt) ? 8u : 0u);
+                m_mean[n] = mean; m_vr[n] = vr; m_c2[n] = c2; m_c3[n] = c3; m_c4[n] = c4; m_i1[n] = i1;
+                m_is1[n] = fv ? i1 : 1.f / std_o;                // 1 / std as recomputed after nan_to_num
             }
-            put(rr, F + j, mean_o);
-            put(rr, F + M + j, std_o);
-            put(rr, F + 2 * M + j, skew_o);
-            put(rr, F + 3 * M + j, kurt_o);
+            if (rr < R) {
+                put(rr, F + j, mean_o);
+                put(rr, F + M + j, std_o);
+                put(rr, F + 2 * M + j, skew_o);
+                put(rr, F + 3 * M + j, kurt_o);
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < NX; ++n) {
+            const int rr = ix_rr[n];
+            if (rr < R) put(rr, ix_c[n], rr < rows ? __ldg(p.x_s + (row0 + rr) * F + ix_c[n]) : 0.f);
         }
         // ---- dy = BatchNorm backward of the upstream gradient ---------------------------------------
         {
             const float* sv = p.bn_save + (size_t)g * 4 * F;
             const float* st = p.bn_stat + (size_t)g * 2 * F;
             const float invS = 1.f / (float)p.S;
-            for (int i = threadIdx.x; i < R * F; i += blockDim.x) {
-                const int rr = i / F, f = i - rr * F;
+#pragma unroll
+            for (int n = 0; n < NX; ++n) {
+                const int rr = iy_rr[n], f = iy_f[n];
+                if (rr >= R) continue;
                 float dy = 0.f;
                 if (rr < rows) {
                     const float gv = __ldg(p.gout + (row0 + rr) * F + f);
@@ -189,15 +248,13 @@ __global__ void __launch_bounds__(kNodeThreadsC) k_source_node_bwd_mma(const Sou
 #pragma unroll
             for (int c = 0; c < C; ++c) d[c] = 0.f;
             const float* y = DY + (r < R ? r : 0) * LDY;
-#pragma unroll
-            for (int f = 0; f < F; ++f) {
-                const float2 v = make_float2(y[f], y[f]);
-#pragma unroll
-                for (int c = 0; c < C; c += 2) {
-                    const float2 w = make_float2(c_w[CW::kW4o + off + f * J + c], c_w[CW::kW4o + off + f * J + c + 1]);
-                    const float2 e = __ffma2_rn(w, v, make_float2(d[c], d[c + 1]));
-                    d[c] = e.x; d[c + 1] = e.y;
-                }
+            // the chunk is warp-uniform: one copy of the loop per chunk, weights as constant-bank immediates
+            switch (chunk) {
+                case 0: dh3_chunk<F, 0>(y, d); break;
+                case 1: dh3_chunk<F, 1>(y, d); break;
+                case 2: dh3_chunk<F, 2>(y, d); break;
+                case 3: dh3_chunk<F, 3>(y, d); break;
+                default: dh3_chunk<F, 4>(y, d); break;
             }
             const bool live = r < rows;
             if (r < R) {
@@ -294,27 +351,21 @@ __global__ void __launch_bounds__(kNodeThreadsC) k_source_node_bwd_mma(const Sou
             const int rr = i / F, k = i - rr * F;
             p.g_x_s[(row0 + rr) * F + k] = A3[rr * LDC + k];
         }
-        for (int i = threadIdx.x; i < rows * M; i += blockDim.x) {
-            const int rr = i / M, j = i - rr * M;
-            const float* mo = p.moments + (row0 + rr) * 5 * M + j;
-            const float mean = __ldg(mo), ex2 = __ldg(mo + M), c2 = __ldg(mo + 2 * M), c3 = __ldg(mo + 3 * M),
-                        c4 = __ldg(mo + 4 * M);
+#pragma unroll
+        for (int n = 0; n < NI; ++n) {
+            const int rr = it_rr[n], j = it_j[n];
+            if (rr >= rows) continue;
             const float* dh = A3 + rr * LDC + F + j;
-            float d_mean = dh[0], d_std = dh[M], d_skew = dh[2 * M], d_kurt = dh[3 * M];
-            const float vr = ex2 - mean * mean;
-            const float var = vr > 0.f ? vr : kSlopeVar * vr;
-            const float std0 = sqrtf(var + kStdEps);
-            const float s3 = std0 * std0 * std0, s4 = s3 * std0;
+            const unsigned fin = m_fin[n];
             // torch: nan_to_num backward passes the gradient only where the value was finite
-            if (!finite_f(mean)) d_mean = 0.f;
-            if (!finite_f(var)) d_std = 0.f;
-            if (!finite_f(c3 / s3)) d_skew = 0.f;
-            if (!finite_f(c4 / s4)) d_kurt = 0.f;
-            const float std1 = sqrtf(nan_to_num(var) + kStdEps);
-            const float d_c3 = d_skew / s3, d_c4 = d_kurt / s4;
-            const float d_var = d_std / (2.f * std1) + (-3.f * c3 / s4 * d_skew - 4.f * c4 / (s4 * std0) * d_kurt) / (2.f * std0);
-            const float d_vr = d_var * (vr > 0.f ? 1.f : kSlopeVar);
-            const float d_mu = d_mean - 2.f * mean * d_vr - 3.f * c2 * d_c3 - 4.f * c3 * d_c4;
+            const float d_mean = (fin & 1u) ? dh[0] : 0.f, d_std = (fin & 2u) ? dh[M] : 0.f;
+            const float d_skew = (fin & 4u) ? dh[2 * M] : 0.f, d_kurt = (fin & 8u) ? dh[3 * M] : 0.f;
+            const float i1 = m_i1[n], i2 = i1 * i1, i3 = i2 * i1, i4 = i2 * i2;
+            const float c3 = m_c3[n], c4 = m_c4[n];
+            const float d_c3 = d_skew * i3, d_c4 = d_kurt * i4;
+            const float d_var = 0.5f * (d_std * m_is1[n] - (3.f * c3 * i4 * d_skew + 4.f * c4 * i4 * i1 * d_kurt) * i1);
+            const float d_vr = d_var * (m_vr[n] > 0.f ? 1.f : kSlopeVar);
+            const float d_mu = d_mean - 2.f * m_mean[n] * d_vr - 3.f * m_c2[n] * d_c3 - 4.f * c3 * d_c4;
             float* o = p.coefA + (row0 + rr) * 4 * M + j;
             o[0] = d_mu;
             o[M] = 2.f * d_vr;
