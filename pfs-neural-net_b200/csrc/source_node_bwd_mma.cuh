@@ -169,6 +169,38 @@ __global__ void __launch_bounds__(kNodeThreadsC) k_source_node_bwd_mma(const Sou
         Hlo[o] = to_tf32(v - hi);
     };
     const int total = p.ntiles * p.G;
+    // Inputs of the scalar phase are fetched one tile ahead into registers: with one CTA of 10 warps per SM
+    // nothing else hides their DRAM latency.
+    float pf_mo[NI][5], pf_xs[NX], pf_g[NX], pf_y[NX];
+    auto prefetch = [&](int tile2) {
+        if (tile2 >= total) return;
+        const int g2 = tile2 / p.ntiles, f2 = (tile2 - g2 * p.ntiles) * R;
+        const int rows2 = min(R, p.S - f2);
+        const size_t row2 = (size_t)g2 * p.S + f2;
+#pragma unroll
+        for (int n = 0; n < NI; ++n) {
+            if (it_rr[n] < rows2) {
+                const float* mo = p.moments + (row2 + it_rr[n]) * 5 * M + it_j[n];
+#pragma unroll
+                for (int q = 0; q < 5; ++q) pf_mo[n][q] = __ldg(mo + q * M);
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < NX; ++n) {
+            if (ix_rr[n] < rows2) pf_xs[n] = __ldg(p.x_s + (row2 + ix_rr[n]) * F + ix_c[n]);
+            if (iy_rr[n] < rows2) {
+                pf_g[n] = __ldg(p.gout + (row2 + iy_rr[n]) * F + iy_f[n]);
+                pf_y[n] = p.mode == 1 ? __ldg(p.y_pre + (row2 + iy_rr[n]) * F + iy_f[n]) : 0.f;
+            }
+        }
+    };
+#pragma unroll
+    for (int n = 0; n < NI; ++n)
+#pragma unroll
+        for (int q = 0; q < 5; ++q) pf_mo[n][q] = 0.f;
+#pragma unroll
+    for (int n = 0; n < NX; ++n) pf_xs[n] = pf_g[n] = pf_y[n] = 0.f;
+    prefetch(blockIdx.x);
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
         const int g = tile / p.ntiles, lt = tile - g * p.ntiles;
         const int f0 = lt * R;
@@ -187,9 +219,7 @@ __global__ void __launch_bounds__(kNodeThreadsC) k_source_node_bwd_mma(const Sou
             m_fin[n] = 0u;
             m_mean[n] = m_vr[n] = m_c2[n] = m_c3[n] = m_c4[n] = m_i1[n] = m_is1[n] = 0.f;
             if (rr < rows) {
-                const float* mo = p.moments + (row0 + rr) * 5 * M + j;
-                const float mean = __ldg(mo), ex2 = __ldg(mo + M), c2 = __ldg(mo + 2 * M), c3 = __ldg(mo + 3 * M),
-                            c4 = __ldg(mo + 4 * M);
+                const float mean = pf_mo[n][0], ex2 = pf_mo[n][1], c2 = pf_mo[n][2], c3 = pf_mo[n][3], c4 = pf_mo[n][4];
                 const float vr = ex2 - mean * mean;
                 const float var = vr > 0.f ? vr : kSlopeVar * vr;
                 const float i1 = rsqrtf(var + kStdEps);          // 1 / std (NaN for var + eps < 0, like the sqrt)
@@ -214,7 +244,7 @@ __global__ void __launch_bounds__(kNodeThreadsC) k_source_node_bwd_mma(const Sou
 #pragma unroll
         for (int n = 0; n < NX; ++n) {
             const int rr = ix_rr[n];
-            if (rr < R) put(rr, ix_c[n], rr < rows ? __ldg(p.x_s + (row0 + rr) * F + ix_c[n]) : 0.f);
+            if (rr < R) put(rr, ix_c[n], rr < rows ? pf_xs[n] : 0.f);
         }
         // ---- dy = BatchNorm backward of the upstream gradient ---------------------------------------
         {
@@ -227,10 +257,10 @@ __global__ void __launch_bounds__(kNodeThreadsC) k_source_node_bwd_mma(const Sou
                 if (rr >= R) continue;
                 float dy = 0.f;
                 if (rr < rows) {
-                    const float gv = __ldg(p.gout + (row0 + rr) * F + f);
+                    const float gv = pf_g[n];
                     if (p.mode == 1) {
                         const float rstd = rsqrtf(sv[F + f] + p.eps);
-                        const float xh = (__ldg(p.y_pre + (row0 + rr) * F + f) - sv[f]) * rstd;
+                        const float xh = (pf_y[n] - sv[f]) * rstd;
                         dy = sv[2 * F + f] * (gv - st[f] * invS - xh * st[F + f] * invS);
                     } else if (p.mode == 2) {
                         dy = gv * sv[2 * F + f];
@@ -241,6 +271,7 @@ __global__ void __launch_bounds__(kNodeThreadsC) k_source_node_bwd_mma(const Sou
                 DY[rr * LDY + f] = dy;
             }
         }
+        prefetch(tile + gridDim.x);      // next tile's scalar inputs: in flight under the rest of this tile
         __syncthreads();
         // ---- dh3 = (dy . W4) * lrelu'(h3): thread = (fibre, chunk of 2F hidden units) ---------------
         {
