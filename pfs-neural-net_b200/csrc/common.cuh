@@ -548,6 +548,48 @@ struct RunningStats {
 };
 
 // ------------------------------------------------------------------------------------------
+// in-tile segment sums over a shared-memory tile X[edge][LD] (W features, 4 per thread, 16-byte loads;
+// the edges of a segment are added in their order, so the result does not depend on the mapping)
+// ------------------------------------------------------------------------------------------
+// out[lf * W + k] = sum over the edges of local fibre lf; `out` points at the row of the tile's first fibre
+template <int W, int LD>
+__device__ __forceinline__ void tile_fibre_sums(const Topo& tp, const Tile& t, const float* X, float* __restrict__ out) {
+    static_assert(W % 4 == 0 && LD % 4 == 0, "16-byte rows");
+    constexpr int W4 = W / 4;
+    for (int i = threadIdx.x; i < t.nfib * W4; i += kThreads) {
+        const int lf = i / W4, k = (i - lf * W4) * 4;
+        int e0, n;
+        fibre_range(tp, t, lf, e0, n);
+        const float4* x = reinterpret_cast<const float4*>(X + e0 * LD + k);
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (int e = 0; e < n; ++e) {
+            const float4 v = x[e * (LD / 4)];
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        *reinterpret_cast<float4*>(out + (size_t)lf * W + k) = s;
+    }
+}
+// dense layout (edge lf * T + c belongs to class c): cp[c * W + k] = sum over the tile's fibres
+template <int W, int LD>
+__device__ __forceinline__ void tile_class_sums(const Topo& tp, const Tile& t, const float* X, float* __restrict__ cp) {
+    static_assert(W % 4 == 0 && LD % 4 == 0, "16-byte rows");
+    constexpr int W4 = W / 4;
+    const int stride = tp.T * (LD / 4);
+    for (int i = threadIdx.x; i < tp.T * W4; i += kThreads) {
+        const int c = i / W4, k = (i - c * W4) * 4;
+        const float4* x = reinterpret_cast<const float4*>(X + c * LD + k);
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (int lf = 0; lf < t.nfib; ++lf) {
+            const float4 v = x[lf * stride];
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        *reinterpret_cast<float4*>(cp + c * W + k) = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // outer-product accumulation  dW[J][K] += sum_r D[r][0..J) (x) X[r][0..K)
 // D and X are shared-memory tiles with leading dimensions ldD / ldX.  The J x K result is
 // register-blocked TJ x TK per thread; rows are split over `groups` thread groups and the

@@ -303,25 +303,9 @@ __global__ void __launch_bounds__(kThreads) k_edge_bwd(const EdgeBwdParams p) {
         __syncthreads();
         accw1.accumulate(DH, LDH, XE, F, t.ne);
         accw2.accumulate(DZ, LDF, A1, LDH, t.ne);
-        // fibre sums of dh -> dPs
-        for (int i = threadIdx.x; i < t.nfib * H; i += kThreads) {
-            const int lf = i / H, k = i - lf * H;
-            int e0, n;
-            fibre_range(tp, t, lf, e0, n);
-            float s = 0.f;
-            for (int e = 0; e < n; ++e) s += DH[(e0 + e) * LDH + k];
-            p.dPs[((size_t)t.g * tp.S + t.fibre0 + lf) * H + k] = s;
-        }
-        // class sums of dh (dense layout: edge lf*T + c belongs to class c)
-        if (p.class_part) {
-            float* cp = p.class_part + (size_t)tile * tp.T * H;
-            for (int i = threadIdx.x; i < tp.T * H; i += kThreads) {
-                const int c = i / H, k = i - c * H;
-                float s = 0.f;
-                for (int lf = 0; lf < t.nfib; ++lf) s += DH[(lf * tp.T + c) * LDH + k];
-                cp[i] = s;
-            }
-        }
+        // fibre sums of dh -> dPs, class sums of dh (dense layout: edge lf*T + c belongs to class c)
+        tile_fibre_sums<H, LDH>(tp, t, DH, p.dPs + ((size_t)t.g * tp.S + t.fibre0) * H);
+        if (p.class_part) tile_class_sums<H, LDH>(tp, t, DH, p.class_part + (size_t)tile * tp.T * H);
         __syncthreads();
     }
     cp_async_wait<0>();

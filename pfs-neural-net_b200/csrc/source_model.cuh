@@ -580,15 +580,7 @@ __global__ void __launch_bounds__(kThreads) k_source_edge_bwd(const SourceEdgeBw
         __syncthreads();
         accw2.accumulate(DM, LDM, AS, LDM, t.ne);
         accw1.accumulate(DHS, LDM, XE, LDF, t.ne);
-        if (p.class_part) {
-            float* cp = p.class_part + (size_t)tile * tp.T * M;
-            for (int i = threadIdx.x; i < tp.T * M; i += kThreads) {
-                const int c = i / M, k = i - c * M;
-                float s = 0.f;
-                for (int lf = 0; lf < t.nfib; ++lf) s += DHS[(lf * tp.T + c) * LDM + k];
-                cp[i] = s;
-            }
-        }
+        if (p.class_part) tile_class_sums<M, LDM>(tp, t, DHS, p.class_part + (size_t)tile * tp.T * M);
         __syncthreads();
     }
     float* out = p.wpartial + (size_t)blockIdx.x * p.pstride;

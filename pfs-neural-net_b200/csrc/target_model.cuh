@@ -386,14 +386,7 @@ __global__ void __launch_bounds__(kThreads) k_target_edge_bwd(const TargetEdgeBw
         }
         __syncthreads();
         accw1.accumulate(DHT, LDM, XE, LDF, t.ne);
-        for (int i = threadIdx.x; i < t.nfib * M; i += kThreads) {
-            const int lf = i / M, k = i - lf * M;
-            int e0, n;
-            fibre_range(tp, t, lf, e0, n);
-            float s = 0.f;
-            for (int e = 0; e < n; ++e) s += DHT[(e0 + e) * LDM + k];
-            p.dRs[((size_t)t.g * tp.S + t.fibre0 + lf) * M + k] = s;
-        }
+        tile_fibre_sums<M, LDM>(tp, t, DHT, p.dRs + ((size_t)t.g * tp.S + t.fibre0) * M);
         __syncthreads();
     }
     accw1.flush(DHT, p.wpartial + (size_t)blockIdx.x * p.pstride, F, 0);
