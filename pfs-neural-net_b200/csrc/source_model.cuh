@@ -482,7 +482,7 @@ struct SourceEdgeBwdSmem {
 };
 
 template <int F>
-__global__ void __launch_bounds__(kThreads) k_source_edge_bwd(const SourceEdgeBwdParams p) {
+__global__ void __launch_bounds__(kThreads, (F <= 10 ? 2 : 1)) k_source_edge_bwd(const SourceEdgeBwdParams p) {
     using SM = SourceEdgeBwdSmem<F>;
     constexpr int M = 2 * F, LDM = SM::LDM, LDF = SM::LDF;
     extern __shared__ __align__(16) float sm[];
