@@ -91,31 +91,70 @@ __global__ void __launch_bounds__(kNodeThreadsC) k_source_node_fwd_mma(const Sou
     uint32_t parity = 0;
 
     const int total = p.ntiles * p.G;
+    // Tile-invariant work items of the operand build.  Moment items (fibre r, message feature j) and x_s items
+    // (r, c) are numbered with the feature's low two bits fastest, then the fibre: a warp's 4-byte operand stores
+    // fill whole 16-byte core-matrix rows (no bank conflicts) and its global reads are 16 contiguous bytes per
+    // fibre.  Their inputs are fetched ONE TILE AHEAD into registers: with one CTA of 10 warps per SM nothing
+    // else hides the DRAM latency in front of the MMAs.
+    constexpr int NI = (kNodeRowsC * M2 + kNodeThreadsC - 1) / kNodeThreadsC;
+    constexpr int XG = (F + 3) / 4;                                          // 4-column groups of x_s
+    constexpr int NX = (kNodeRowsC * 4 * XG + kNodeThreadsC - 1) / kNodeThreadsC;
+    auto item_r = [](int i) { return (i >> 2) & (kNodeRowsC - 1); };
+    auto item_c = [](int i) { return ((i >> 9) << 2) | (i & 3); };           // feature index (j or c)
+    float pf_mo[NI][4], pf_xs[NX];
+#pragma unroll
+    for (int n = 0; n < NI; ++n)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) pf_mo[n][q] = 0.f;
+#pragma unroll
+    for (int n = 0; n < NX; ++n) pf_xs[n] = 0.f;
+    auto prefetch = [&](int tile2) {
+        if (tile2 >= total) return;
+        const int g2 = tile2 / p.ntiles, f2 = (tile2 - g2 * p.ntiles) * kNodeRowsC;
+        const int rows2 = min(kNodeRowsC, p.S - f2);
+        const size_t row2 = (size_t)g2 * p.S + f2;
+#pragma unroll
+        for (int n = 0; n < NI; ++n) {
+            const int i = threadIdx.x + n * kNodeThreadsC, r = item_r(i), j = item_c(i);
+            if (i < kNodeRowsC * M2 && r < rows2) {
+                const float* mo = p.moments + (row2 + r) * 5 * M2 + j;
+                pf_mo[n][0] = __ldg(mo); pf_mo[n][1] = __ldg(mo + M2); pf_mo[n][2] = __ldg(mo + 3 * M2); pf_mo[n][3] = __ldg(mo + 4 * M2);
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < NX; ++n) {
+            const int i = threadIdx.x + n * kNodeThreadsC, r = item_r(i), c = item_c(i);
+            if (i < kNodeRowsC * 4 * XG && c < F && r < rows2) pf_xs[n] = __ldg(p.x_s + (row2 + r) * F + c);
+        }
+    };
+    prefetch(blockIdx.x);
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
         const int g = tile / p.ntiles, lt = tile - g * p.ntiles;
         const int f0 = lt * kNodeRowsC;
         const int rows = min(kNodeRowsC, p.S - f0);
         const size_t row0 = (size_t)g * p.S + f0;
         // ---- A operand: hcat = [x_s | mean | std | skew | kurt] per fibre, split hi/lo ----------------
-        // element (r, k) -> byte (k / 4) * LBO_A + r * 16 + (k % 4) * 4; consecutive threads take
-        // consecutive fibres r, so a warp writes one 512-byte run of a K chunk
+        // element (r, k) -> byte (k / 4) * LBO_A + r * 16 + (k % 4) * 4
         auto put = [&](int r, int k, float v) {
             const float hi = to_tf32(v);
             const int o = ((k >> 2) * MM::LBO_A + r * 16 + (k & 3) * 4) >> 2;
             Ahi[o] = hi;
             Alo[o] = to_tf32(v - hi);
         };
-        for (int i = threadIdx.x; i < 128 * (F + KP - K9); i += blockDim.x) {      // x_s columns and the zero padding
-            const int c = i >> 7, r = i & 127;
-            if (c < F) put(r, c, r < rows ? __ldg(p.x_s + (row0 + r) * F + c) : 0.f);
-            else put(r, K9 + (c - F), 0.f);
+        for (int i = threadIdx.x; i < 128 * (KP - K9); i += blockDim.x)            // zero padding of K (A3 overwrote it)
+            put(i & 127, K9 + (i >> 7), 0.f);
+#pragma unroll
+        for (int n = 0; n < NX; ++n) {
+            const int i = threadIdx.x + n * kNodeThreadsC, r = item_r(i), c = item_c(i);
+            if (i < kNodeRowsC * 4 * XG && c < F) put(r, c, r < rows ? pf_xs[n] : 0.f);
         }
-        for (int i = threadIdx.x; i < 128 * M2; i += blockDim.x) {                 // the four statistics of feature j
-            const int j = i >> 7, r = i & 127;
+#pragma unroll
+        for (int n = 0; n < NI; ++n) {
+            const int i = threadIdx.x + n * kNodeThreadsC, r = item_r(i), j = item_c(i);
+            if (i >= kNodeRowsC * M2) continue;
             float mean_o = 0.f, std_o = 0.f, skew_o = 0.f, kurt_o = 0.f;
             if (r < rows) {
-                const float* mo = p.moments + (row0 + r) * 5 * M2 + j;
-                const float mean = __ldg(mo), ex2 = __ldg(mo + M2), c3 = __ldg(mo + 3 * M2), c4 = __ldg(mo + 4 * M2);
+                const float mean = pf_mo[n][0], ex2 = pf_mo[n][1], c3 = pf_mo[n][2], c4 = pf_mo[n][3];
                 const float vr = ex2 - mean * mean;
                 const float var = vr > 0.f ? vr : kSlopeVar * vr;
                 const float std0 = sqrtf(var + kStdEps);
@@ -130,6 +169,7 @@ __global__ void __launch_bounds__(kNodeThreadsC) k_source_node_fwd_mma(const Sou
             put(r, F + 2 * M2 + j, skew_o);
             put(r, F + 3 * M2 + j, kurt_o);
         }
+        prefetch(tile + gridDim.x);       // next tile's inputs: in flight under the MMAs and the epilogue
         for (int j = threadIdx.x; j < J; j += blockDim.x) {
             float s = __ldg(p.b3 + j);
             for (int k = 0; k < F; ++k) s = fmaf(__ldg(p.w3 + (size_t)j * J + K9 + k), __ldg(p.u + (size_t)g * F + k), s);
