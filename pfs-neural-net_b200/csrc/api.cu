@@ -265,7 +265,7 @@ struct Reducer {
     }
     int run(const float* partial, int ncta, int pstride, cudaStream_t st) {
         if (rl.nseg == 0) return PFS_OK;
-        k_reduce_multi<<<(rl.total + 127) / 128, 128, 0, st>>>(partial, ncta, pstride, rl);
+        k_reduce_multi<<<(rl.total + 31) / 32, 32 * kReduceSlices, 0, st>>>(partial, ncta, pstride, rl);
         PFS_LAUNCH_CHECK("k_reduce_partials");
         return PFS_OK;
     }

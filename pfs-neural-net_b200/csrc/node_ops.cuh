@@ -131,26 +131,39 @@ struct ReduceList {
     ReduceSeg seg[kMaxReduceSegs];
     int nseg, total;
 };
-__global__ void k_reduce_multi(const float* __restrict__ partial, int ncta, int pstride, const ReduceList rl) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= rl.total) return;
+// block = kReduceSlices slices x 32 outputs: slice s adds the partials of CTAs s, s + slices, ... (one short
+// dependent chain each instead of one chain over all CTAs), the slices are then added in a fixed order
+constexpr int kReduceSlices = 8;
+__global__ void __launch_bounds__(32 * kReduceSlices) k_reduce_multi(const float* __restrict__ partial, int ncta, int pstride,
+                                                                     const ReduceList rl) {
+    __shared__ float red[kReduceSlices][33];
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    int i = blockIdx.x * 32 + lane;
+    const bool live = i < rl.total;
     int q = 0;
-    while (q < rl.nseg - 1 && i >= rl.seg[q].n) {
+    while (live && q < rl.nseg - 1 && i >= rl.seg[q].n) {
         i -= rl.seg[q].n;
         ++q;
     }
-    const ReduceSeg sg = rl.seg[q];
-    const float* p = partial + sg.poff + i;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // fixed association: four interleaved chains, then a fixed tree
-    int c = 0;
-    for (; c + 3 < ncta; c += 4) {
-        s0 += p[(size_t)c * pstride];
-        s1 += p[(size_t)(c + 1) * pstride];
-        s2 += p[(size_t)(c + 2) * pstride];
-        s3 += p[(size_t)(c + 3) * pstride];
+    float s0 = 0.f, s1 = 0.f;        // fixed association: two interleaved chains per slice
+    if (live) {
+        const float* p = partial + rl.seg[q].poff + i;
+        int c = slice;
+        for (; c + kReduceSlices < ncta; c += 2 * kReduceSlices) {
+            s0 += p[(size_t)c * pstride];
+            s1 += p[(size_t)(c + kReduceSlices) * pstride];
+        }
+        if (c < ncta) s0 += p[(size_t)c * pstride];
     }
-    for (; c < ncta; ++c) s0 += p[(size_t)c * pstride];
-    sg.out[(i / sg.cols) * sg.ldo + sg.coff + (i % sg.cols)] = (s0 + s1) + (s2 + s3);
+    red[slice][lane] = s0 + s1;
+    __syncthreads();
+    if (slice == 0 && live) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < kReduceSlices; ++k) s += red[k][lane];
+        const ReduceSeg& sg = rl.seg[q];
+        sg.out[(i / sg.cols) * sg.ldo + sg.coff + (i % sg.cols)] = s;
+    }
 }
 
 // colsum over rows and graphs: out[j] = sum_n x[n][j] (single CTA per 32 columns; fixed order)
