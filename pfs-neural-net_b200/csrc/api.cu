@@ -282,7 +282,7 @@ int colsum_graph(const float* x, int rows, int J, int G, float* out, cudaStream_
     return PFS_OK;
 }
 int outer_graphs(const float* a, const float* b, int G, int J, int K, float* out, int ldo, int koff, cudaStream_t st) {
-    k_outer_graphs<<<(J * K + 127) / 128, 128, 0, st>>>(a, b, G, J, K, out, ldo, koff);
+    k_outer_graphs<<<(J * K + 31) / 32, 256, 0, st>>>(a, b, G, J, K, out, ldo, koff);
     PFS_LAUNCH_CHECK("k_outer_graphs");
     return PFS_OK;
 }

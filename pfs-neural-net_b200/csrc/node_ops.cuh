@@ -202,14 +202,32 @@ __global__ void k_colsum_graph(const float* __restrict__ x, int rows, int J, flo
 }
 
 // out[j][koff + k] = sum_g a[g][j] * b[g][k]      (the `u` columns of a first-layer weight gradient)
-__global__ void k_outer_graphs(const float* __restrict__ a, const float* __restrict__ b, int G, int J, int K,
-                               float* __restrict__ out, int ldo, int koff) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= J * K) return;
-    const int j = i / K, k = i - j * K;
-    float s = 0.f;
-    for (int g = 0; g < G; ++g) s += a[(size_t)g * J + j] * b[(size_t)g * K + k];
-    out[j * ldo + koff + k] = s;
+// block = 8 slices x 32 outputs: slice s takes graphs s, s + 8, ... with four loads in flight, the slices are
+// added in a fixed order (one thread looping over all graphs was a 256-deep chain of dependent L2 round trips)
+__global__ void __launch_bounds__(256) k_outer_graphs(const float* __restrict__ a, const float* __restrict__ b, int G,
+                                                      int J, int K, float* __restrict__ out, int ldo, int koff) {
+    __shared__ float red[8][33];
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + lane;
+    const bool live = i < J * K;
+    const int j = live ? i / K : 0, k = live ? i - j * K : 0;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int g = slice;
+    for (; g + 24 < G; g += 32) {
+        s0 = fmaf(a[(size_t)g * J + j], b[(size_t)g * K + k], s0);
+        s1 = fmaf(a[(size_t)(g + 8) * J + j], b[(size_t)(g + 8) * K + k], s1);
+        s2 = fmaf(a[(size_t)(g + 16) * J + j], b[(size_t)(g + 16) * K + k], s2);
+        s3 = fmaf(a[(size_t)(g + 24) * J + j], b[(size_t)(g + 24) * K + k], s3);
+    }
+    for (; g < G; g += 8) s0 = fmaf(a[(size_t)g * J + j], b[(size_t)g * K + k], s0);
+    red[slice][lane] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (slice == 0 && live) {
+        float s = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s += red[q][lane];
+        out[j * ldo + koff + k] = s;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
