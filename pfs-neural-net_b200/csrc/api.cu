@@ -197,6 +197,15 @@ bool node_bwd_mma_enabled() {
     return v == 1 && node_mma_enabled();
 }
 
+bool edge_bwd_lean_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PFS_EDGE_BWD_LEAN");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+
 // staging geometry of the edge kernels (common.cuh: TileStage)
 int max_fibres_per_tile(const Topo& tp) {
     const int m = tp.layout == PFS_LAYOUT_DENSE ? tp.fpt : kTile;
@@ -441,12 +450,19 @@ int edge_bwd_impl(const pfs_edge_args& a, const Topo& tp) {
     const int total = tp.ntiles * tp.G;
     const int mode = !a.normed ? 0 : (a.training ? 1 : 2);
     using SM = EdgeBwdSmem<F>;
-    auto kern = k_edge_bwd<F>;
+    // PFS_EDGE_BWD_LEAN=1 selects the lean variant: two CTAs per SM (x_e staged only, 128 registers).  Measured at
+    // C3: 1.73 ms against 1.62 ms for the double-buffered one-CTA-per-SM default -- at Fdim 10 the 225-register
+    // kernel spills 400 B per thread under the 128-register cap, which costs more than the second CTA hides
+    const bool lean = SM::lean_fits && edge_bwd_lean_enabled();
+    auto kern = lean ? k_edge_bwd<F, true> : k_edge_bwd<F, false>;
     const int max_fib = max_fibres_per_tile(tp);
     const bool sc = stage_class_table(tp, H);
-    size_t smem_bwd = 0;
-    const int nbuf = pick_nbuf([&](int nb) { return SM::bytes(max_fib, tp.T, sc, nb); }, smem_bwd);
-    if (!nbuf) return fail(PFS_ERR_UNSUPPORTED, "edge_bwd: tile staging does not fit shared memory");
+    size_t smem_bwd = SM::bytes_lean;
+    int nbuf = 1;
+    if (!lean) {
+        nbuf = pick_nbuf([&](int nb) { return SM::bytes(max_fib, tp.T, sc, nb); }, smem_bwd);
+        if (!nbuf) return fail(PFS_ERR_UNSUPPORTED, "edge_bwd: tile staging does not fit shared memory");
+    }
     PFS_TRY(allow_smem(kern, smem_bwd));
     const int grid = persistent_grid(kern, smem_bwd, total);
     constexpr int pstride = 2 * H * F + F;

@@ -6,6 +6,8 @@
 //           registers, weight gradients as a CTA-wide outer-product accumulation over the tile,
 //           fibre sums / class sums of dh for the node tables.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace pfs {
@@ -226,14 +228,20 @@ struct EdgeBwdSmem {
     static size_t bytes(int max_fib, int T, bool with_class, int nbuf) {
         return sizeof(float) * ((size_t)kTiles + Stage::floats(max_fib, T, with_class, nbuf));
     }
+    // lean variant (two CTAs per SM): only x_e is staged (single buffer, it is needed in shared memory for dW1_e);
+    // the other per-edge rows and the node tables are read straight from global / L1, the second resident CTA
+    // hides their latency
+    using StageLean = TileStage<F, 1, 0, 0>;
+    static constexpr size_t bytes_lean = sizeof(float) * ((size_t)kTiles + (size_t)kTile * F);   // + one x_e buffer
+    static constexpr bool lean_fits = bytes_lean <= 113 * 1024;
 };
 
-template <int F>
-__global__ void __launch_bounds__(kThreads) k_edge_bwd(const EdgeBwdParams p) {
+template <int F, bool LEAN>
+__global__ void __launch_bounds__(kThreads, LEAN ? 2 : 1) k_edge_bwd(const EdgeBwdParams p) {
     constexpr int H = 4 * F;
     using SM = EdgeBwdSmem<F>;
     using CW = EdgeBwdConst<F>;
-    using Stage = typename SM::Stage;
+    using Stage = typename std::conditional<LEAN, typename SM::StageLean, typename SM::Stage>::type;
     constexpr int LDH = SM::LDH, LDF = SM::LDF;
     extern __shared__ __align__(16) float sm[];
     float* DH = sm;                  // [kTile][LDH]
@@ -241,7 +249,7 @@ __global__ void __launch_bounds__(kThreads) k_edge_bwd(const EdgeBwdParams p) {
     float* DZ = A1 + kTile * LDH;    // [kTile][LDF]
     const Topo& tp = p.tp;
     Stage stg;
-    stg.init(DZ + kTile * LDF, p.max_fib, tp.T, p.stage_class != 0, p.nbuf);
+    stg.init(DZ + kTile * LDF, LEAN ? 0 : p.max_fib, tp.T, !LEAN && p.stage_class != 0, LEAN ? 1 : p.nbuf);
     auto tile_of = [&](int i) { return get_tile(tp, i); };
     // the two weight-gradient accumulations run side by side on the two halves of the CTA
     typename SM::AccW1 accw1;
@@ -265,14 +273,25 @@ __global__ void __launch_bounds__(kThreads) k_edge_bwd(const EdgeBwdParams p) {
             const EdgeRef er = get_edge(tp, t, threadIdx.x);
             float x[F], h[H], dz[F];
             lds_row<F>(XE + threadIdx.x * F, x);
-            lds_row<H>(stg.fib(b) + (er.src - t.fibre0) * H, h);
-            if (p.stage_class) lds_add_row<H>(stg.cls(b) + er.tgt * Stage::PCP, h);
-            else add_row<H>(p.Pt + ((size_t)t.g * tp.T + er.tgt) * H, h);
+            if constexpr (LEAN) {
+                load_row<H>(p.Ps + ((size_t)t.g * tp.S + er.src) * H, h);
+                add_row<H>(p.Pt + ((size_t)t.g * tp.T + er.tgt) * H, h);
+            } else {
+                lds_row<H>(stg.fib(b) + (er.src - t.fibre0) * H, h);
+                if (p.stage_class) lds_add_row<H>(stg.cls(b) + er.tgt * Stage::PCP, h);
+                else add_row<H>(p.Pt + ((size_t)t.g * tp.T + er.tgt) * H, h);
+            }
             dense_acc_c<F, H, CW::kW1t>(x, h);
             {
                 float gr[F], xo[F];
-                lds_row<F>(stg.edge(b, 2) + threadIdx.x * F, gr);
-                lds_row<F>(stg.edge(b, 1) + threadIdx.x * F, xo);
+                if constexpr (LEAN) {
+                    const size_t row = ((size_t)t.g * tp.E + er.e) * F;
+                    load_row<F>(p.gout + row, gr);
+                    load_row<F>(p.xe2 + row, xo);
+                } else {
+                    lds_row<F>(stg.edge(b, 2) + threadIdx.x * F, gr);
+                    lds_row<F>(stg.edge(b, 1) + threadIdx.x * F, xo);
+                }
                 const float* c = p.coef + (size_t)t.g * 6 * F;
 #pragma unroll
                 for (int j = 0; j < F; ++j) {
