@@ -177,6 +177,24 @@ int upload_weights(const PackList& pl, int nfloats, float* staging, cudaStream_t
     return PFS_OK;
 }
 
+// message-MLP weights of the SModel / TModel edge kernels -> constant bank (common.cuh: MsgEdgeConst)
+template <int F>
+int upload_msg_weights(const float* w1, const float* w2, const float* b2, float* wstage, cudaStream_t st) {
+    using CW = MsgEdgeConst<F>;
+    constexpr int M = 2 * F;
+    PackList pl{};
+    int n = 0;
+    pl.it[n++] = PackItem{w1, M, F, F, M, 1, CW::kW1t};       // W1[:, F:] input-major [F][M]
+    pl.it[n++] = PackItem{w1, M, F, F, M, 0, CW::kW1o};       // W1[:, F:] as stored [M][F]
+    if (w2) {
+        pl.it[n++] = PackItem{w2, M, 0, M, M, 1, CW::kW2t};   // W2 input-major
+        pl.it[n++] = PackItem{w2, M, 0, M, M, 0, CW::kW2o};   // W2 as stored
+    }
+    if (b2) pl.it[n++] = PackItem{b2, 1, 0, 1, M, 0, CW::kB2};
+    pl.n = n;
+    return upload_weights(pl, CW::kFloats, wstage, st);
+}
+
 // PFS_NODE_MMA=0 switches the fibre MLP back from the tcgen05 kernel to the FMA kernel (A/B runs)
 bool node_mma_enabled() {
     static int v = -1;
@@ -553,6 +571,7 @@ int source_fwd_impl(const pfs_source_args& a, const Topo& tp) {
     PFS_TRY((node_linear<F, M>(a.x_t, tp.T, tp.G, a.w1, M, 0, a.b1, nullptr, Qt, st)));
     {
         SourceEdgeFwdParams p{tp, a.x_e, Qt, a.w1, a.w2, a.b2, a.moments};
+        PFS_TRY(upload_msg_weights<F>(a.w1, a.w2, a.b2, wstage, st));
         const int grid = persistent_grid(k_source_edge_fwd<F>, 0, total);
         k_source_edge_fwd<F><<<grid, kThreads, 0, st>>>(p);
         PFS_LAUNCH_CHECK("k_source_edge_fwd");
@@ -710,6 +729,7 @@ int source_bwd_impl(const pfs_source_args& a, const Topo& tp) {
         const bool dense = tp.layout == PFS_LAYOUT_DENSE;
         SourceEdgeBwdParams p{tp, a.x_e, Qt, a.w1, a.w2, a.b2, a.moments, coefA, a.g_x_e,
                               dense ? stage : nullptr, dense ? nullptr : stage, wpe, pstride_e};
+        PFS_TRY(upload_msg_weights<F>(a.w1, a.w2, a.b2, wstage, st));
         ke<<<gride, kThreads, SME::bytes, st>>>(p);
         PFS_LAUNCH_CHECK("k_source_edge_bwd");
     }
@@ -754,6 +774,7 @@ int target_fwd_impl(const pfs_target_args& a, const Topo& tp) {
     float* Rs = ws.f((size_t)tp.G * tp.S * M);
     float* stage = ws.f(class_stage_floats(tp, M));
     float* cscs = ws.f(csc_scratch_floats(tp, M) + 1);
+    float* wstage = ws.f(kConstFloats);
     if (!ws.ok) return fail(PFS_ERR_WORKSPACE, "target_fwd: workspace too small (%zu B)", a.workspace_bytes);
     if (a.normed) PFS_REQUIRE(a.gamma && a.beta && a.bn_save, "normed target model needs gamma, beta, bn_save");
     if (a.normed && a.training && tp.T <= 1)
@@ -763,6 +784,7 @@ int target_fwd_impl(const pfs_target_args& a, const Topo& tp) {
     {
         const bool dense = tp.layout == PFS_LAYOUT_DENSE;
         TargetEdgeFwdParams p{tp, a.x_e, Rs, a.w1, dense ? stage : nullptr, dense ? nullptr : stage};
+        PFS_TRY(upload_msg_weights<F>(a.w1, nullptr, nullptr, wstage, st));
         const int grid = persistent_grid(k_target_edge_fwd<F>, 0, total);
         k_target_edge_fwd<F><<<grid, kThreads, 0, st>>>(p);
         PFS_LAUNCH_CHECK("k_target_edge_fwd");
@@ -803,6 +825,7 @@ int target_bwd_impl(const pfs_target_args& a, const Topo& tp) {
     float* dRs = ws.f((size_t)tp.G * tp.S * M);
     float* wpe = ws.f((size_t)gride * pstride_e);
     float* opart = ws.f((size_t)kMaxCtas * (M * F + M));
+    float* wstage = ws.f(kConstFloats);
     if (!ws.ok) return fail(PFS_ERR_WORKSPACE, "target_bwd: workspace too small (%zu B)", a.workspace_bytes);
     {
         TargetTailParams p = make_tail(a, tp);
@@ -831,6 +854,7 @@ int target_bwd_impl(const pfs_target_args& a, const Topo& tp) {
     PFS_TRY((node_linear<F, M>(a.x_s, tp.S, tp.G, a.w1, M, 0, a.b1, nullptr, Rs, st)));
     {
         TargetEdgeBwdParams p{tp, a.x_e, Rs, a.w1, dasum, a.g_x_e, dRs, wpe, pstride_e};
+        PFS_TRY(upload_msg_weights<F>(a.w1, nullptr, nullptr, wstage, st));
         ke<<<gride, kThreads, SM::bytes, st>>>(p);
         PFS_LAUNCH_CHECK("k_target_edge_bwd");
     }

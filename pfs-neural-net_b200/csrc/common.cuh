@@ -381,6 +381,18 @@ __device__ __forceinline__ void dense_acc_c(const float (&x)[K], float (&y)[J]) 
     }
 }
 
+// constant-bank layout of the SModel / TModel edge kernels (floats; common.cuh: c_w).  The message-MLP weights are
+// warp-uniform operands: read as LDCU -> uniform registers -> FFMA2 they do not touch the shared-memory return
+// path, whose 128 B/clk/SM capped the broadcast-LDS version of these kernels at ~25 % of the FMA pipe.
+//   W1t [F][M] input-major (h_j += W1[j][F+k] x_k), W2t [M][M] input-major, W2o [M][M] as stored
+//   (da_k += W2[j][k] dm_j), W1o [M][F] as stored (dx_k += W1[j][F+k] dh_j), b2 [M]
+template <int F>
+struct MsgEdgeConst {
+    static constexpr int M = 2 * F;
+    static constexpr int kW1t = 0, kW2t = F * M, kW2o = F * M + M * M, kW1o = F * M + 2 * M * M,
+                         kB2 = 2 * F * M + 2 * M * M, kFloats = 2 * F * M + 2 * M * M + M;
+};
+
 // packs dst[k * J + j] = W[j * ld + koff + k] (input-major) or dst[j * K + k] (output-major)
 struct PackItem {
     const float* W;

@@ -34,14 +34,8 @@ template <int F>
 __global__ void __launch_bounds__(kThreads) k_source_edge_fwd(const SourceEdgeFwdParams p) {
     constexpr int M = 2 * F;
     constexpr int LDT = kTile + 1;
-    __shared__ __align__(16) float W1t[F * M];
-    __shared__ __align__(16) float W2t[M * M];
-    __shared__ float b2s[M];
+    using CW = MsgEdgeConst<F>;
     __shared__ float MT[M * LDT];   // messages, feature-major
-    load_w_inmajor<F, M>(W1t, p.w1, M, F);
-    load_w_inmajor<M, M>(W2t, p.w2, M, 0);
-    load_vec<M>(b2s, p.b2);
-    __syncthreads();
     const Topo& tp = p.tp;
     const int total = tp.ntiles * tp.G;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
@@ -51,13 +45,13 @@ __global__ void __launch_bounds__(kThreads) k_source_edge_fwd(const SourceEdgeFw
             float x[F], h[M], m[M];
             load_row<F>(p.xe2 + ((size_t)t.g * tp.E + er.e) * F, x);
             load_row<M>(p.Qt + ((size_t)t.g * tp.T + er.tgt) * M, h);
-            dense_acc<F, M>(W1t, x, h);
+            dense_acc_c<F, M, CW::kW1t>(x, h);
 #pragma unroll
             for (int j = 0; j < M; ++j) {
                 h[j] = lrelu(h[j]);
-                m[j] = b2s[j];
+                m[j] = c_w[CW::kB2 + j];
             }
-            dense_acc<M, M>(W2t, h, m);
+            dense_acc_c<M, M, CW::kW2t>(h, m);
 #pragma unroll
             for (int j = 0; j < M; ++j) MT[j * LDT + threadIdx.x] = m[j];
         }
@@ -476,7 +470,7 @@ template <int F>
 struct SourceEdgeBwdSmem {
     static constexpr int M = 2 * F;
     static constexpr int LDM = M + 4, LDF = F + 2;
-    static constexpr int kWeights = F * M + 2 * M * M + F * M + M;
+    static constexpr int kWeights = 0;   // the weights live in the constant bank (MsgEdgeConst)
     static constexpr int kTiles = kTile * (3 * LDM + LDF);
     static constexpr size_t bytes = sizeof(float) * (kWeights + kTiles);
 };
@@ -486,21 +480,11 @@ __global__ void __launch_bounds__(kThreads, (F <= 10 ? 2 : 1)) k_source_edge_bwd
     using SM = SourceEdgeBwdSmem<F>;
     constexpr int M = 2 * F, LDM = SM::LDM, LDF = SM::LDF;
     extern __shared__ __align__(16) float sm[];
-    float* W1t = sm;                 // [k<F][j<M]
-    float* W2t = W1t + F * M;        // [k<M][j<M]
-    float* W2o = W2t + M * M;        // [j<M][k<M]   das_k += W2[j][k] dm_j
-    float* W1o = W2o + M * M;        // [j<M][k<F]   dx_k  += W1[j][F+k] dhs_j
-    float* b2s = W1o + F * M;        // [M]
-    float* DM = b2s + M;             // [kTile][LDM]
+    using CW = MsgEdgeConst<F>;
+    float* DM = sm;                  // [kTile][LDM]
     float* AS = DM + kTile * LDM;
     float* DHS = AS + kTile * LDM;
     float* XE = DHS + kTile * LDM;   // [kTile][LDF]
-    load_w_inmajor<F, M>(W1t, p.w1, M, F);
-    load_w_inmajor<M, M>(W2t, p.w2, M, 0);
-    load_w_outmajor<M, M>(W2o, p.w2, M, 0);
-    load_w_outmajor<F, M>(W1o, p.w1, M, F);
-    load_vec<M>(b2s, p.b2);
-    __syncthreads();
     using AccW2 = OuterAcc<M, M, 4, F / 2, 0, 160>;            // dW2[j][k]   = sum dm_j as_k
     using AccW1 = OuterAcc<M, F, 4, F / 2, 160, 96>;           // dW1_e[j][k] = sum dhs_j x_k
     AccW2 accw2;
@@ -520,14 +504,14 @@ __global__ void __launch_bounds__(kThreads, (F <= 10 ? 2 : 1)) k_source_edge_bwd
             float x[F], h[M], m[M];
             load_row<F>(p.xe2 + row, x);
             load_row<M>(p.Qt + ((size_t)t.g * tp.T + er.tgt) * M, h);
-            dense_acc<F, M>(W1t, x, h);
+            dense_acc_c<F, M, CW::kW1t>(x, h);
             float a[M];
 #pragma unroll
             for (int j = 0; j < M; ++j) {
                 a[j] = lrelu(h[j]);
-                m[j] = b2s[j];
+                m[j] = c_w[CW::kB2 + j];
             }
-            dense_acc<M, M>(W2t, a, m);
+            dense_acc_c<M, M, CW::kW2t>(a, m);
             // dm = (A0 + A1 m + A2 d^2 + A3 d^3) / count
             int e0, n;
             fibre_range(tp, t, er.src - t.fibre0, e0, n);
@@ -566,14 +550,14 @@ __global__ void __launch_bounds__(kThreads, (F <= 10 ? 2 : 1)) k_source_edge_bwd
             float da[M];
 #pragma unroll
             for (int k = 0; k < M; ++k) da[k] = 0.f;
-            dense_acc<M, M>(W2o, dm, da);
+            dense_acc_c<M, M, CW::kW2o>(dm, da);
 #pragma unroll
             for (int k = 0; k < M; ++k) da[k] *= dlrelu(h[k]);   // dhs
             store_row_smem<M>(DHS + threadIdx.x * LDM, da);
             float dx[F];
 #pragma unroll
             for (int k = 0; k < F; ++k) dx[k] = 0.f;
-            dense_acc<M, F>(W1o, da, dx);
+            dense_acc_c<M, F, CW::kW1o>(da, dx);
             store_row<F>(p.g_x_e + row, dx);
             if (p.dhs_rows) store_row<M>(p.dhs_rows + ((size_t)t.g * tp.E + t.q0 + threadIdx.x) * M, da);
         }

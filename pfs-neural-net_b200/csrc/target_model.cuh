@@ -23,10 +23,8 @@ struct TargetEdgeFwdParams {
 template <int F>
 __global__ void __launch_bounds__(kThreads) k_target_edge_fwd(const TargetEdgeFwdParams p) {
     constexpr int M = 2 * F, LDM = M + 1;
-    __shared__ __align__(16) float W1t[F * M];
+    using CW = MsgEdgeConst<F>;      // only W1t / W1o of the layout are used by the TModel kernels
     __shared__ float AT[kTile * LDM];
-    load_w_inmajor<F, M>(W1t, p.w1, M, F);
-    __syncthreads();
     const Topo& tp = p.tp;
     const int total = tp.ntiles * tp.G;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
@@ -36,7 +34,7 @@ __global__ void __launch_bounds__(kThreads) k_target_edge_fwd(const TargetEdgeFw
             float x[F], h[M];
             load_row<F>(p.xe2 + ((size_t)t.g * tp.E + er.e) * F, x);
             load_row<M>(p.Rs + ((size_t)t.g * tp.S + er.src) * M, h);
-            dense_acc<F, M>(W1t, x, h);
+            dense_acc_c<F, M, CW::kW1t>(x, h);
 #pragma unroll
             for (int j = 0; j < M; ++j) h[j] = lrelu(h[j]);
             if (p.act_rows) {
@@ -343,7 +341,7 @@ struct TargetEdgeBwdSmem {
     static constexpr int kTiles = kTile * (LDM + LDF);
     // the tile region doubles as the cross-group scratch of the weight-gradient flush
     static constexpr int kRegion = kTiles > AccW1::kScratchFloats ? kTiles : AccW1::kScratchFloats;
-    static constexpr int kFloats = 2 * F * M + kRegion;
+    static constexpr int kFloats = kRegion;   // the weights live in the constant bank (MsgEdgeConst)
     static constexpr size_t bytes = sizeof(float) * kFloats;
 };
 
@@ -352,13 +350,9 @@ __global__ void __launch_bounds__(kThreads) k_target_edge_bwd(const TargetEdgeBw
     using SM = TargetEdgeBwdSmem<F>;
     constexpr int M = 2 * F, LDM = SM::LDM, LDF = SM::LDF;
     extern __shared__ __align__(16) float sm[];
-    float* W1t = sm;               // [k<F][j<M]
-    float* W1o = W1t + F * M;      // [j<M][k<F]
-    float* DHT = W1o + F * M;      // [kTile][LDM]
+    using CW = MsgEdgeConst<F>;
+    float* DHT = sm;               // [kTile][LDM]
     float* XE = DHT + kTile * LDM; // [kTile][LDF]
-    load_w_inmajor<F, M>(W1t, p.w1, M, F);
-    load_w_outmajor<F, M>(W1o, p.w1, M, F);
-    __syncthreads();
     using AccW1 = typename SM::AccW1;
     AccW1 accw1;
     accw1.init();
@@ -372,7 +366,7 @@ __global__ void __launch_bounds__(kThreads) k_target_edge_bwd(const TargetEdgeBw
             float x[F], h[M], d[M];
             load_row<F>(p.xe2 + row, x);
             load_row<M>(p.Rs + ((size_t)t.g * tp.S + er.src) * M, h);
-            dense_acc<F, M>(W1t, x, h);
+            dense_acc_c<F, M, CW::kW1t>(x, h);
             load_row<M>(p.dasum + ((size_t)t.g * tp.T + er.tgt) * M, d);
 #pragma unroll
             for (int j = 0; j < M; ++j) d[j] *= dlrelu(h[j]);
@@ -381,7 +375,7 @@ __global__ void __launch_bounds__(kThreads) k_target_edge_bwd(const TargetEdgeBw
             float dx[F];
 #pragma unroll
             for (int k = 0; k < F; ++k) dx[k] = 0.f;
-            dense_acc<M, F>(W1o, d, dx);
+            dense_acc_c<M, F, CW::kW1o>(d, dx);
             store_row<F>(p.g_x_e + row, dx);
         }
         __syncthreads();
