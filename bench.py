@@ -45,7 +45,7 @@ KERNEL_ROWS = {
     "k_source_node_fwd_mma": (0, 22), "k_source_node_bwd_mma": (0, 32),
 }
 # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` captures of
-# the default C3 workload (profiles/r01_ncu_full_c3_top4.txt, r01_ncu_full_fma_path.txt); reported as `roofline.traffic`
+# the default C3 workload (profiles/r01_ncu_full_c3_top7.txt, r01_ncu_full_fma_path.txt); reported as `roofline.traffic`
 # for that workload only
 KERNEL_TRAFFIC_C3 = {"k_edge_bwd": 1404.0e6, "k_source_edge_bwd": 907.8e6, "k_source_node_bwd": 766.2e6,
                      "k_source_node_bwd_mma": 766.5e6, "k_source_node_fwd_mma": 497.7e6, "k_edge_fwd": 655.6e6,

@@ -256,38 +256,102 @@ __device__ __forceinline__ void stage_rows(float* dst, const float* __restrict__
 // per-fibre table (rows of PF floats, the tile's fibres are consecutive) and one per-class table
 // (rows of PC floats, padded to PC + 4 in shared memory against bank conflicts; staged only
 // when it is small enough, else read through L1).  All threads of the CTA call issue().
+// TMA bulk copy (cp.async.bulk, 1-D): one elected thread moves a whole contiguous slab global -> shared and the
+// bytes land on an mbarrier; addresses and size must be multiples of 16 bytes
+__device__ __forceinline__ void bulk_g2s(float* smem, const float* gmem, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem)),
+                 "l"(gmem), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void stage_bar_init(uint64_t* bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)));
+}
+__device__ __forceinline__ void stage_bar_expect(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void stage_bar_wait(uint64_t* bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
 template <int F, int NE, int PF, int PC>
 struct TileStage {
     static constexpr int PCP = PC + 4;
     float* base;
+    uint64_t* bars;          // one mbarrier per buffer (bulk-copied tiles)
+    unsigned phase[2];
     int per, max_fib;
     bool with_class, dbl;
     // nbuf = 2: double-buffered (tile i+1 in flight while tile i is computed); 1: load-then-compute
     __host__ __device__ static size_t floats(int max_fib, int T, bool with_class, int nbuf = 2) {
-        return nbuf * ((size_t)NE * kTile * F + (size_t)max_fib * PF + (with_class ? (size_t)T * PCP : 0));
+        return nbuf * ((size_t)NE * kTile * F + (size_t)max_fib * PF + (with_class ? (size_t)T * PCP : 0)) + 4;   // + 2 mbarriers
     }
+    // all threads of the CTA call init(); ends with a __syncthreads()
     __device__ __forceinline__ void init(float* dyn, int max_fib_, int T, bool with_class_, int nbuf = 2) {
         base = dyn;
         max_fib = max_fib_;
         with_class = with_class_;
         dbl = nbuf == 2;
         per = NE * kTile * F + max_fib * PF + (with_class ? T * PCP : 0);
+        bars = reinterpret_cast<uint64_t*>(base + (size_t)nbuf * per + ((nbuf * per) & 1));
+        phase[0] = phase[1] = 0u;
+        if (threadIdx.x == 0) {
+            stage_bar_init(bars);
+            stage_bar_init(bars + 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
+    // A tile of the dense layout is a few contiguous slabs: when every slab is 16-byte aligned and a multiple of
+    // 16 bytes it is fetched by TMA bulk copies issued by ONE thread (no per-thread address arithmetic, completion
+    // on an mbarrier); otherwise (general edge lists: row gathers; odd sizes) every thread issues cp.async chunks.
+    __device__ __forceinline__ bool bulk_ok(const Topo& tp, const Tile& t, const float* const* esrc, const float* fsrc,
+                                            const float* csrc) const {
+        if (tp.layout != PFS_LAYOUT_DENSE) return false;
+        uintptr_t bits = (uintptr_t)base | (uintptr_t)((size_t)per * sizeof(float)) | (uintptr_t)((size_t)t.ne * F * sizeof(float));
+#pragma unroll
+        for (int i = 0; i < NE; ++i) bits |= (uintptr_t)(esrc[i] + ((size_t)t.g * tp.E + t.q0) * F);
+        if constexpr (PF > 0) bits |= (uintptr_t)(fsrc + ((size_t)t.g * tp.S + t.fibre0) * PF) | (uintptr_t)(PF * sizeof(float)) |
+                                      (uintptr_t)((size_t)max_fib * PF * sizeof(float));
+        if constexpr (PC > 0) {
+            if (with_class) bits |= (uintptr_t)(csrc + (size_t)t.g * tp.T * PC) | (uintptr_t)(PC * sizeof(float));
+        }
+        return (bits & 15) == 0;
     }
     // pipeline step at the top of the loop body for `tile` (buffer parity b): returns the buffer
     // holding this tile once the following __syncthreads() has passed
     template <class GetTile>
     __device__ __forceinline__ int step(const Topo& tp, int tile, int t_end, int b, const float* const* esrc,
-                                        const float* fsrc, const float* csrc, GetTile get) const {
+                                        const float* fsrc, const float* csrc, GetTile get) {
         if (dbl) {
             if (tile + 1 < t_end) issue(tp, get(tile + 1), b ^ 1, esrc, fsrc, csrc);
             cp_async_commit();
             cp_async_wait<1>();
+            wait_bulk(tp, get(tile), b, esrc, fsrc, csrc);
             return b;
         }
         issue(tp, get(tile), 0, esrc, fsrc, csrc);
         cp_async_commit();
         cp_async_wait<0>();
+        wait_bulk(tp, get(tile), 0, esrc, fsrc, csrc);
         return 0;
+    }
+    __device__ __forceinline__ void wait_bulk(const Topo& tp, const Tile& t, int b, const float* const* esrc,
+                                              const float* fsrc, const float* csrc) {
+        if (bulk_ok(tp, t, esrc, fsrc, csrc)) {
+            stage_bar_wait(bars + b, phase[b]);
+            phase[b] ^= 1u;
+        }
     }
     // before the loop: first tile of a double-buffered pipeline
     template <class GetTile>
@@ -304,6 +368,22 @@ struct TileStage {
     // enqueue the copies of tile t into buffer b (no commit: the caller may add more, then commits)
     __device__ __forceinline__ void issue(const Topo& tp, const Tile& t, int b, const float* const* esrc,
                                           const float* fsrc, const float* csrc) const {
+        if (bulk_ok(tp, t, esrc, fsrc, csrc)) {
+            if (threadIdx.x == 0) {
+                const unsigned eb = (unsigned)(t.ne * F * sizeof(float)), fb = (unsigned)(t.nfib * PF * sizeof(float));
+                const unsigned cb = (PC > 0 && with_class) ? (unsigned)(tp.T * PC * sizeof(float)) : 0u;
+                stage_bar_expect(bars + b, NE * eb + fb + cb);
+#pragma unroll
+                for (int i = 0; i < NE; ++i) bulk_g2s(edge(b, i), esrc[i] + ((size_t)t.g * tp.E + t.q0) * F, eb, bars + b);
+                if constexpr (PF > 0) bulk_g2s(fib(b), fsrc + ((size_t)t.g * tp.S + t.fibre0) * PF, fb, bars + b);
+                if constexpr (PC > 0) {
+                    if (with_class)      // rows are padded to PCP floats in shared memory: one copy per class row
+                        for (int c = 0; c < tp.T; ++c)
+                            bulk_g2s(cls(b) + c * PCP, csrc + ((size_t)t.g * tp.T + c) * PC, (unsigned)(PC * sizeof(float)), bars + b);
+                }
+            }
+            return;
+        }
         const int* idx = (tp.layout != PFS_LAYOUT_DENSE && tp.eid) ? tp.eid + t.q0 : nullptr;
         const long long row0 = idx ? 0 : t.q0;
 #pragma unroll

@@ -21,6 +21,7 @@
 //     bank), dW4 / db4 (outer-product accumulators on five warps, running under the MMAs), the
 //     BatchNorm backward of the upstream gradient and the moment-polynomial coefficients.
 #pragma once
+#include <cfloat>
 #include "source_node_c.cuh"
 #include "tc_ptx.cuh"
 
@@ -225,14 +226,23 @@ __global__ void __launch_bounds__(kNodeThreadsC) k_source_node_bwd_mma(const Sou
                 const float i1 = rsqrtf(var + kStdEps);          // 1 / std (NaN for var + eps < 0, like the sqrt)
                 const float i2 = i1 * i1;
                 const float skew = c3 * (i2 * i1), kurt = c4 * (i2 * i2);
-                const bool fv = finite_f(var);
-                std_o = fv ? (var + kStdEps) * i1 : sqrtf(nan_to_num(var) + kStdEps);
-                mean_o = nan_to_num(mean);
-                skew_o = nan_to_num(skew);
-                kurt_o = nan_to_num(kurt);
-                m_fin[n] = (finite_f(mean) ? 1u : 0u) | (fv ? 2u : 0u) | (finite_f(skew) ? 4u : 0u) | (finite_f(kurt) ? 8u : 0u);
+                // |x| <= FLT_MAX is false for NaN and +-inf: one compare per statistic on the common path
+                const bool fm = fabsf(mean) <= FLT_MAX, fv = fabsf(var) <= FLT_MAX;
+                const bool fs = fabsf(skew) <= FLT_MAX, fk = fabsf(kurt) <= FLT_MAX;
+                mean_o = mean; std_o = (var + kStdEps) * i1; skew_o = skew; kurt_o = kurt;
+                float is1 = i1;
+                if (!(fm && fv && fs && fk)) {                   // rare: torch.nan_to_num semantics
+                    mean_o = nan_to_num(mean);
+                    skew_o = nan_to_num(skew);
+                    kurt_o = nan_to_num(kurt);
+                    if (!fv) {
+                        std_o = sqrtf(nan_to_num(var) + kStdEps);
+                        is1 = 1.f / std_o;                       // 1 / std as recomputed after nan_to_num
+                    }
+                }
+                m_fin[n] = (fm ? 1u : 0u) | (fv ? 2u : 0u) | (fs ? 4u : 0u) | (fk ? 8u : 0u);
                 m_mean[n] = mean; m_vr[n] = vr; m_c2[n] = c2; m_c3[n] = c3; m_c4[n] = c4; m_i1[n] = i1;
-                m_is1[n] = fv ? i1 : 1.f / std_o;                // 1 / std as recomputed after nan_to_num
+                m_is1[n] = is1;
             }
             if (rr < R) {
                 put(rr, F + j, mean_o);

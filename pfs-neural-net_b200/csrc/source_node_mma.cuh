@@ -13,6 +13,7 @@
 //     commits to an mbarrier; warps 0-3 read their 32 lanes back with tcgen05.ld and run the
 //     epilogue (bias, LeakyReLU, hidden store, second layer, BatchNorm tile statistics).
 #pragma once
+#include <cfloat>
 #include "source_node_c.cuh"
 #include "tc_ptx.cuh"
 
@@ -157,12 +158,17 @@ __global__ void __launch_bounds__(kNodeThreadsC) k_source_node_fwd_mma(const Sou
                 const float mean = pf_mo[n][0], ex2 = pf_mo[n][1], c3 = pf_mo[n][2], c4 = pf_mo[n][3];
                 const float vr = ex2 - mean * mean;
                 const float var = vr > 0.f ? vr : kSlopeVar * vr;
-                const float std0 = sqrtf(var + kStdEps);
-                const float s3 = std0 * std0 * std0;
-                mean_o = nan_to_num(mean);
-                std_o = sqrtf(nan_to_num(var) + kStdEps);
-                skew_o = nan_to_num(c3 / s3);
-                kurt_o = nan_to_num(c4 / (s3 * std0));
+                const float i1 = rsqrtf(var + kStdEps);          // 1 / std (NaN for var + eps < 0, like the sqrt)
+                const float i2 = i1 * i1;
+                const float skew = c3 * (i2 * i1), kurt = c4 * (i2 * i2);
+                mean_o = mean; std_o = (var + kStdEps) * i1; skew_o = skew; kurt_o = kurt;
+                // |x| <= FLT_MAX is false for NaN and +-inf: one compare per statistic on the common path
+                if (!(fabsf(mean) <= FLT_MAX && fabsf(var) <= FLT_MAX && fabsf(skew) <= FLT_MAX && fabsf(kurt) <= FLT_MAX)) {
+                    mean_o = nan_to_num(mean);                   // rare: torch.nan_to_num semantics
+                    skew_o = nan_to_num(skew);
+                    kurt_o = nan_to_num(kurt);
+                    if (!(fabsf(var) <= FLT_MAX)) std_o = sqrtf(nan_to_num(var) + kStdEps);
+                }
             }
             put(r, F + j, mean_o);
             put(r, F + M2 + j, std_o);
