@@ -219,7 +219,7 @@ bool edge_bwd_lean_enabled() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("PFS_EDGE_BWD_LEAN");
-        v = (e && e[0] == '1') ? 1 : 0;
+        v = (e && e[0] == '0') ? 0 : 1;
     }
     return v == 1;
 }
@@ -468,11 +468,11 @@ int edge_bwd_impl(const pfs_edge_args& a, const Topo& tp) {
     const int total = tp.ntiles * tp.G;
     const int mode = !a.normed ? 0 : (a.training ? 1 : 2);
     using SM = EdgeBwdSmem<F>;
-    // PFS_EDGE_BWD_LEAN=1 selects the lean variant: two CTAs per SM (x_e staged only, 128 registers).  Measured at
-    // C3: 1.73 ms against 1.62 ms for the double-buffered one-CTA-per-SM default -- at Fdim 10 the 225-register
-    // kernel spills 400 B per thread under the 128-register cap, which costs more than the second CTA hides
+    // k_edge_bwd2 (two CTAs per SM: x_e staged only, hidden layer in two halves, shared accumulator registers) where
+    // its tiles fit 113 KB; PFS_EDGE_BWD_LEAN=0 selects the double-buffered one-CTA-per-SM kernel (A/B runs).
+    // Measured at C3: 1.21 ms against 1.60 ms.
     const bool lean = SM::lean_fits && edge_bwd_lean_enabled();
-    auto kern = lean ? k_edge_bwd<F, true> : k_edge_bwd<F, false>;
+    auto kern = lean ? k_edge_bwd2<F> : k_edge_bwd<F>;
     const int max_fib = max_fibres_per_tile(tp);
     const bool sc = stage_class_table(tp, H);
     size_t smem_bwd = SM::bytes_lean;

@@ -289,7 +289,7 @@ struct TileStage {
     static constexpr int PCP = PC + 4;
     float* base;
     uint64_t* bars;          // one mbarrier per buffer (bulk-copied tiles)
-    unsigned phase[2];
+    unsigned phase;          // bit b = parity of buffer b's mbarrier
     int per, max_fib;
     bool with_class, dbl;
     // nbuf = 2: double-buffered (tile i+1 in flight while tile i is computed); 1: load-then-compute
@@ -304,7 +304,7 @@ struct TileStage {
         dbl = nbuf == 2;
         per = NE * kTile * F + max_fib * PF + (with_class ? T * PCP : 0);
         bars = reinterpret_cast<uint64_t*>(base + (size_t)nbuf * per + ((nbuf * per) & 1));
-        phase[0] = phase[1] = 0u;
+        phase = 0u;
         if (threadIdx.x == 0) {
             stage_bar_init(bars);
             stage_bar_init(bars + 1);
@@ -349,8 +349,8 @@ struct TileStage {
     __device__ __forceinline__ void wait_bulk(const Topo& tp, const Tile& t, int b, const float* const* esrc,
                                               const float* fsrc, const float* csrc) {
         if (bulk_ok(tp, t, esrc, fsrc, csrc)) {
-            stage_bar_wait(bars + b, phase[b]);
-            phase[b] ^= 1u;
+            stage_bar_wait(bars + b, (phase >> b) & 1u);
+            phase ^= 1u << b;
         }
     }
     // before the loop: first tile of a double-buffered pipeline
@@ -445,15 +445,16 @@ constexpr int kConstFloats = 15360;   // 60 KB of the 64 KB constant bank
 __constant__ __align__(16) float c_w[kConstFloats];
 
 // y[j] += sum_k c_w[OFF + k * J + j] * x[k]   (J even; packed FFMA2 R, R.F32, UR.F32x2, R)
-template <int K, int J, int OFF>
+// (LDW = row stride of the packed matrix: a column block of a wider matrix is OFF + first column, LDW = its width)
+template <int K, int J, int OFF, int LDW = J>
 __device__ __forceinline__ void dense_acc_c(const float (&x)[K], float (&y)[J]) {
-    static_assert(J % 2 == 0 && OFF % 2 == 0, "pairs of outputs");
+    static_assert(J % 2 == 0 && OFF % 2 == 0 && LDW % 2 == 0, "pairs of outputs");
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const float2 xx = make_float2(x[k], x[k]);
 #pragma unroll
         for (int j = 0; j < J; j += 2) {
-            const float2 a = __ffma2_rn(make_float2(c_w[OFF + k * J + j], c_w[OFF + k * J + j + 1]), xx,
+            const float2 a = __ffma2_rn(make_float2(c_w[OFF + k * LDW + j], c_w[OFF + k * LDW + j + 1]), xx,
                                         make_float2(y[j], y[j + 1]));
             y[j] = a.x;
             y[j + 1] = a.y;
@@ -779,6 +780,81 @@ struct OuterAcc {
             for (int a = 0; a < TJ; ++a)
 #pragma unroll
                 for (int c = 0; c < TK; ++c) scratch[grp * (J * K) + (j0 + a) * K + k0 + c] = acc[a][c];
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < J * K; i += kThreads) {
+            float s = 0.f;
+            for (int g = 0; g < GROUPS; ++g) s += scratch[g * (J * K) + i];
+            const int j = i / K, k = i - j * K;
+            out[j * ldo + ko + k] = s;
+        }
+        __syncthreads();
+    }
+};
+
+// OuterAcc with the accumulators passed in by the caller: two accumulations that run on disjoint thread ranges
+// of a CTA (each thread is live in exactly one) can share ONE register array instead of holding one each.
+template <int J, int K, int TJ, int TK, int T0 = 0, int NT = kThreads>
+struct OuterAccX {
+    static_assert(J % TJ == 0 && K % TK == 0 && TJ % 2 == 0, "block must divide the matrix, row pairs");
+    static constexpr int NB = (J / TJ) * (K / TK);
+    static_assert(NB <= NT, "too many blocks for the thread range");
+    static constexpr int GROUPS = NT / NB;
+    static constexpr int kScratchFloats = GROUPS * J * K;
+    static constexpr int kAcc = TJ * TK;
+    int grp, j0, k0;
+    bool live;
+    __device__ __forceinline__ void init() {
+        const int t = (int)threadIdx.x - T0;
+        grp = t >= 0 ? t / NB : GROUPS;
+        live = t >= 0 && grp < GROUPS;
+        const int b = t >= 0 ? t - grp * NB : 0;
+        j0 = (b / (K / TK)) * TJ;
+        k0 = (b % (K / TK)) * TK;
+    }
+    template <int NA>
+    __device__ __forceinline__ void fma_row(float (&A)[NA], const float (&d)[TJ], const float (&x)[TK]) const {
+        static_assert(NA >= kAcc, "accumulator array too small");
+#pragma unroll
+        for (int a = 0; a < TJ; a += 2)
+#pragma unroll
+            for (int c = 0; c < TK; ++c) {
+                const float2 v = __ffma2_rn(make_float2(d[a], d[a + 1]), make_float2(x[c], x[c]),
+                                            make_float2(A[a * TK + c], A[(a + 1) * TK + c]));
+                A[a * TK + c] = v.x;
+                A[(a + 1) * TK + c] = v.y;
+            }
+    }
+    template <int NA>
+    __device__ __forceinline__ void accumulate(float (&A)[NA], const float* D, int ldD, const float* X, int ldX, int rows) const {
+        if (!live) return;
+        using Base = OuterAcc<J, K, TJ, TK, T0, NT>;
+        int r = grp;
+        for (; r + GROUPS < rows; r += 2 * GROUPS) {
+            float d0[TJ], x0[TK], d1[TJ], x1[TK];
+            Base::template load_vec_smem<TJ>(D + r * ldD + j0, d0);
+            Base::template load_vec_smem<TK>(X + r * ldX + k0, x0);
+            Base::template load_vec_smem<TJ>(D + (r + GROUPS) * ldD + j0, d1);
+            Base::template load_vec_smem<TK>(X + (r + GROUPS) * ldX + k0, x1);
+            fma_row(A, d0, x0);
+            fma_row(A, d1, x1);
+        }
+        if (r < rows) {
+            float d0[TJ], x0[TK];
+            Base::template load_vec_smem<TJ>(D + r * ldD + j0, d0);
+            Base::template load_vec_smem<TK>(X + r * ldX + k0, x0);
+            fma_row(A, d0, x0);
+        }
+    }
+    // call with ALL threads of the CTA
+    template <int NA>
+    __device__ __forceinline__ void flush(const float (&A)[NA], float* scratch, float* __restrict__ out, int ldo, int ko) const {
+        __syncthreads();
+        if (live) {
+#pragma unroll
+            for (int a = 0; a < TJ; ++a)
+#pragma unroll
+                for (int c = 0; c < TK; ++c) scratch[grp * (J * K) + (j0 + a) * K + k0 + c] = A[a * TK + c];
         }
         __syncthreads();
         for (int i = threadIdx.x; i < J * K; i += kThreads) {

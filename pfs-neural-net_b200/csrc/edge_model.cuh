@@ -232,16 +232,16 @@ struct EdgeBwdSmem {
     // the other per-edge rows and the node tables are read straight from global / L1, the second resident CTA
     // hides their latency
     using StageLean = TileStage<F, 1, 0, 0>;
-    static constexpr size_t bytes_lean = sizeof(float) * ((size_t)kTiles + (size_t)kTile * F);   // + one x_e buffer
+    static constexpr size_t bytes_lean = sizeof(float) * ((size_t)kTiles + (size_t)kTile * F + 4);   // + one x_e buffer, 2 mbarriers
     static constexpr bool lean_fits = bytes_lean <= 113 * 1024;
 };
 
-template <int F, bool LEAN>
-__global__ void __launch_bounds__(kThreads, LEAN ? 2 : 1) k_edge_bwd(const EdgeBwdParams p) {
+template <int F>
+__global__ void __launch_bounds__(kThreads) k_edge_bwd(const EdgeBwdParams p) {
     constexpr int H = 4 * F;
     using SM = EdgeBwdSmem<F>;
     using CW = EdgeBwdConst<F>;
-    using Stage = typename std::conditional<LEAN, typename SM::StageLean, typename SM::Stage>::type;
+    using Stage = typename SM::Stage;
     constexpr int LDH = SM::LDH, LDF = SM::LDF;
     extern __shared__ __align__(16) float sm[];
     float* DH = sm;                  // [kTile][LDH]
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(kThreads, LEAN ? 2 : 1) k_edge_bwd(const EdgeB
     float* DZ = A1 + kTile * LDH;    // [kTile][LDF]
     const Topo& tp = p.tp;
     Stage stg;
-    stg.init(DZ + kTile * LDF, LEAN ? 0 : p.max_fib, tp.T, !LEAN && p.stage_class != 0, LEAN ? 1 : p.nbuf);
+    stg.init(DZ + kTile * LDF, p.max_fib, tp.T, p.stage_class != 0, p.nbuf);
     auto tile_of = [&](int i) { return get_tile(tp, i); };
     // the two weight-gradient accumulations run side by side on the two halves of the CTA
     typename SM::AccW1 accw1;
@@ -273,25 +273,14 @@ __global__ void __launch_bounds__(kThreads, LEAN ? 2 : 1) k_edge_bwd(const EdgeB
             const EdgeRef er = get_edge(tp, t, threadIdx.x);
             float x[F], h[H], dz[F];
             lds_row<F>(XE + threadIdx.x * F, x);
-            if constexpr (LEAN) {
-                load_row<H>(p.Ps + ((size_t)t.g * tp.S + er.src) * H, h);
-                add_row<H>(p.Pt + ((size_t)t.g * tp.T + er.tgt) * H, h);
-            } else {
-                lds_row<H>(stg.fib(b) + (er.src - t.fibre0) * H, h);
-                if (p.stage_class) lds_add_row<H>(stg.cls(b) + er.tgt * Stage::PCP, h);
-                else add_row<H>(p.Pt + ((size_t)t.g * tp.T + er.tgt) * H, h);
-            }
+            lds_row<H>(stg.fib(b) + (er.src - t.fibre0) * H, h);
+            if (p.stage_class) lds_add_row<H>(stg.cls(b) + er.tgt * Stage::PCP, h);
+            else add_row<H>(p.Pt + ((size_t)t.g * tp.T + er.tgt) * H, h);
             dense_acc_c<F, H, CW::kW1t>(x, h);
             {
                 float gr[F], xo[F];
-                if constexpr (LEAN) {
-                    const size_t row = ((size_t)t.g * tp.E + er.e) * F;
-                    load_row<F>(p.gout + row, gr);
-                    load_row<F>(p.xe2 + row, xo);
-                } else {
-                    lds_row<F>(stg.edge(b, 2) + threadIdx.x * F, gr);
-                    lds_row<F>(stg.edge(b, 1) + threadIdx.x * F, xo);
-                }
+                lds_row<F>(stg.edge(b, 2) + threadIdx.x * F, gr);
+                lds_row<F>(stg.edge(b, 1) + threadIdx.x * F, xo);
                 const float* c = p.coef + (size_t)t.g * 6 * F;
 #pragma unroll
                 for (int j = 0; j < F; ++j) {
@@ -347,6 +336,118 @@ __global__ void __launch_bounds__(kThreads, LEAN ? 2 : 1) k_edge_bwd(const EdgeB
             for (int i = 0; i < kWarps; ++i) s += red[i * F + threadIdx.x];
             out[2 * H * F + threadIdx.x] = s;
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_edge_bwd2: the same backward shaped for TWO CTAs per SM (<= 128 registers, 113 KB of shared memory):
+//   * only x_e is staged (single buffer: it has to be in shared memory for dW1_e); the other per-edge rows and
+//     the node tables come straight from global / L1, the second resident CTA hides their latency;
+//   * the hidden layer is processed in two halves of 2F units (h, dh: 2F live registers each instead of 4F);
+//   * the two weight-gradient accumulations run on the two halves of the CTA and SHARE one register array;
+//   * db2 = sum dz is taken from the staged dz rows instead of a per-thread running sum.
+// ------------------------------------------------------------------------------------------
+template <int F, int HALF>
+__device__ __forceinline__ void edge_bwd_half(const EdgeBwdParams& p, const float* __restrict__ ps, const float* __restrict__ pt,
+                                              const float (&x)[F], const float (&dz)[F], float (&dx)[F], float* A1row,
+                                              float* DHrow, float* dh_row_out) {
+    constexpr int H = 4 * F, HH = 2 * F;
+    using CW = EdgeBwdConst<F>;
+    float hh[HH], da[HH];
+    load_row<HH>(ps + HALF * HH, hh);
+    add_row<HH>(pt + HALF * HH, hh);
+    dense_acc_c<F, HH, CW::kW1t + HALF * HH, H>(x, hh);
+#pragma unroll
+    for (int k = 0; k < HH; ++k) da[k] = 0.f;
+    dense_acc_c<F, HH, CW::kW2o + HALF * HH, H>(dz, da);
+#pragma unroll
+    for (int k = 0; k < HH; ++k) {
+        da[k] *= dlrelu(hh[k]);      // dh
+        hh[k] = lrelu(hh[k]);        // a1
+    }
+    store_row_smem<HH>(A1row + HALF * HH, hh);
+    store_row_smem<HH>(DHrow + HALF * HH, da);
+    dense_acc_c<HH, F, CW::kW1o + HALF * HH * F, F>(da, dx);
+    if (dh_row_out) store_row<HH>(dh_row_out + HALF * HH, da);
+}
+
+template <int F>
+__global__ void __launch_bounds__(kThreads, 2) k_edge_bwd2(const EdgeBwdParams p) {
+    constexpr int H = 4 * F;
+    using SM = EdgeBwdSmem<F>;
+    using Stage = typename SM::StageLean;
+    constexpr int LDH = SM::LDH, LDF = SM::LDF;
+    extern __shared__ __align__(16) float sm[];
+    float* DH = sm;                  // [kTile][LDH]
+    float* A1 = DH + kTile * LDH;    // [kTile][LDH]
+    float* DZ = A1 + kTile * LDH;    // [kTile][LDF]
+    const Topo& tp = p.tp;
+    Stage stg;
+    stg.init(DZ + kTile * LDF, 0, tp.T, false, 1);
+    auto tile_of = [&](int i) { return get_tile(tp, i); };
+    using AccW1 = OuterAccX<H, F, 8, F / 2, 0, kThreads / 2>;              // dW1_e[j][k] = sum dh_j x_k
+    using AccW2 = OuterAccX<F, H, 2, 2 * F, kThreads / 2, kThreads / 2>;   // dW2[j][k]   = sum dz_j a1_k
+    constexpr int kAcc = AccW1::kAcc > AccW2::kAcc ? AccW1::kAcc : AccW2::kAcc;
+    float acc[kAcc];
+#pragma unroll
+    for (int i = 0; i < kAcc; ++i) acc[i] = 0.f;
+    AccW1 accw1;
+    AccW2 accw2;
+    accw1.init();
+    accw2.init();
+    float dzs = 0.f;                 // db2 partial of thread (row part = tid / F < 4, column tid % F)
+    const int dz_col = threadIdx.x % F, dz_part = threadIdx.x / F;
+    const float* esrc[1] = {p.x_e};
+    const int total = tp.ntiles * tp.G;
+    const int t_begin = chunk_begin(blockIdx.x, gridDim.x, total), t_end = chunk_begin(blockIdx.x + 1, gridDim.x, total);
+    for (int tile = t_begin; tile < t_end; ++tile) {
+        const Tile t = get_tile(tp, tile);
+        const int b = stg.step(tp, tile, t_end, 0, esrc, nullptr, nullptr, tile_of);
+        __syncthreads();
+        const float* XE = stg.edge(b, 0);
+        if (threadIdx.x < t.ne) {
+            const EdgeRef er = get_edge(tp, t, threadIdx.x);
+            const size_t row = ((size_t)t.g * tp.E + er.e) * F;
+            float x[F], dz[F], dx[F];
+            lds_row<F>(XE + threadIdx.x * F, x);
+            {
+                float gr[F], xo[F];
+                load_row<F>(p.gout + row, gr);
+                load_row<F>(p.xe2 + row, xo);
+                const float* c = p.coef + (size_t)t.g * 6 * F;
+#pragma unroll
+                for (int j = 0; j < F; ++j) {
+                    const float xh = (xo[j] - __ldg(c + 4 * F + j)) * __ldg(c + 3 * F + j);
+                    dz[j] = __ldg(c + j) * (gr[j] - __ldg(c + F + j) - xh * __ldg(c + 2 * F + j));
+                }
+            }
+            store_row_smem<F>(DZ + threadIdx.x * LDF, dz);
+#pragma unroll
+            for (int k = 0; k < F; ++k) dx[k] = 0.f;
+            const float* ps = p.Ps + ((size_t)t.g * tp.S + er.src) * H;
+            const float* pt = p.Pt + ((size_t)t.g * tp.T + er.tgt) * H;
+            float* dho = p.dh_rows ? p.dh_rows + ((size_t)t.g * tp.E + t.q0 + threadIdx.x) * H : nullptr;
+            edge_bwd_half<F, 0>(p, ps, pt, x, dz, dx, A1 + threadIdx.x * LDH, DH + threadIdx.x * LDH, dho);
+            edge_bwd_half<F, 1>(p, ps, pt, x, dz, dx, A1 + threadIdx.x * LDH, DH + threadIdx.x * LDH, dho);
+            store_row<F>(p.g_x_e + row, dx);
+        }
+        __syncthreads();
+        accw1.accumulate(acc, DH, LDH, XE, F, t.ne);
+        accw2.accumulate(acc, DZ, LDF, A1, LDH, t.ne);
+        if (dz_part < 4)
+            for (int r = dz_part; r < t.ne; r += 4) dzs += DZ[r * LDF + dz_col];
+        tile_fibre_sums<H, LDH>(tp, t, DH, p.dPs + ((size_t)t.g * tp.S + t.fibre0) * H);
+        if (p.class_part) tile_class_sums<H, LDH>(tp, t, DH, p.class_part + (size_t)tile * tp.T * H);
+        __syncthreads();
+    }
+    float* out = p.wpartial + (size_t)blockIdx.x * p.pstride;
+    accw1.flush(acc, DH, out, F, 0);
+    accw2.flush(acc, DH, out + H * F, H, 0);
+    {   // db2 = sum dz: the four row parts of each column, fixed order
+        float* red = DH;
+        if (dz_part < 4) red[threadIdx.x] = dzs;
+        __syncthreads();
+        if (threadIdx.x < F) out[2 * H * F + threadIdx.x] = (red[threadIdx.x] + red[F + threadIdx.x]) + (red[2 * F + threadIdx.x] + red[3 * F + threadIdx.x]);
     }
 }
 
