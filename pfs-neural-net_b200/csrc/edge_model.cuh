@@ -93,44 +93,60 @@ struct EdgeBnStatParams {
     float* partial;      // [G*ntiles][2F]
 };
 
+// A CTA owns a contiguous range of tiles; the rows' contributions are summed per thread over a whole graph segment
+// of that range and reduced over the CTA ONCE per segment (not once per tile: the 2F warp-shuffle trees per tile
+// made this streaming kernel instruction-bound at half the HBM rate).  The segment's sums go to the slot of its
+// first tile, the other tiles of the segment get zeros, so the per-graph consumer (k_tile_partial_sums) is unchanged.
 template <int F>
 __global__ void __launch_bounds__(kThreads) k_edge_bn_bwd_stats(const EdgeBnStatParams p) {
     __shared__ float red[kWarps * 2 * F];
     const Topo& tp = p.tp;
     const int total = tp.ntiles * tp.G;
+    const int t_begin = chunk_begin(blockIdx.x, gridDim.x, total), t_end = chunk_begin(blockIdx.x + 1, gridDim.x, total);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        const Tile t = get_tile(tp, tile);
-        const bool active = threadIdx.x < t.ne;
-        float g[F], xh[F];
+    float sg[F], sx[F];
 #pragma unroll
-        for (int j = 0; j < F; ++j) g[j] = xh[j] = 0.f;
-        if (active) {
+    for (int j = 0; j < F; ++j) sg[j] = sx[j] = 0.f;
+    int seg_first = t_begin;
+    for (int tile = t_begin; tile < t_end; ++tile) {
+        const Tile t = get_tile(tp, tile);
+        if (threadIdx.x < t.ne) {
             const EdgeRef er = get_edge(tp, t, threadIdx.x);
             const size_t row = ((size_t)t.g * tp.E + er.e) * F;
+            float g[F], xh[F];
             load_row<F>(p.gout + row, g);
             load_row<F>(p.xe2 + row, xh);
             const float* c = p.coef + (size_t)t.g * 6 * F;
 #pragma unroll
-            for (int j = 0; j < F; ++j) xh[j] = (xh[j] - c[4 * F + j]) * c[3 * F + j];
-        }
-#pragma unroll
-        for (int j = 0; j < F; ++j) {
-            const float a = warp_sum(g[j]);
-            const float b = warp_sum(g[j] * xh[j]);
-            if (lane == 0) {
-                red[w * 2 * F + j] = a;
-                red[w * 2 * F + F + j] = b;
+            for (int j = 0; j < F; ++j) {
+                const float v = (xh[j] - __ldg(c + 4 * F + j)) * __ldg(c + 3 * F + j);
+                sg[j] += g[j];
+                sx[j] = fmaf(g[j], v, sx[j]);
             }
         }
-        __syncthreads();
-        if (threadIdx.x < 2 * F) {
-            float s = 0.f;
+        const bool last = (tile + 1 == t_end) || ((tile + 1) / tp.ntiles != t.g);
+        if (tile != seg_first && threadIdx.x < 2 * F) p.partial[(size_t)tile * 2 * F + threadIdx.x] = 0.f;
+        if (last) {
 #pragma unroll
-            for (int i = 0; i < kWarps; ++i) s += red[i * 2 * F + threadIdx.x];
-            p.partial[(size_t)tile * 2 * F + threadIdx.x] = s;
+            for (int j = 0; j < F; ++j) {
+                const float a = warp_sum(sg[j]);
+                const float b = warp_sum(sx[j]);
+                if (lane == 0) {
+                    red[w * 2 * F + j] = a;
+                    red[w * 2 * F + F + j] = b;
+                }
+                sg[j] = sx[j] = 0.f;
+            }
+            __syncthreads();
+            if (threadIdx.x < 2 * F) {
+                float s = 0.f;
+#pragma unroll
+                for (int i = 0; i < kWarps; ++i) s += red[i * 2 * F + threadIdx.x];
+                p.partial[(size_t)seg_first * 2 * F + threadIdx.x] = s;
+            }
+            __syncthreads();
+            seg_first = tile + 1;
         }
-        __syncthreads();
     }
 }
 
