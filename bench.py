@@ -39,7 +39,7 @@ UNIT = "edges/s"
 # algorithmic bytes each kernel must move, in units of F*4 bytes (one fp32 feature row):
 # per edge (E) and per fibre (S); DESIGN.md section 6 derives them from SURVEY.md section 8(d).
 KERNEL_ROWS = {
-    "k_edge_fwd": (2, 0), "k_edge_bwd": (3, 0), "k_edge_bn_bwd_stats": (2, 0), "k_affine_rows": (2, 0),
+    "k_edge_fwd": (2, 0), "k_edge_bwd": (3, 0), "k_edge_bwd2": (3, 0), "k_edge_bn_bwd_stats": (2, 0), "k_affine_rows": (2, 0),
     "k_source_edge_fwd": (1, 10), "k_source_edge_bwd": (2, 18), "k_target_edge_fwd": (1, 2),
     "k_target_edge_bwd": (2, 2), "k_source_node_fwd": (0, 22), "k_source_node_bwd": (0, 32),
     "k_source_node_fwd_mma": (0, 22), "k_source_node_bwd_mma": (0, 32),
@@ -47,7 +47,7 @@ KERNEL_ROWS = {
 # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` captures of
 # the default C3 workload (profiles/r01_ncu_full_c3_top7.txt, r01_ncu_full_fma_path.txt); reported as `roofline.traffic`
 # for that workload only
-KERNEL_TRAFFIC_C3 = {"k_edge_bwd": 1404.0e6, "k_source_edge_bwd": 907.8e6, "k_source_node_bwd": 766.2e6,
+KERNEL_TRAFFIC_C3 = {"k_edge_bwd": 1404.0e6, "k_edge_bwd2": 1405.4e6, "k_source_edge_bwd": 907.8e6, "k_source_node_bwd": 766.2e6,
                      "k_source_node_bwd_mma": 766.5e6, "k_source_node_fwd_mma": 497.7e6, "k_edge_fwd": 655.6e6,
                      "k_source_edge_fwd": 502.8e6, "k_target_edge_bwd": 644.9e6}
 # executed multiply-accumulates per edge / per fibre, forward + backward, in units of F^2

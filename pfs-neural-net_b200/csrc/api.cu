@@ -533,7 +533,11 @@ int edge_bwd_impl(const pfs_edge_args& a, const Topo& tp) {
     EdgeBwdParams p{tp, a.x_e, a.x_e_out, a.g_out, Ps, Pt, coef, a.g_x_e, dPs,
                     dense ? stage : nullptr, dense ? nullptr : stage, wpart, pstride, max_fib, sc ? 1 : 0, nbuf};
     kern<<<grid, kThreads, smem_bwd, st>>>(p);
-    PFS_LAUNCH_CHECK("k_edge_bwd");
+    if (lean) {
+        PFS_LAUNCH_CHECK("k_edge_bwd2");
+    } else {
+        PFS_LAUNCH_CHECK("k_edge_bwd");
+    }
     {
         Reducer rd;
         rd.add(0, H * F, F, a.g_w1, H, 2 * F);

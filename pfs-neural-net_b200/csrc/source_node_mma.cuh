@@ -39,6 +39,35 @@ struct SourceNodeMma {
                                  SourceNodeConst<F>::fits;
 };
 
+// epilogue of columns [C0, C1) of the first-layer accumulator of one fibre (TMEM lane): bias, LeakyReLU, hidden
+// activation into the staging row, and this column range's share of the second layer y += a_j * W4[:, j]
+template <int F, int C0, int C1>
+__device__ __forceinline__ void node_fwd_epilogue_cols(uint32_t taddr, const float* b3e, float* a3row, float (&y)[F]) {
+    using CW = SourceNodeConst<F>;
+    constexpr int J = 10 * F;
+#pragma unroll
+    for (int c0 = C0; c0 < C1; c0 += 16) {
+        if (c0 >= J) break;
+        float v[16];
+        tmem_ld16(taddr + c0, v);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int j = c0 + q;
+            if (j < J) {
+                const float a = lrelu(v[q] + b3e[j]);
+                a3row[j] = a;
+                const float2 aa = make_float2(a, a);
+#pragma unroll
+                for (int f = 0; f < F; f += 2) {
+                    const float2 e = __ffma2_rn(make_float2(c_w[CW::kW4t + j * F + f], c_w[CW::kW4t + j * F + f + 1]), aa,
+                                                make_float2(y[f], y[f + 1]));
+                    y[f] = e.x; y[f + 1] = e.y;
+                }
+            }
+        }
+    }
+}
+
 template <int F>
 __global__ void __launch_bounds__(kNodeThreadsC) k_source_node_fwd_mma(const SourceNodeFwdParams p) {
     using MM = SourceNodeMma<F>;
@@ -78,10 +107,6 @@ __global__ void __launch_bounds__(kNodeThreadsC) k_source_node_fwd_mma(const Sou
         const int o = (kc * MM::LBO_B + (j >> 3) * 128 + (j & 7) * 16) >> 2;
         *reinterpret_cast<float4*>(Bhi + o) = make_float4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<float4*>(Blo + o) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-    }
-    for (int i = threadIdx.x; i < J * F; i += blockDim.x) {
-        const int j = i / F, f = i - j * F;
-        W4s[i] = __ldg(p.w4 + (size_t)f * J + j);
     }
     fence_proxy_async();
     tc_fence_before();
@@ -208,26 +233,14 @@ __global__ void __launch_bounds__(kNodeThreadsC) k_source_node_fwd_mma(const Sou
             const int quarter = warp & 3, half = warp >> 2;
             const int r = quarter * 32 + lane;
             constexpr int NH = (NP / 16 + 1) / 2 * 16;       // columns of the first half (multiple of 16)
-            const int c_begin = half ? NH : 0, c_end = half ? NP : NH;
             float y[F];
 #pragma unroll
             for (int f = 0; f < F; ++f) y[f] = half ? 0.f : c_w[CW::kB4 + f];
-#pragma unroll 1
-            for (int c0 = c_begin; c0 < c_end; c0 += 16) {
-                float v[16];
-                tmem_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + c0, v);
-#pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                    const int j = c0 + q;
-                    if (j < J) {
-                        const float a = lrelu(v[q] + b3e[j]);
-                        A3[r * LDA + j] = a;
-                        const float* w4 = W4s + j * F;
-#pragma unroll
-                        for (int f = 0; f < F; ++f) y[f] = fmaf(a, w4[f], y[f]);
-                    }
-                }
-            }
+            // one fully unrolled copy of the column loop per half: the column index is then a compile-time
+            // constant and the second-layer weights are constant-bank immediates of the FFMA2s (no shared-memory
+            // weight reads)
+            if (half == 0) node_fwd_epilogue_cols<F, 0, NH>(tmem + ((uint32_t)(quarter * 32) << 16), b3e, A3 + r * LDA, y);
+            else node_fwd_epilogue_cols<F, NH, NP>(tmem + ((uint32_t)(quarter * 32) << 16), b3e, A3 + r * LDA, y);
 #pragma unroll
             for (int f = 0; f < F; ++f) YS[(half * 128 + r) * F + f] = y[f];
         }
