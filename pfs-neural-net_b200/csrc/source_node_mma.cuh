@@ -254,9 +254,11 @@ __global__ void __launch_bounds__(kNodeThreadsC) k_source_node_fwd_mma(const Sou
         tc_fence_before();
         __syncthreads();
         // hidden activations to global (coalesced), BatchNorm tile statistics
-        for (int i = threadIdx.x; i < rows * J; i += blockDim.x) {
-            const int r = i / J, j = i - r * J;
-            p.hidden[(row0 + r) * J + j] = A3[r * LDA + j];
+        static_assert(J % 4 == 0, "16-byte stores of the hidden rows");
+        for (int i = threadIdx.x; i < rows * (J / 4); i += blockDim.x) {
+            const int r = i / (J / 4), c = (i - r * (J / 4)) * 4;
+            const float* a = A3 + r * LDA + c;
+            *reinterpret_cast<float4*>(p.hidden + (row0 + r) * J + c) = make_float4(a[0], a[1], a[2], a[3]);
         }
         __syncthreads();
         if (p.bn_partial) {
