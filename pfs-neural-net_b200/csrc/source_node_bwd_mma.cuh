@@ -145,27 +145,36 @@ __global__ void __launch_bounds__(kNodeThreadsC) k_source_node_bwd_mma(const Sou
     // stays in registers for its backward half after the MMAs.
     constexpr int NI = (R * M + kNodeThreadsC - 1) / kNodeThreadsC;      // moment items per thread
     constexpr int NX = (R * F + kNodeThreadsC - 1) / kNodeThreadsC;      // x_s / dy items per thread
-    int it_rr[NI], it_j[NI];
+    // every offset an item needs (operand slot, global rows relative to the tile, dhcat slot) is computed once here
+    auto hslot = [](int rr, int k) { return ((rr >> 2) * MM::CS_H + k * 16 + (rr & 3) * 4) >> 2; };
+    int it_rr[NI], it_po[NI], it_go[NI], it_co[NI], it_do[NI];
 #pragma unroll
     for (int n = 0; n < NI; ++n) {
         const int i = threadIdx.x + n * kNodeThreadsC;
         const int q = i / (4 * M), rem = i - q * (4 * M);
-        it_rr[n] = i < R * M ? 4 * q + (rem & 3) : R;                    // R = no item
-        it_j[n] = rem >> 2;
+        const int rr = i < R * M ? 4 * q + (rem & 3) : R, j = rem >> 2;   // R = no item
+        it_rr[n] = rr;
+        it_po[n] = hslot(rr < R ? rr : 0, F + j);        // operand slot of the mean; std / skew / kurt follow at + s * 4M floats
+        it_go[n] = rr * 5 * M + j;                       // moments, relative to the tile's first row
+        it_co[n] = rr * 4 * M + j;                       // coefA, relative to the tile's first row
+        it_do[n] = rr * LDC + F + j;                     // dhcat staging
     }
-    int ix_rr[NX], ix_c[NX], iy_rr[NX], iy_f[NX];
+    int ix_rr[NX], ix_po[NX], ix_go[NX], iy_rr[NX], iy_f[NX], iy_so[NX], iy_go[NX];
 #pragma unroll
     for (int n = 0; n < NX; ++n) {
         const int i = threadIdx.x + n * kNodeThreadsC;
         const int q = i / (4 * F), rem = i - q * (4 * F);
-        ix_rr[n] = i < R * F ? 4 * q + (rem & 3) : R;
-        ix_c[n] = rem >> 2;
+        const int rr = i < R * F ? 4 * q + (rem & 3) : R, c = rem >> 2;
+        ix_rr[n] = rr;
+        ix_po[n] = hslot(rr < R ? rr : 0, c);
+        ix_go[n] = rr * F + c;
         iy_rr[n] = i < R * F ? i / F : R;
         iy_f[n] = i % F;
+        iy_so[n] = iy_rr[n] * LDY + iy_f[n];
+        iy_go[n] = iy_rr[n] * F + iy_f[n];
     }
-    auto put = [&](int rr, int k, float v) {
+    auto put = [&](int o, float v) {
         const float hi = to_tf32(v);
-        const int o = ((rr >> 2) * MM::CS_H + k * 16 + (rr & 3) * 4) >> 2;
         Hhi[o] = hi;
         Hlo[o] = to_tf32(v - hi);
     };
@@ -178,20 +187,21 @@ __global__ void __launch_bounds__(kNodeThreadsC) k_source_node_bwd_mma(const Sou
         const int g2 = tile2 / p.ntiles, f2 = (tile2 - g2 * p.ntiles) * R;
         const int rows2 = min(R, p.S - f2);
         const size_t row2 = (size_t)g2 * p.S + f2;
+        const float* mo2 = p.moments + row2 * 5 * M;
+        const float *xs2 = p.x_s + row2 * F, *go2 = p.gout + row2 * F, *yp2 = p.y_pre + row2 * F;
 #pragma unroll
         for (int n = 0; n < NI; ++n) {
             if (it_rr[n] < rows2) {
-                const float* mo = p.moments + (row2 + it_rr[n]) * 5 * M + it_j[n];
 #pragma unroll
-                for (int q = 0; q < 5; ++q) pf_mo[n][q] = __ldg(mo + q * M);
+                for (int q = 0; q < 5; ++q) pf_mo[n][q] = __ldg(mo2 + it_go[n] + q * M);
             }
         }
 #pragma unroll
         for (int n = 0; n < NX; ++n) {
-            if (ix_rr[n] < rows2) pf_xs[n] = __ldg(p.x_s + (row2 + ix_rr[n]) * F + ix_c[n]);
+            if (ix_rr[n] < rows2) pf_xs[n] = __ldg(xs2 + ix_go[n]);
             if (iy_rr[n] < rows2) {
-                pf_g[n] = __ldg(p.gout + (row2 + iy_rr[n]) * F + iy_f[n]);
-                pf_y[n] = p.mode == 1 ? __ldg(p.y_pre + (row2 + iy_rr[n]) * F + iy_f[n]) : 0.f;
+                pf_g[n] = __ldg(go2 + iy_go[n]);
+                pf_y[n] = p.mode == 1 ? __ldg(yp2 + iy_go[n]) : 0.f;
             }
         }
     };
@@ -215,7 +225,7 @@ __global__ void __launch_bounds__(kNodeThreadsC) k_source_node_bwd_mma(const Sou
         unsigned m_fin[NI];      // bit 0..3: mean, var, skew, kurt were finite (nan_to_num passes their gradient)
 #pragma unroll
         for (int n = 0; n < NI; ++n) {
-            const int rr = it_rr[n], j = it_j[n];
+            const int rr = it_rr[n];
             float mean_o = 0.f, std_o = 0.f, skew_o = 0.f, kurt_o = 0.f;
             m_fin[n] = 0u;
             m_mean[n] = m_vr[n] = m_c2[n] = m_c3[n] = m_c4[n] = m_i1[n] = m_is1[n] = 0.f;
@@ -245,16 +255,16 @@ __global__ void __launch_bounds__(kNodeThreadsC) k_source_node_bwd_mma(const Sou
                 m_is1[n] = is1;
             }
             if (rr < R) {
-                put(rr, F + j, mean_o);
-                put(rr, F + M + j, std_o);
-                put(rr, F + 2 * M + j, skew_o);
-                put(rr, F + 3 * M + j, kurt_o);
+                put(it_po[n], mean_o);
+                put(it_po[n] + 4 * M, std_o);
+                put(it_po[n] + 8 * M, skew_o);
+                put(it_po[n] + 12 * M, kurt_o);
             }
         }
 #pragma unroll
         for (int n = 0; n < NX; ++n) {
             const int rr = ix_rr[n];
-            if (rr < R) put(rr, ix_c[n], rr < rows ? pf_xs[n] : 0.f);
+            if (rr < R) put(ix_po[n], rr < rows ? pf_xs[n] : 0.f);
         }
         // ---- dy = BatchNorm backward of the upstream gradient ---------------------------------------
         {
@@ -278,7 +288,7 @@ __global__ void __launch_bounds__(kNodeThreadsC) k_source_node_bwd_mma(const Sou
                         dy = gv;
                     }
                 }
-                DY[rr * LDY + f] = dy;
+                DY[iy_so[n]] = dy;
             }
         }
         prefetch(tile + gridDim.x);      // next tile's scalar inputs: in flight under the rest of this tile
@@ -394,9 +404,9 @@ __global__ void __launch_bounds__(kNodeThreadsC) k_source_node_bwd_mma(const Sou
         }
 #pragma unroll
         for (int n = 0; n < NI; ++n) {
-            const int rr = it_rr[n], j = it_j[n];
+            const int rr = it_rr[n];
             if (rr >= rows) continue;
-            const float* dh = A3 + rr * LDC + F + j;
+            const float* dh = A3 + it_do[n];
             const unsigned fin = m_fin[n];
             // torch: nan_to_num backward passes the gradient only where the value was finite
             const float d_mean = (fin & 1u) ? dh[0] : 0.f, d_std = (fin & 2u) ? dh[M] : 0.f;
@@ -407,7 +417,7 @@ __global__ void __launch_bounds__(kNodeThreadsC) k_source_node_bwd_mma(const Sou
             const float d_var = 0.5f * (d_std * m_is1[n] - (3.f * c3 * i4 * d_skew + 4.f * c4 * i4 * i1 * d_kurt) * i1);
             const float d_vr = d_var * (m_vr[n] > 0.f ? 1.f : kSlopeVar);
             const float d_mu = d_mean - 2.f * m_mean[n] * d_vr - 3.f * m_c2[n] * d_c3 - 4.f * c3 * d_c4;
-            float* o = p.coefA + (row0 + rr) * 4 * M + j;
+            float* o = p.coefA + row0 * 4 * M + it_co[n];
             o[0] = d_mu;
             o[M] = 2.f * d_vr;
             o[2 * M] = 3.f * d_c3;
