@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PFS_ABI_VERSION 1
+#define PFS_ABI_VERSION 2
 
 enum {
     PFS_OK = 0,
@@ -160,6 +160,7 @@ typedef struct pfs_source_args {
     float* y_pre;                                /* [G,S,F] saved: node MLP output before the norm */
     float* bn_save;                              /* [G,4,F] */
     const float* g_out;                          /* dL/dx_s_out [G,S,F] */
+    const float* g_x_e_add;                      /* optional [G,E,F]: g_x_e = (this module's dL/dx_e) + g_x_e_add, fused into the store */
     float *g_x_s, *g_x_t, *g_x_e, *g_u;
     float *g_w1, *g_b1, *g_w2, *g_b2, *g_w3, *g_b3, *g_w4, *g_b4, *g_gamma, *g_beta;
     void* workspace; size_t workspace_bytes;
@@ -187,6 +188,7 @@ typedef struct pfs_target_args {
     float* y_pre;                                /* [G,T,F] saved */
     float* bn_save;                              /* [G,4,F] */
     const float* g_out;                          /* dL/dx_t_out [G,T,F] */
+    const float* g_x_e_add;                      /* optional [G,E,F]: g_x_e = (this module's dL/dx_e) + g_x_e_add, fused into the store */
     float *g_x_s, *g_x_t, *g_x_e, *g_u;
     float *g_w1, *g_b1, *g_w2, *g_b2, *g_w3, *g_b3, *g_w4, *g_b4, *g_gamma, *g_beta;
     void* workspace; size_t workspace_bytes;

@@ -731,7 +731,7 @@ int source_bwd_impl(const pfs_source_args& a, const Topo& tp) {
     PFS_TRY((node_linear<F, M>(a.x_t, tp.T, tp.G, a.w1, M, 0, a.b1, nullptr, Qt, st)));
     {
         const bool dense = tp.layout == PFS_LAYOUT_DENSE;
-        SourceEdgeBwdParams p{tp, a.x_e, Qt, a.w1, a.w2, a.b2, a.moments, coefA, a.g_x_e,
+        SourceEdgeBwdParams p{tp, a.x_e, Qt, a.w1, a.w2, a.b2, a.moments, coefA, a.g_x_e, a.g_x_e_add,
                               dense ? stage : nullptr, dense ? nullptr : stage, wpe, pstride_e};
         PFS_TRY(upload_msg_weights<F>(a.w1, a.w2, a.b2, wstage, st));
         ke<<<gride, kThreads, SME::bytes, st>>>(p);
@@ -857,7 +857,7 @@ int target_bwd_impl(const pfs_target_args& a, const Topo& tp) {
     }
     PFS_TRY((node_linear<F, M>(a.x_s, tp.S, tp.G, a.w1, M, 0, a.b1, nullptr, Rs, st)));
     {
-        TargetEdgeBwdParams p{tp, a.x_e, Rs, a.w1, dasum, a.g_x_e, dRs, wpe, pstride_e};
+        TargetEdgeBwdParams p{tp, a.x_e, Rs, a.w1, dasum, a.g_x_e, a.g_x_e_add, dRs, wpe, pstride_e};
         PFS_TRY(upload_msg_weights<F>(a.w1, nullptr, nullptr, wstage, st));
         ke<<<gride, kThreads, SM::bytes, st>>>(p);
         PFS_LAUNCH_CHECK("k_target_edge_bwd");

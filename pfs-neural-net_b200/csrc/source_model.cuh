@@ -460,6 +460,7 @@ struct SourceEdgeBwdParams {
     const float *w1, *w2, *b2;
     const float *moments, *coefA;   // [G,S,5,2F], [G,S,4,2F]
     float* g_x_e;                   // [G,E,F]
+    const float* g_add;             // optional [G,E,F] added to g_x_e on store
     float* class_part;              // dense: [G,ntiles,T,2F] class sums of dhs
     float* dhs_rows;                // general: [G,E(q),2F]
     float* wpartial;                // [ncta][pstride]: dW1_e [2F*F], dW2 [2F*2F], db2 [2F]
@@ -558,6 +559,7 @@ __global__ void __launch_bounds__(kThreads, (F <= 10 ? 2 : 1)) k_source_edge_bwd
 #pragma unroll
             for (int k = 0; k < F; ++k) dx[k] = 0.f;
             dense_acc_c<M, F, CW::kW1o>(da, dx);
+            if (p.g_add) add_row<F>(p.g_add + row, dx);
             store_row<F>(p.g_x_e + row, dx);
             if (p.dhs_rows) store_row<M>(p.dhs_rows + ((size_t)t.g * tp.E + t.q0 + threadIdx.x) * M, da);
         }

@@ -329,6 +329,7 @@ struct TargetEdgeBwdParams {
     const float *xe2, *Rs, *w1;
     const float* dasum;     // [G,T,2F]
     float* g_x_e;           // [G,E,F]
+    const float* g_add;     // optional [G,E,F] added to g_x_e on store (gradient of x_e from its other consumers)
     float* dRs;             // [G,S,2F]
     float* wpartial;        // [ncta][pstride]: dW1_e [2F*F]
     int pstride;
@@ -376,6 +377,7 @@ __global__ void __launch_bounds__(kThreads) k_target_edge_bwd(const TargetEdgeBw
 #pragma unroll
             for (int k = 0; k < F; ++k) dx[k] = 0.f;
             dense_acc_c<M, F, CW::kW1o>(d, dx);
+            if (p.g_add) add_row<F>(p.g_add + row, dx);
             store_row<F>(p.g_x_e + row, dx);
         }
         __syncthreads();

@@ -59,6 +59,80 @@ def _check_shapes(topo, x_s, x_t, x_e, u):
     return G, F
 
 
+class XeGradBus:
+    """Lets the backward kernels of a Block add up the three gradients of the updated edge embedding x_e'
+    (it feeds SModel, TModel and the Block output) instead of autograd: 2 x 3 passes over [G, E, F] per step.
+
+    Opportunistic and order-independent: whoever runs later fuses what is already there into its own store
+    (`g_x_e_add` of pfs_target_bwd / pfs_source_bwd) and marks it used; `XeFanout.backward` adds whatever was not
+    fused, so every combination of used / unused branches gives the same sum.  In a training step autograd runs
+    the output tap first, then TModel, then SModel, and nothing is left for it to add."""
+    __slots__ = ("g_o", "g_t", "o_used", "t_used")
+
+    def __init__(self):
+        self.clear()
+
+    def clear(self):
+        self.g_o = self.g_t = None
+        self.o_used = self.t_used = False
+
+    def addend_for_target(self, like):
+        if (self.g_o is not None and not self.o_used and self.g_o.numel() == like.numel()
+                and self.g_o.dtype == torch.float32 and self.g_o.device == like.device):
+            self.o_used = True
+            return self.g_o.contiguous()
+        return None
+
+    def addend_for_source(self, like):
+        if self.g_t is not None and not self.t_used and self.g_t.numel() == like.numel():
+            self.t_used = True
+            return self.g_t
+        return self.addend_for_target(like)
+
+
+class XeFanout(torch.autograd.Function):
+    """x_e' -> (for SModel, for TModel, for the output); backward adds the parts the kernels have not fused."""
+
+    @staticmethod
+    def forward(ctx, x, bus):
+        ctx.bus = bus
+        ctx.set_materialize_grads(False)
+        return x.view_as(x), x.view_as(x), x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g_s, g_t, g_o):
+        bus = ctx.bus
+        parts = []
+        if g_s is not None:
+            parts.append(g_s)
+        if g_t is not None and not bus.t_used:
+            parts.append(g_t)
+        if g_o is not None and not bus.o_used:
+            parts.append(g_o)
+        bus.clear()
+        if not parts:
+            return None, None
+        total = parts[0]
+        for q in parts[1:]:
+            total = total + q
+        return total, None
+
+
+class XeOutTap(torch.autograd.Function):
+    """Identity on the Block's x_e' output: its backward runs before the modules' and shows them the upstream
+    gradient."""
+
+    @staticmethod
+    def forward(ctx, x, bus):
+        ctx.bus = bus
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        ctx.bus.g_o = g
+        return g, None
+
+
 class EdgeFunction(torch.autograd.Function):
     """EdgeModel (reference src/gnn.py:73-101) -> pfs_edge_fwd / pfs_edge_bwd."""
 
@@ -115,7 +189,7 @@ class SourceFunction(torch.autograd.Function):
     """SModel (reference src/gnn.py:104-154) -> pfs_source_fwd / pfs_source_bwd."""
 
     @staticmethod
-    def forward(ctx, topo, training, normed, x_s, x_t, x_e, u, w1, b1, w2, b2, w3, b3, w4, b4, gamma, beta, rm, rv, nbt):
+    def forward(ctx, topo, training, normed, x_s, x_t, x_e, u, w1, b1, w2, b2, w3, b3, w4, b4, gamma, beta, rm, rv, nbt, bus=None):
         dev = _dev_check(x_s, x_t, x_e, u, w1, b1, w2, b2, w3, b3, w4, b4, gamma, beta, rm, rv)
         (x_s, x_t, x_e, u, w1, b1, w2, b2, w3, b3, w4, b4, gamma, beta) = (
             _c(t) for t in (x_s, x_t, x_e, u, w1, b1, w2, b2, w3, b3, w4, b4, gamma, beta))
@@ -137,6 +211,7 @@ class SourceFunction(torch.autograd.Function):
             a.stream = _stream(dev)
             _abi.check(lib.pfs_source_fwd(ct.byref(a)), "pfs_source_fwd")
         ctx.topo, ctx.training, ctx.normed = topo, training, normed
+        ctx.bus = bus
         ctx.buffers = (rm, rv)
         ctx.save_for_backward(x_s, x_t, x_e, u, w1, b1, w2, b2, w3, b3, w4, b4, gamma, beta, moments, hidden, y_pre,
                               bn_save)
@@ -161,7 +236,8 @@ class SourceFunction(torch.autograd.Function):
         named = dict(x_s=x_s, x_t=x_t, x_e=x_e, u=u, w1=w1, b1=b1, w2=w2, b2=b2, w3=w3, b3=b3, w4=w4, b4=b4,
                      gamma=gamma, beta=beta, running_mean=rm, running_var=rv, moments=moments, hidden=hidden,
                      y_pre=y_pre, bn_save=bn_save, g_out=g)
-        named.update(gr)
+        add = ctx.bus.addend_for_source(x_e) if ctx.bus is not None else None
+        named.update(gr, g_x_e_add=add)
         a = _abi.SourceArgs()
         ws = _fill_common(a, topo, G, F, named)
         a.training, a.normed, a.eps, a.momentum = int(ctx.training), int(ctx.normed), BN_EPS, BN_MOMENTUM
@@ -171,14 +247,14 @@ class SourceFunction(torch.autograd.Function):
         del ws
         return (None, None, None, gr["g_x_s"], gr["g_x_t"], gr["g_x_e"], gr["g_u"], gr["g_w1"], gr["g_b1"],
                 gr["g_w2"], gr["g_b2"], gr["g_w3"], gr["g_b3"], gr["g_w4"], gr["g_b4"], gr["g_gamma"], gr["g_beta"],
-                None, None, None)
+                None, None, None, None)
 
 
 class TargetFunction(torch.autograd.Function):
     """TModel (reference src/gnn.py:157-192) -> pfs_target_fwd / pfs_target_bwd."""
 
     @staticmethod
-    def forward(ctx, topo, training, normed, x_s, x_t, x_e, u, w1, b1, w2, b2, w3, b3, w4, b4, gamma, beta, rm, rv, nbt):
+    def forward(ctx, topo, training, normed, x_s, x_t, x_e, u, w1, b1, w2, b2, w3, b3, w4, b4, gamma, beta, rm, rv, nbt, bus=None):
         dev = _dev_check(x_s, x_t, x_e, u, w1, b1, w2, b2, w3, b3, w4, b4, gamma, beta, rm, rv)
         (x_s, x_t, x_e, u, w1, b1, w2, b2, w3, b3, w4, b4, gamma, beta) = (
             _c(t) for t in (x_s, x_t, x_e, u, w1, b1, w2, b2, w3, b3, w4, b4, gamma, beta))
@@ -199,6 +275,7 @@ class TargetFunction(torch.autograd.Function):
             a.stream = _stream(dev)
             _abi.check(lib.pfs_target_fwd(ct.byref(a)), "pfs_target_fwd")
         ctx.topo, ctx.training, ctx.normed = topo, training, normed
+        ctx.bus = bus
         ctx.buffers = (rm, rv)
         ctx.save_for_backward(x_s, x_t, x_e, u, w1, b1, w2, b2, w3, b3, w4, b4, gamma, beta, act_sum, y_pre, bn_save)
         del ws
@@ -221,7 +298,8 @@ class TargetFunction(torch.autograd.Function):
         named = dict(x_s=x_s, x_t=x_t, x_e=x_e, u=u, w1=w1, b1=b1, w2=w2, b2=b2, w3=w3, b3=b3, w4=w4, b4=b4,
                      gamma=gamma, beta=beta, running_mean=rm, running_var=rv, act_sum=act_sum, y_pre=y_pre,
                      bn_save=bn_save, g_out=g)
-        named.update(gr)
+        add = ctx.bus.addend_for_target(x_e) if ctx.bus is not None else None
+        named.update(gr, g_x_e_add=add)
         a = _abi.TargetArgs()
         ws = _fill_common(a, topo, G, F, named)
         a.training, a.normed, a.eps, a.momentum = int(ctx.training), int(ctx.normed), BN_EPS, BN_MOMENTUM
@@ -229,9 +307,11 @@ class TargetFunction(torch.autograd.Function):
             a.stream = _stream(dev)
             _abi.check(lib.pfs_target_bwd(ct.byref(a)), "pfs_target_bwd")
         del ws
+        if ctx.bus is not None:
+            ctx.bus.g_t = gr["g_x_e"]
         return (None, None, None, gr["g_x_s"], gr["g_x_t"], gr["g_x_e"], gr["g_u"], gr["g_w1"], gr["g_b1"],
                 gr["g_w2"], gr["g_b2"], gr["g_w3"], gr["g_b3"], gr["g_w4"], gr["g_b4"], gr["g_gamma"], gr["g_beta"],
-                None, None, None)
+                None, None, None, None)
 
 
 _global_ws = {}

@@ -190,7 +190,7 @@ class SModel(torch.nn.Module):
         m1, m2 = self.node_mlp_1, self.node_mlp_2
         out = pf.SourceFunction.apply(topo, self.training, normed, x_s, x_t, edge_attr, u, m1[0].weight, m1[0].bias,
                                       m1[2].weight, m1[2].bias, m2[0].weight, m2[0].bias, m2[2].weight, m2[2].bias,
-                                      gamma, beta, rm, rv, nbt)
+                                      gamma, beta, rm, rv, nbt, getattr(self, "_xe_bus", None))
         return out[0] if single else out
 
 
@@ -219,7 +219,7 @@ class TModel(torch.nn.Module):
         m1, m2 = self.node_mlp_1, self.node_mlp_2
         out = pf.TargetFunction.apply(topo, self.training, normed, x_s, x_t, edge_attr, u, m1[0].weight, m1[0].bias,
                                       m1[2].weight, m1[2].bias, m2[0].weight, m2[0].bias, m2[2].weight, m2[2].bias,
-                                      gamma, beta, rm, rv, nbt)
+                                      gamma, beta, rm, rv, nbt, getattr(self, "_xe_bus", None))
         return out[0] if single else out
 
 
@@ -271,12 +271,30 @@ class Block(torch.nn.Module):
         edge_index, x_s, x_t, x_e, x_u = args
         if hasattr(self, "edge_model"):
             x_e = self.edge_model(x_s, x_t, edge_index, x_e, x_u)
-        if hasattr(self, "s_model"):
-            x_s = self.s_model(x_s, x_t, edge_index, x_e, x_u)
-        if hasattr(self, "t_model"):
-            x_t = self.t_model(x_s, x_t, edge_index, x_e, x_u)
+        # fp32 path: the three gradients of x_e' (SModel, TModel, the output) are added up inside the backward
+        # kernels instead of by autograd (functional.XeGradBus); the values are the same sum
+        bus = None
+        x_e_s = x_e_t = x_e
+        if (torch.is_grad_enabled() and x_e.requires_grad and x_e.is_cuda and x_e.dtype == torch.float32
+                and hasattr(self, "s_model") and hasattr(self, "t_model")):
+            bus = pf.XeGradBus()
+            x_e_s, x_e_t, x_e = pf.XeFanout.apply(x_e, bus)
+        try:
+            if hasattr(self, "s_model"):
+                self.s_model._xe_bus = bus
+                x_s = self.s_model(x_s, x_t, edge_index, x_e_s, x_u)
+            if hasattr(self, "t_model"):
+                self.t_model._xe_bus = bus
+                x_t = self.t_model(x_s, x_t, edge_index, x_e_t, x_u)
+        finally:
+            if hasattr(self, "s_model"):
+                self.s_model._xe_bus = None
+            if hasattr(self, "t_model"):
+                self.t_model._xe_bus = None
         if hasattr(self, "global_model"):
             x_u = self.global_model(x_s, x_t, edge_index, x_e, x_u)
+        if bus is not None:
+            x_e = pf.XeOutTap.apply(x_e, bus)
         return edge_index, x_s, x_t, x_e, x_u
 
 
