@@ -804,6 +804,9 @@ struct OuterAccX {
     static constexpr int kAcc = TJ * TK;
     int grp, j0, k0;
     bool live;
+    // the FFMA2 operand pair (rows a, a+1 of column c) sits in two ADJACENT slots whatever the block shape, so two
+    // accumulations of different shapes can share the register array without repacking moves
+    static __device__ __forceinline__ constexpr int slot(int a, int c) { return ((a >> 1) * TK + c) * 2 + (a & 1); }
     __device__ __forceinline__ void init() {
         const int t = (int)threadIdx.x - T0;
         grp = t >= 0 ? t / NB : GROUPS;
@@ -820,9 +823,9 @@ struct OuterAccX {
 #pragma unroll
             for (int c = 0; c < TK; ++c) {
                 const float2 v = __ffma2_rn(make_float2(d[a], d[a + 1]), make_float2(x[c], x[c]),
-                                            make_float2(A[a * TK + c], A[(a + 1) * TK + c]));
-                A[a * TK + c] = v.x;
-                A[(a + 1) * TK + c] = v.y;
+                                            make_float2(A[slot(a, c)], A[slot(a + 1, c)]));
+                A[slot(a, c)] = v.x;
+                A[slot(a + 1, c)] = v.y;
             }
     }
     template <int NA>
@@ -854,7 +857,7 @@ struct OuterAccX {
 #pragma unroll
             for (int a = 0; a < TJ; ++a)
 #pragma unroll
-                for (int c = 0; c < TK; ++c) scratch[grp * (J * K) + (j0 + a) * K + k0 + c] = A[a * TK + c];
+                for (int c = 0; c < TK; ++c) scratch[grp * (J * K) + (j0 + a) * K + k0 + c] = A[slot(a, c)];
         }
         __syncthreads();
         for (int i = threadIdx.x; i < J * K; i += kThreads) {
