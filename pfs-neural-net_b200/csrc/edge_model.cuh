@@ -419,6 +419,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_edge_bwd2(const EdgeBwdParams p
     for (int tile = t_begin; tile < t_end; ++tile) {
         const Tile t = get_tile(tp, tile);
         const int b = stg.step(tp, tile, t_end, 0, esrc, nullptr, nullptr, tile_of);
+        if (threadIdx.x == 0 && tile + 1 < t_end && tp.layout == PFS_LAYOUT_DENSE) {   // next tile's slabs -> L2
+            const Tile tn = get_tile(tp, tile + 1);
+            const size_t off = ((size_t)tn.g * tp.E + tn.q0) * F, bytes = (size_t)tn.ne * F * sizeof(float);
+            bulk_prefetch_l2(p.x_e + off, bytes);
+            bulk_prefetch_l2(p.xe2 + off, bytes);
+            bulk_prefetch_l2(p.gout + off, bytes);
+        }
         __syncthreads();
         const float* XE = stg.edge(b, 0);
         if (threadIdx.x < t.ne) {

@@ -499,6 +499,15 @@ __global__ void __launch_bounds__(kThreads, (F <= 10 ? 2 : 1)) k_source_edge_bwd
     const int total = tp.ntiles * tp.G;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
         const Tile t = get_tile(tp, tile);
+        if (threadIdx.x == 0 && tile + (int)gridDim.x < total && tp.layout == PFS_LAYOUT_DENSE) {   // next tile -> L2
+            const Tile tn = get_tile(tp, tile + gridDim.x);
+            const size_t off = ((size_t)tn.g * tp.E + tn.q0) * F, bytes = (size_t)tn.ne * F * sizeof(float);
+            const size_t frow = (size_t)tn.g * tp.S + tn.fibre0;
+            bulk_prefetch_l2(p.xe2 + off, bytes);
+            if (p.g_add) bulk_prefetch_l2(p.g_add + off, bytes);
+            bulk_prefetch_l2(p.coefA + frow * 4 * M, (size_t)tn.nfib * 4 * M * sizeof(float));
+            bulk_prefetch_l2(p.moments + frow * 5 * M, (size_t)tn.nfib * 5 * M * sizeof(float));
+        }
         if (threadIdx.x < t.ne) {
             const EdgeRef er = get_edge(tp, t, threadIdx.x);
             const size_t row = ((size_t)t.g * tp.E + er.e) * F;

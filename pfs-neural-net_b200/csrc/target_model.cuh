@@ -361,6 +361,13 @@ __global__ void __launch_bounds__(kThreads) k_target_edge_bwd(const TargetEdgeBw
     const int total = tp.ntiles * tp.G;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
         const Tile t = get_tile(tp, tile);
+        if (threadIdx.x == 0 && tile + (int)gridDim.x < total && tp.layout == PFS_LAYOUT_DENSE) {   // next tile -> L2
+            const Tile tn = get_tile(tp, tile + gridDim.x);
+            const size_t off = ((size_t)tn.g * tp.E + tn.q0) * F, bytes = (size_t)tn.ne * F * sizeof(float);
+            bulk_prefetch_l2(p.xe2 + off, bytes);
+            if (p.g_add) bulk_prefetch_l2(p.g_add + off, bytes);
+            bulk_prefetch_l2(p.Rs + ((size_t)tn.g * tp.S + tn.fibre0) * M, (size_t)tn.nfib * M * sizeof(float));
+        }
         if (threadIdx.x < t.ne) {
             const EdgeRef er = get_edge(tp, t, threadIdx.x);
             const size_t row = ((size_t)t.g * tp.E + er.e) * F;
