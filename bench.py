@@ -47,7 +47,7 @@ KERNEL_ROWS = {
 # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` captures of
 # the default C3 workload (profiles/r01_ncu_full_c3_top7.txt, r01_ncu_full_fma_path.txt); reported as `roofline.traffic`
 # for that workload only
-KERNEL_TRAFFIC_C3 = {"k_edge_bwd": 1404.0e6, "k_edge_bwd2": 1405.4e6, "k_source_edge_bwd": 1209.7e6, "k_source_node_bwd": 766.2e6,
+KERNEL_TRAFFIC_C3 = {"k_edge_bwd": 1404.0e6, "k_edge_bwd2": 1405.4e6, "k_source_edge_bwd": 1341.0e6, "k_source_node_bwd": 766.2e6,
                      "k_source_node_bwd_mma": 766.5e6, "k_source_node_fwd_mma": 497.7e6, "k_edge_fwd": 655.6e6,
                      "k_source_edge_fwd": 502.8e6, "k_target_edge_bwd": 955.4e6}
 # executed multiply-accumulates per edge / per fibre, forward + backward, in units of F^2

@@ -27,9 +27,10 @@ def main(path):
         for w in WANT:
             if w in idx:
                 print("   %-66s %16s %s" % (w, r[idx[w]], units[idx[w]]))
-        rd = float(r[idx["dram__bytes_read.sum"]] or 0)
-        wr = float(r[idx["dram__bytes_write.sum"]] or 0)
-        print("   %-66s %16.3f %s (read+write)" % ("dram traffic", rd + wr, units[idx["dram__bytes_read.sum"]]))
+        mb = {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3, "Tbyte": 1e6}     # the two columns may differ in unit
+        rd = float(r[idx["dram__bytes_read.sum"]] or 0) * mb.get(units[idx["dram__bytes_read.sum"]], 1.0)
+        wr = float(r[idx["dram__bytes_write.sum"]] or 0) * mb.get(units[idx["dram__bytes_write.sum"]], 1.0)
+        print("   %-66s %16.3f %s (read+write)" % ("dram traffic", rd + wr, "Mbyte"))
         top = sorted(((float(r[idx[k]] or 0), k) for k in stall if r[idx[k]] not in ("", "n/a")), reverse=True)[:5]
         print("   top stalls (warps per issue): " + ", ".join(
             "%s %.2f" % (k.split("issue_stalled_")[1].replace("_per_issue_active.ratio", ""), v) for v, k in top))
