@@ -12,6 +12,13 @@
  *   - the caller allocates every output and the workspace (size from pfs_workspace_bytes);
  *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no hidden streams, no
  *     device synchronisation, no host allocation inside a call;
+ *   - ONE STREAM AND ONE HOST THREAD PER DEVICE AT A TIME: the module-level entry points stage their
+ *     small MLP weights in one per-device __constant__ bank (uploaded on `stream` ahead of the kernels
+ *     that read it) and the caller passes one workspace per topology, so calls on the same device
+ *     must be serialised on a single stream by a single host thread.  The library checks this
+ *     cheaply: a call on a different stream than the previous call on that device first makes the
+ *     new stream wait for everything enqueued so far (an event wait, no host sync), so switching
+ *     streams between steps is safe; truly concurrent use of two streams is not supported;
  *   - return value 0 = ok, negative = error; pfs_last_error() gives the message (thread local);
  *   - nothing throws across the ABI; there is no CPU fallback: without a CUDA device every
  *     compute entry point returns PFS_ERR_CUDA;
@@ -31,7 +38,7 @@
 extern "C" {
 #endif
 
-#define PFS_ABI_VERSION 2
+#define PFS_ABI_VERSION 3
 
 enum {
     PFS_OK = 0,
@@ -311,21 +318,26 @@ int pfs_wide_rowmap(int32_t kind, const void* x, int32_t x_dtype, int64_t ldx, c
                     int64_t R, int32_t C, void* out_bf16, int64_t ldo, void* stream);
 /* out[seg][c] = sum of x[row][c] over the segment's rows -> fp32 and/or bf16 [nseg, C] */
 size_t pfs_wide_segsum_workspace(const pfs_wide_segments* sd, int32_t C);
-int pfs_wide_segsum(const pfs_wide_segments* sd, const void* x_bf16, int64_t ldx, int32_t C, float* out_f32,
+int pfs_wide_segsum(const pfs_wide_segments* sd, const void* x, int32_t x_dtype, int64_t ldx, int32_t C, float* out_f32,
                     void* out_bf16, void* workspace, size_t workspace_bytes, void* stream);
 /* SModel moment statistics (src/gnn.py:140-151) of the messages m [E,2F] per fibre:
  * moments [S,5,2F] = {mean, E[m^2], c2, c3, c4}; hcat [S,9F] = [x_s|mean|std|skew|kurt] */
-int pfs_wide_moments_fwd(const pfs_wide_segments* sd, const void* m_bf16, int32_t C, float* moments, void* stream);
-int pfs_wide_source_hcat(const void* x_s_bf16, const float* moments, int32_t S, int32_t F, void* hcat_bf16, void* stream);
+int pfs_wide_moments_fwd(const pfs_wide_segments* sd, const void* m, int32_t m_dtype, int32_t C, float* moments, void* stream);
+int pfs_wide_source_hcat(const void* x_s_bf16, const float* moments, int32_t S, int32_t F, void* hcat_bf16, int64_t ldo,
+                         int32_t with_lo, void* stream);
+/* with_lo: rows of 17F columns, [hcat | bf16 remainders of the 8F statistics columns]; contracted against
+ * [W3[:, :9F] | W3[:, F:9F]] the fibre MLP sees the statistics to ~2^-17 instead of 2^-9.
+ * pfs_wide_split: out[r] = [hi(x[r]) | lo(x[r])] (bf16 [R, 2C]) for any node-level fp32 GEMM operand */
+int pfs_wide_split(const float* x, int64_t ldx, int64_t R, int32_t C, void* out_bf16, int64_t ldo, void* stream);
 /* backward of the statistics: dh [S,9F] fp32 -> dx_s bf16 [S,F] and cubic coefficients coef [S,4,2F];
  * dm[e] = A0 + A1 m + A2 d^2 + A3 d^3 per edge (src = fibre of every edge, NULL: e / T) */
 int pfs_wide_source_coef(const pfs_wide_segments* sd, const float* dh, const float* moments, int32_t S, int32_t F,
                          void* dx_s_bf16, float* coef, void* stream);
-int pfs_wide_source_dm(const void* m_bf16, const float* moments, const float* coef, const int32_t* src, int32_t T,
+int pfs_wide_source_dm(const void* m, int32_t m_dtype, const float* moments, const float* coef, const int32_t* src, int32_t T,
                        int64_t E, int32_t C, void* dm_bf16, void* stream);
 /* the same, one CTA per fibre segment (coefficients stay in registers over the fibre's edges) */
-int pfs_wide_source_dm_seg(const pfs_wide_segments* fibres, const void* m_bf16, const float* moments, const float* coef,
-                           int32_t C, void* dm_bf16, void* stream);
+int pfs_wide_source_dm_seg(const pfs_wide_segments* fibres, const void* m, int32_t m_dtype, const float* moments,
+                           const float* coef, int32_t C, void* dm_bf16, void* stream);
 /* out[e] = tab[idx ? idx[e] : e % mod] * (act[e] > 0 ? 1 : 0.1)   (TModel backward, src/gnn.py:188-190) */
 int pfs_wide_gather_mask(const float* tab, const int32_t* idx, int32_t mod, const void* act_bf16, int64_t E, int32_t C,
                          void* out_bf16, void* stream);

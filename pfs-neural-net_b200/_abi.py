@@ -18,7 +18,7 @@ HEADER = os.path.join(os.path.dirname(_HERE), "include", "pfs_b200.h")
 PFS_LAYOUT_DENSE = 0
 PFS_LAYOUT_CSR = 1
 PFS_TILE_EDGES = 256
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _P = ct.c_void_p
 
@@ -169,12 +169,13 @@ SYMBOLS = {
     "pfs_wide_colstats": (ct.c_int, [_I32, _P, _I32, _I64, _P, _I32, _I64, _P, _P, _P, _I64, _I32, _P, _P, ct.c_size_t, _P]),
     "pfs_wide_rowmap": (ct.c_int, [_I32, _P, _I32, _I64, _P, _I32, _I64, _P, _P, _P, _P, _P, _I64, _I32, _P, _I64, _P]),
     "pfs_wide_segsum_workspace": (ct.c_size_t, [ct.POINTER(WideSegments), _I32]),
-    "pfs_wide_segsum": (ct.c_int, [ct.POINTER(WideSegments), _P, _I64, _I32, _P, _P, _P, ct.c_size_t, _P]),
-    "pfs_wide_moments_fwd": (ct.c_int, [ct.POINTER(WideSegments), _P, _I32, _P, _P]),
-    "pfs_wide_source_hcat": (ct.c_int, [_P, _P, _I32, _I32, _P, _P]),
+    "pfs_wide_segsum": (ct.c_int, [ct.POINTER(WideSegments), _P, _I32, _I64, _I32, _P, _P, _P, ct.c_size_t, _P]),
+    "pfs_wide_moments_fwd": (ct.c_int, [ct.POINTER(WideSegments), _P, _I32, _I32, _P, _P]),
+    "pfs_wide_source_hcat": (ct.c_int, [_P, _P, _I32, _I32, _P, _I64, _I32, _P]),
+    "pfs_wide_split": (ct.c_int, [_P, _I64, _I64, _I32, _P, _I64, _P]),
     "pfs_wide_source_coef": (ct.c_int, [ct.POINTER(WideSegments), _P, _P, _I32, _I32, _P, _P, _P]),
-    "pfs_wide_source_dm": (ct.c_int, [_P, _P, _P, _P, _I32, _I64, _I32, _P, _P]),
-    "pfs_wide_source_dm_seg": (ct.c_int, [ct.POINTER(WideSegments), _P, _P, _P, _I32, _P, _P]),
+    "pfs_wide_source_dm": (ct.c_int, [_P, _I32, _P, _P, _P, _I32, _I64, _I32, _P, _P]),
+    "pfs_wide_source_dm_seg": (ct.c_int, [ct.POINTER(WideSegments), _P, _I32, _P, _P, _I32, _P, _P]),
     "pfs_wide_gather_mask": (ct.c_int, [_P, _P, _I32, _P, _I64, _I32, _P, _P]),
     "pfs_wide_head_fwd": (ct.c_int, [_P, _P, _P, ct.c_float, _I64, _I32, _P, _P, _I32, _P, _P, _P, _P, _P]),
     "pfs_wide_head_bwd": (ct.c_int, [_P, _P, _P, _P, ct.c_float, _I64, _I32, _P, _P, _P]),

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -47,7 +48,7 @@ struct ProfMark {
     const char* name;   // nullptr = start-of-call marker
     cudaEvent_t ev;
 };
-long long g_launches = 0;
+std::atomic<long long> g_launches{0};
 bool g_prof_on = false;
 std::vector<ProfMark> g_marks;
 std::vector<cudaEvent_t> g_event_pool;
@@ -81,6 +82,42 @@ void prof_mark(const char* name, cudaStream_t st) {
         int rc__ = (expr);       \
         if (rc__ != PFS_OK) return rc__; \
     } while (0)
+
+// ---- single-stream contract (include/pfs_b200.h, "Conventions") --------------------------------------------
+// The module-level entry points share one __constant__ weight bank and one caller-provided workspace per device, so
+// consecutive calls on a device must be ordered.  Every such call records an event on its stream when it returns;
+// a call arriving on a DIFFERENT stream first makes that stream wait for the previous call's event (device-side
+// wait, no host synchronisation).  Streams under CUDA-graph capture are left alone (the capture orders them).
+struct StreamOrder {
+    static constexpr int kMaxDev = 16;
+    cudaStream_t last[kMaxDev] = {};
+    cudaEvent_t ev[kMaxDev] = {};
+    bool valid[kMaxDev] = {};
+};
+StreamOrder g_order;
+
+struct CallGuard {
+    cudaStream_t st;
+    int dev = -1;
+    bool capturing = false;
+    explicit CallGuard(void* stream) : st((cudaStream_t)stream) {
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= StreamOrder::kMaxDev) { dev = -1; return; }
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { (void)cudaGetLastError(); dev = -1; return; }
+        capturing = cs != cudaStreamCaptureStatusNone;
+        if (capturing) { g_order.valid[dev] = false; return; }
+        if (g_order.valid[dev] && g_order.last[dev] != st) (void)cudaStreamWaitEvent(st, g_order.ev[dev], 0);
+    }
+    ~CallGuard() {
+        if (dev < 0 || capturing) return;
+        if (!g_order.ev[dev] && cudaEventCreateWithFlags(&g_order.ev[dev], cudaEventDisableTiming) != cudaSuccess) {
+            g_order.ev[dev] = nullptr;
+            return;
+        }
+        g_order.valid[dev] = cudaEventRecord(g_order.ev[dev], st) == cudaSuccess;
+        g_order.last[dev] = st;
+    }
+};
 
 constexpr int kMaxCtas = 1024;
 
@@ -1101,6 +1138,7 @@ int pfs_build_topology(const int64_t* edge_index, int64_t E, int32_t S, int32_t 
 }
 
 int pfs_edge_fwd(const pfs_edge_args* a) {
+    CallGuard guard(a ? a->stream : nullptr);
     PFS_REQUIRE(a && a->x_s && a->x_t && a->x_e && a->u && a->w1 && a->b1 && a->w2 && a->b2 && a->x_e_out && a->workspace,
                 "null pointer");
     Topo tp;
@@ -1109,6 +1147,7 @@ int pfs_edge_fwd(const pfs_edge_args* a) {
     return PFS_OK;
 }
 int pfs_edge_bwd(const pfs_edge_args* a) {
+    CallGuard guard(a ? a->stream : nullptr);
     PFS_REQUIRE(a && a->x_s && a->x_t && a->x_e && a->u && a->w1 && a->b1 && a->w2 && a->x_e_out && a->g_out &&
                     a->g_x_s && a->g_x_t && a->g_x_e && a->g_u && a->g_w1 && a->g_b1 && a->g_w2 && a->g_b2 && a->workspace,
                 "null pointer");
@@ -1119,6 +1158,7 @@ int pfs_edge_bwd(const pfs_edge_args* a) {
     return PFS_OK;
 }
 int pfs_source_fwd(const pfs_source_args* a) {
+    CallGuard guard(a ? a->stream : nullptr);
     PFS_REQUIRE(a && a->x_s && a->x_t && a->x_e && a->u && a->w1 && a->b1 && a->w2 && a->b2 && a->w3 && a->b3 && a->w4 &&
                     a->b4 && a->x_s_out && a->moments && a->hidden && a->y_pre && a->workspace, "null pointer");
     Topo tp;
@@ -1127,6 +1167,7 @@ int pfs_source_fwd(const pfs_source_args* a) {
     return PFS_OK;
 }
 int pfs_source_bwd(const pfs_source_args* a) {
+    CallGuard guard(a ? a->stream : nullptr);
     PFS_REQUIRE(a && a->x_s && a->x_t && a->x_e && a->u && a->w1 && a->b1 && a->w2 && a->b2 && a->w3 && a->w4 &&
                     a->moments && a->hidden && a->y_pre && a->g_out && a->g_x_s && a->g_x_t && a->g_x_e && a->g_u &&
                     a->g_w1 && a->g_b1 && a->g_w2 && a->g_b2 && a->g_w3 && a->g_b3 && a->g_w4 && a->g_b4 && a->workspace,
@@ -1138,6 +1179,7 @@ int pfs_source_bwd(const pfs_source_args* a) {
     return PFS_OK;
 }
 int pfs_target_fwd(const pfs_target_args* a) {
+    CallGuard guard(a ? a->stream : nullptr);
     PFS_REQUIRE(a && a->x_s && a->x_t && a->x_e && a->u && a->w1 && a->b1 && a->w2 && a->b2 && a->w3 && a->b3 && a->w4 &&
                     a->b4 && a->x_t_out && a->act_sum && a->y_pre && a->workspace, "null pointer");
     Topo tp;
@@ -1146,6 +1188,7 @@ int pfs_target_fwd(const pfs_target_args* a) {
     return PFS_OK;
 }
 int pfs_target_bwd(const pfs_target_args* a) {
+    CallGuard guard(a ? a->stream : nullptr);
     PFS_REQUIRE(a && a->x_s && a->x_t && a->x_e && a->u && a->w1 && a->b1 && a->w2 && a->b2 && a->w3 && a->b3 && a->w4 &&
                     a->act_sum && a->y_pre && a->g_out && a->g_x_s && a->g_x_t && a->g_x_e && a->g_u && a->g_w1 &&
                     a->g_b1 && a->g_w2 && a->g_b2 && a->g_w3 && a->g_b3 && a->g_w4 && a->g_b4 && a->workspace,
@@ -1169,6 +1212,7 @@ static int global_common(const pfs_global_args* a, GlobalParams& p) {
     return PFS_OK;
 }
 int pfs_global_fwd(const pfs_global_args* a) {
+    CallGuard guard(a ? a->stream : nullptr);
     GlobalParams p;
     PFS_TRY(global_common(a, p));
     PFS_REQUIRE(a->u_out, "null pointer");
@@ -1180,6 +1224,7 @@ int pfs_global_fwd(const pfs_global_args* a) {
     return PFS_OK;
 }
 int pfs_global_bwd(const pfs_global_args* a) {
+    CallGuard guard(a ? a->stream : nullptr);
     GlobalParams p;
     PFS_TRY(global_common(a, p));
     PFS_REQUIRE(a->g_out && a->g_x_s && a->g_x_t && a->g_u && a->g_w1 && a->g_b1 && a->g_w2 && a->g_b2 && a->workspace,
@@ -1208,6 +1253,7 @@ int pfs_global_bwd(const pfs_global_args* a) {
 }
 
 int pfs_time_head_fwd(const pfs_head_args* a) {
+    CallGuard guard(a ? a->stream : nullptr);
     PFS_REQUIRE(a && a->x_e && a->w1 && a->b1 && a->w2 && a->b2 && a->time, "null pointer");
     Topo tp;
     PFS_TRY(make_topo(a->topo, tp));
@@ -1215,6 +1261,7 @@ int pfs_time_head_fwd(const pfs_head_args* a) {
     return PFS_OK;
 }
 int pfs_time_head_bwd(const pfs_head_args* a) {
+    CallGuard guard(a ? a->stream : nullptr);
     PFS_REQUIRE(a && a->x_e && a->w1 && a->b1 && a->w2 && a->b2 && a->g_time && a->g_x_e && a->g_w1 && a->g_b1 &&
                     a->g_w2 && a->g_b2 && a->workspace, "null pointer");
     Topo tp;

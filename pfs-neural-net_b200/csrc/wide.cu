@@ -366,11 +366,12 @@ size_t pfs_wide_segsum_workspace(const pfs_wide_segments* sd, int32_t C) {
     return (size_t)segsum_chunks(*sd, C) * sd->nseg * C * sizeof(float) + 256;
 }
 
-int pfs_wide_segsum(const pfs_wide_segments* sd, const void* x_bf16, int64_t ldx, int32_t C, float* out_f32, void* out_bf16,
-                    void* workspace, size_t workspace_bytes, void* stream) {
+int pfs_wide_segsum(const pfs_wide_segments* sd, const void* x, int32_t x_dtype, int64_t ldx, int32_t C, float* out_f32,
+                    void* out_bf16, void* workspace, size_t workspace_bytes, void* stream) {
     W_TRY(check_seg(sd));
-    W_REQUIRE(x_bf16 && (out_f32 || out_bf16) && C >= 8 && C % 8 == 0 && ldx % 8 == 0 && ((uintptr_t)x_bf16 & 15) == 0,
+    W_REQUIRE(x && (out_f32 || out_bf16) && C >= 8 && C % 8 == 0 && ldx % 8 == 0 && ((uintptr_t)x & 15) == 0,
               "bad arguments (C and ldx multiples of 8, 16-byte aligned rows)");
+    W_REQUIRE(x_dtype == 0 || x_dtype == 1, "dtype code (0 = bf16, 1 = fp32)");
     cudaStream_t st = (cudaStream_t)stream;
     pfs_host::mark_launch(nullptr, st);
     const int nchunk = segsum_chunks(*sd, C);
@@ -380,8 +381,12 @@ int pfs_wide_segsum(const pfs_wide_segments* sd, const void* x_bf16, int64_t ldx
             return wfail(PFS_ERR_WORKSPACE, "segsum: workspace too small");
         partial = (float*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     }
-    k_wide_segsum<<<dim3(sd->nseg, nchunk), 256, 0, st>>>(make_seg(*sd), (const bf16*)x_bf16, (int)ldx, C, nchunk, out_f32,
-                                                          (bf16*)out_bf16, partial);
+    if (x_dtype == 0)
+        k_wide_segsum<bf16><<<dim3(sd->nseg, nchunk), 256, 0, st>>>(make_seg(*sd), (const bf16*)x, (int)ldx, C, nchunk, out_f32,
+                                                                    (bf16*)out_bf16, partial);
+    else
+        k_wide_segsum<float><<<dim3(sd->nseg, nchunk), 256, 0, st>>>(make_seg(*sd), (const float*)x, (int)ldx, C, nchunk, out_f32,
+                                                                     (bf16*)out_bf16, partial);
     W_LAUNCH_CHECK("k_wide_segsum");
     if (nchunk > 1) {
         const long long n = (long long)sd->nseg * C;
@@ -391,22 +396,37 @@ int pfs_wide_segsum(const pfs_wide_segments* sd, const void* x_bf16, int64_t ldx
     return PFS_OK;
 }
 
-int pfs_wide_moments_fwd(const pfs_wide_segments* sd, const void* m_bf16, int32_t C, float* moments, void* stream) {
+int pfs_wide_moments_fwd(const pfs_wide_segments* sd, const void* m, int32_t m_dtype, int32_t C, float* moments, void* stream) {
     W_TRY(check_seg(sd));
-    W_REQUIRE(m_bf16 && moments && C >= 8 && C % 8 == 0 && C <= 2048 && ((uintptr_t)m_bf16 & 15) == 0, "bad arguments");
+    W_REQUIRE(m && moments && C >= 8 && C % 8 == 0 && C <= 2048 && ((uintptr_t)m & 15) == 0, "bad arguments");
+    W_REQUIRE(m_dtype == 0 || m_dtype == 1, "dtype code (0 = bf16, 1 = fp32)");
     cudaStream_t st = (cudaStream_t)stream;
     pfs_host::mark_launch(nullptr, st);
-    k_wide_moments_fwd<<<sd->nseg, 256, 0, st>>>(make_seg(*sd), (const bf16*)m_bf16, C, moments);
+    if (m_dtype == 0) k_wide_moments_fwd<bf16><<<sd->nseg, 256, 0, st>>>(make_seg(*sd), (const bf16*)m, C, moments);
+    else k_wide_moments_fwd<float><<<sd->nseg, 256, 0, st>>>(make_seg(*sd), (const float*)m, C, moments);
     W_LAUNCH_CHECK("k_wide_moments_fwd");
     return PFS_OK;
 }
 
-int pfs_wide_source_hcat(const void* x_s_bf16, const float* moments, int32_t S, int32_t F, void* hcat_bf16, void* stream) {
+int pfs_wide_source_hcat(const void* x_s_bf16, const float* moments, int32_t S, int32_t F, void* hcat_bf16, int64_t ldo,
+                         int32_t with_lo, void* stream) {
     W_REQUIRE(x_s_bf16 && moments && hcat_bf16 && S >= 1 && F >= 2, "bad arguments");
+    W_REQUIRE(ldo >= (with_lo ? 17 : 9) * (int64_t)F, "hcat rows hold 9F columns (17F with the remainders)");
     cudaStream_t st = (cudaStream_t)stream;
     pfs_host::mark_launch(nullptr, st);
-    k_wide_source_hcat<<<grid_for((long long)S * 3 * F), 256, 0, st>>>((const bf16*)x_s_bf16, moments, S, F, (bf16*)hcat_bf16);
+    k_wide_source_hcat<<<grid_for((long long)S * 3 * F), 256, 0, st>>>((const bf16*)x_s_bf16, moments, S, F, (bf16*)hcat_bf16,
+                                                                      (int)ldo, with_lo);
     W_LAUNCH_CHECK("k_wide_source_hcat");
+    return PFS_OK;
+}
+
+int pfs_wide_split(const float* x, int64_t ldx, int64_t R, int32_t C, void* out_bf16, int64_t ldo, void* stream) {
+    W_REQUIRE(x && out_bf16 && R >= 1 && C >= 2 && C % 2 == 0 && ldx % 2 == 0 && ldo % 2 == 0 && ldo >= 2 * (int64_t)C &&
+                  ((uintptr_t)x & 7) == 0 && ((uintptr_t)out_bf16 & 3) == 0, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    pfs_host::mark_launch(nullptr, st);
+    k_wide_split<<<grid_for(R * (C / 2)), 256, 0, st>>>(x, (int)ldx, R, C, (bf16*)out_bf16, (int)ldo);
+    W_LAUNCH_CHECK("k_wide_split");
     return PFS_OK;
 }
 
@@ -421,23 +441,29 @@ int pfs_wide_source_coef(const pfs_wide_segments* sd, const float* dh, const flo
     return PFS_OK;
 }
 
-int pfs_wide_source_dm(const void* m_bf16, const float* moments, const float* coef, const int32_t* src, int32_t T, int64_t E,
-                       int32_t C, void* dm_bf16, void* stream) {
-    W_REQUIRE(m_bf16 && moments && coef && dm_bf16 && E >= 1 && C >= 8 && C % 8 == 0 && (src || T >= 1), "bad arguments");
+int pfs_wide_source_dm(const void* m, int32_t m_dtype, const float* moments, const float* coef, const int32_t* src, int32_t T,
+                       int64_t E, int32_t C, void* dm_bf16, void* stream) {
+    W_REQUIRE(m && moments && coef && dm_bf16 && E >= 1 && C >= 8 && C % 8 == 0 && (src || T >= 1), "bad arguments");
+    W_REQUIRE(m_dtype == 0 || m_dtype == 1, "dtype code (0 = bf16, 1 = fp32)");
     cudaStream_t st = (cudaStream_t)stream;
     pfs_host::mark_launch(nullptr, st);
-    k_wide_source_dm<<<grid_for(E * (C / 8)), 256, 0, st>>>((const bf16*)m_bf16, moments, coef, src, T, E, C, (bf16*)dm_bf16);
+    if (m_dtype == 0)
+        k_wide_source_dm<bf16><<<grid_for(E * (C / 8)), 256, 0, st>>>((const bf16*)m, moments, coef, src, T, E, C, (bf16*)dm_bf16);
+    else
+        k_wide_source_dm<float><<<grid_for(E * (C / 8)), 256, 0, st>>>((const float*)m, moments, coef, src, T, E, C, (bf16*)dm_bf16);
     W_LAUNCH_CHECK("k_wide_source_dm");
     return PFS_OK;
 }
 
-int pfs_wide_source_dm_seg(const pfs_wide_segments* sd, const void* m_bf16, const float* moments, const float* coef, int32_t C,
-                           void* dm_bf16, void* stream) {
+int pfs_wide_source_dm_seg(const pfs_wide_segments* sd, const void* m, int32_t m_dtype, const float* moments, const float* coef,
+                           int32_t C, void* dm_bf16, void* stream) {
     W_TRY(check_seg(sd));
-    W_REQUIRE(m_bf16 && moments && coef && dm_bf16 && C >= 8 && C % 8 == 0 && C <= 2048, "bad arguments");
+    W_REQUIRE(m && moments && coef && dm_bf16 && C >= 8 && C % 8 == 0 && C <= 2048, "bad arguments");
+    W_REQUIRE(m_dtype == 0 || m_dtype == 1, "dtype code (0 = bf16, 1 = fp32)");
     cudaStream_t st = (cudaStream_t)stream;
     pfs_host::mark_launch(nullptr, st);
-    k_wide_source_dm_seg<<<sd->nseg, 256, 0, st>>>(make_seg(*sd), (const bf16*)m_bf16, moments, coef, C, (bf16*)dm_bf16);
+    if (m_dtype == 0) k_wide_source_dm_seg<bf16><<<sd->nseg, 256, 0, st>>>(make_seg(*sd), (const bf16*)m, moments, coef, C, (bf16*)dm_bf16);
+    else k_wide_source_dm_seg<float><<<sd->nseg, 256, 0, st>>>(make_seg(*sd), (const float*)m, moments, coef, C, (bf16*)dm_bf16);
     W_LAUNCH_CHECK("k_wide_source_dm");
     return PFS_OK;
 }

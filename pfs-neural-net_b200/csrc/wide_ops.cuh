@@ -42,6 +42,9 @@ __device__ __forceinline__ void ld8f(const float* p, float (&v)[8]) {
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
+__device__ __forceinline__ void ld8_any(const bf16* p, float (&v)[8]) { ld8(p, v); }
+__device__ __forceinline__ void ld8_any(const float* p, float (&v)[8]) { ld8f(p, v); }
+
 // segments of rows: fibres or classes, dense (implicit) or listed
 struct SegDesc {
     int mode;          // 0: dense fibre (rows seg*T + i, i < T), 1: dense class (rows i*T + seg, i < S), 2: list
@@ -171,8 +174,6 @@ __global__ void __launch_bounds__(256) k_wide_rowmap(int kind, const TX* __restr
     }
 }
 
-__device__ __forceinline__ void ld8_any(const bf16* p, float (&v)[8]) { ld8(p, v); }
-__device__ __forceinline__ void ld8_any(const float* p, float (&v)[8]) { ld8f(p, v); }
 // the same maps with 8 columns per thread (16-byte accesses) and the per-column coefficients held in registers:
 // a thread keeps its column group and strides over the rows
 template <class TX, class TV>
@@ -217,7 +218,8 @@ __global__ void __launch_bounds__(256) k_wide_rowmap8(int kind, const TX* __rest
 // grid (nseg, nchunk), 256 threads, thread = column pair (loops when C > 512);
 // nchunk > 1 writes partial[chunk][seg][C] for k_wide_segsum_final
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_wide_segsum(const SegDesc sd, const bf16* __restrict__ x, int ldx, int C, int nchunk,
+template <class TX>
+__global__ void __launch_bounds__(256) k_wide_segsum(const SegDesc sd, const TX* __restrict__ x, int ldx, int C, int nchunk,
                                                      float* __restrict__ out_f32, bf16* __restrict__ out_bf16,
                                                      float* __restrict__ partial) {
     // thread = 8 columns (one 16-byte load) of one row lane; tpr threads cover a row, 256 / tpr rows are
@@ -237,20 +239,20 @@ __global__ void __launch_bounds__(256) k_wide_segsum(const SegDesc sd, const bf1
 #pragma unroll
         for (int q = 0; q < 8; ++q) acc[q] = 0.f;
         if (live) {
-            const bf16* xc = x + 8 * cg;
+            const TX* xc = x + 8 * cg;
             int i = i0 + lr;
             for (; i + 3 * lanes < i1; i += 4 * lanes) {
                 float v0[8], v1[8], v2[8], v3[8];
-                ld8(xc + seg_row(sd, seg, i) * ldx, v0);
-                ld8(xc + seg_row(sd, seg, i + lanes) * ldx, v1);
-                ld8(xc + seg_row(sd, seg, i + 2 * lanes) * ldx, v2);
-                ld8(xc + seg_row(sd, seg, i + 3 * lanes) * ldx, v3);
+                ld8_any(xc + seg_row(sd, seg, i) * ldx, v0);
+                ld8_any(xc + seg_row(sd, seg, i + lanes) * ldx, v1);
+                ld8_any(xc + seg_row(sd, seg, i + 2 * lanes) * ldx, v2);
+                ld8_any(xc + seg_row(sd, seg, i + 3 * lanes) * ldx, v3);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) acc[q] += (v0[q] + v1[q]) + (v2[q] + v3[q]);
             }
             for (; i < i1; i += lanes) {
                 float v0[8];
-                ld8(xc + seg_row(sd, seg, i) * ldx, v0);
+                ld8_any(xc + seg_row(sd, seg, i) * ldx, v0);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) acc[q] += v0[q];
             }
@@ -296,7 +298,8 @@ __global__ void k_wide_segsum_final(const float* __restrict__ partial, int nchun
 // moments[fibre] = {mean, E[m^2], c2, c3, c4} (central moments about the mean, two passes), [S,5,C]
 // grid (S), C / 2 threads
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_wide_moments_fwd(const SegDesc sd, const bf16* __restrict__ m, int C,
+template <class TM>
+__global__ void __launch_bounds__(256) k_wide_moments_fwd(const SegDesc sd, const TM* __restrict__ m, int C,
                                                           float* __restrict__ moments) {
     // same thread mapping as k_wide_segsum (8 columns x row lanes); pass 1: sum, sum of squares; pass 2: central moments
     __shared__ float red[256 * 8 * 3];
@@ -311,7 +314,7 @@ __global__ void __launch_bounds__(256) k_wide_moments_fwd(const SegDesc sd, cons
     for (int cg0 = 0; cg0 < cgroups; cg0 += tpr) {
         const int cg = cg0 + lc;
         const bool live = lr < lanes && cg < cgroups;
-        const bf16* xc = m + 8 * cg;
+        const TM* xc = m + 8 * cg;
         float s1[8], s2[8], s3[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) s1[q] = s2[q] = s3[q] = 0.f;
@@ -319,8 +322,8 @@ __global__ void __launch_bounds__(256) k_wide_moments_fwd(const SegDesc sd, cons
             int i = lr;
             for (; i + lanes < len; i += 2 * lanes) {
                 float v0[8], v1[8];
-                ld8(xc + seg_row(sd, seg, i) * C, v0);
-                ld8(xc + seg_row(sd, seg, i + lanes) * C, v1);
+                ld8_any(xc + seg_row(sd, seg, i) * C, v0);
+                ld8_any(xc + seg_row(sd, seg, i + lanes) * C, v1);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     s1[q] += v0[q] + v1[q];
@@ -329,7 +332,7 @@ __global__ void __launch_bounds__(256) k_wide_moments_fwd(const SegDesc sd, cons
             }
             for (; i < len; i += lanes) {
                 float v0[8];
-                ld8(xc + seg_row(sd, seg, i) * C, v0);
+                ld8_any(xc + seg_row(sd, seg, i) * C, v0);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     s1[q] += v0[q];
@@ -368,7 +371,7 @@ __global__ void __launch_bounds__(256) k_wide_moments_fwd(const SegDesc sd, cons
         if (live) {
             for (int i = lr; i < len; i += lanes) {
                 float v0[8];
-                ld8(xc + seg_row(sd, seg, i) * C, v0);
+                ld8_any(xc + seg_row(sd, seg, i) * C, v0);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     const float d = v0[q] - mean[q], d2 = d * d;
@@ -424,26 +427,49 @@ __device__ __forceinline__ MomentStats wide_moment_stats(float mean, float ex2, 
     s.kurt = wide_nan_to_num(c4 / (s3 * s.std0));
     return s;
 }
-// hcat[fibre] = [x_s | mean | std | skew | kurt]  (bf16 [S, 9F]; reference src/gnn.py:147-152)
+// hcat[fibre] = [x_s | mean | std | skew | kurt]  (bf16 [S, 9F], row stride ldo; reference src/gnn.py:147-152).
+// with_lo: the row continues with the bf16 remainders of the four statistics, [... | lo(mean) | lo(std) | lo(skew) |
+// lo(kurt)] (17F columns): contracted against [W3 | W3[:, F:9F]] the fibre MLP sees the statistics to ~2^-17
 __global__ void k_wide_source_hcat(const bf16* __restrict__ x_s, const float* __restrict__ moments, int S, int F,
-                                   bf16* __restrict__ hcat) {
+                                   bf16* __restrict__ hcat, int ldo, int with_lo) {
     const int C = 2 * F, K9 = 9 * F;
     const long long total = (long long)S * (F + C);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long s = i / (F + C);
         const int j = (int)(i - s * (F + C));
-        bf16* o = hcat + s * K9;
+        bf16* o = hcat + s * ldo;
         if (j < F) {
             o[j] = x_s[s * F + j];
         } else {
             const int c = j - F;
             const float* mo = moments + s * 5 * C + c;
             const MomentStats st = wide_moment_stats(mo[0], mo[C], mo[3 * C], mo[4 * C]);
-            o[F + c] = __float2bfloat16_rn(st.mean);
-            o[F + C + c] = __float2bfloat16_rn(st.std);
-            o[F + 2 * C + c] = __float2bfloat16_rn(st.skew);
-            o[F + 3 * C + c] = __float2bfloat16_rn(st.kurt);
+            const float v[4] = {st.mean, st.std, st.skew, st.kurt};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const bf16 hi = __float2bfloat16_rn(v[q]);
+                o[F + q * C + c] = hi;
+                if (with_lo) {
+                    const float rem = v[q] - __bfloat162float(hi);       // inf - inf never occurs: nan_to_num clamps to FLT_MAX
+                    o[K9 + q * C + c] = __float2bfloat16_rn(rem == rem ? rem : 0.f);
+                }
+            }
         }
+    }
+}
+// out[r] = [hi(x[r]) | lo(x[r])] (bf16 [R, 2C], row stride ldo): x = hi + lo to ~2^-17, so a bf16 GEMM over the
+// doubled contraction [hi | lo] . [W | W]^T reproduces the fp32 operand (node-level operands only: O(S + T) rows)
+__global__ void k_wide_split(const float* __restrict__ x, int ldx, long long R, int C, bf16* __restrict__ out, int ldo) {
+    const int half = C >> 1;
+    const long long total = R * half;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / half;
+        const int c = 2 * (int)(i - r * half);
+        const float2 v = *reinterpret_cast<const float2*>(x + r * ldx + c);
+        const bf162 hi = __floats2bfloat162_rn(v.x, v.y);
+        const float2 hf = __bfloat1622float2(hi);
+        *reinterpret_cast<bf162*>(out + r * ldo + c) = hi;
+        *reinterpret_cast<bf162*>(out + r * ldo + C + c) = __floats2bfloat162_rn(v.x - hf.x, v.y - hf.y);
     }
 }
 // moments backward: dh [S, 9F] fp32 (gradient of hcat) -> dx_s [S,F] bf16 and the per-fibre cubic
@@ -491,7 +517,8 @@ __global__ void k_wide_source_coef(const SegDesc sd, const float* __restrict__ d
     }
 }
 // dm[e] = A0[src] + A1[src] m + A2[src] d^2 + A3[src] d^3, d = m - mean[src]   (bf16 [E, C])
-__global__ void __launch_bounds__(256) k_wide_source_dm(const bf16* __restrict__ m, const float* __restrict__ moments,
+template <class TM>
+__global__ void __launch_bounds__(256) k_wide_source_dm(const TM* __restrict__ m, const float* __restrict__ moments,
                                                         const float* __restrict__ coef, const int* __restrict__ src, int T,
                                                         long long E, int C, bf16* __restrict__ dm) {
     const int groups = C >> 3;
@@ -501,7 +528,7 @@ __global__ void __launch_bounds__(256) k_wide_source_dm(const bf16* __restrict__
         const int c = 8 * (int)(i - e * groups);
         const long long s = src ? src[e] : e / T;
         float mm[8], mean[8], a0[8], a1[8], a2[8], a3[8], o[8];
-        ld8(m + e * C + c, mm);
+        ld8_any(m + e * C + c, mm);
         ld8f(moments + s * 5 * C + c, mean);
         const float* cf = coef + s * 4 * C + c;
         ld8f(cf, a0); ld8f(cf + C, a1); ld8f(cf + 2 * C, a2); ld8f(cf + 3 * C, a3);
@@ -515,7 +542,8 @@ __global__ void __launch_bounds__(256) k_wide_source_dm(const bf16* __restrict__
 }
 // the same per fibre: a block owns a fibre, a thread keeps the fibre's five coefficient rows of its 8 columns in
 // registers and strides over the fibre's edges (the gathers by src otherwise dominate the L1/L2 traffic)
-__global__ void __launch_bounds__(256) k_wide_source_dm_seg(const SegDesc sd, const bf16* __restrict__ m,
+template <class TM>
+__global__ void __launch_bounds__(256) k_wide_source_dm_seg(const SegDesc sd, const TM* __restrict__ m,
                                                             const float* __restrict__ moments, const float* __restrict__ coef,
                                                             int C, bf16* __restrict__ dm) {
     const int seg = blockIdx.x;
@@ -531,7 +559,7 @@ __global__ void __launch_bounds__(256) k_wide_source_dm_seg(const SegDesc sd, co
     for (int i = lr; i < len; i += lanes) {
         const long long e = seg_row(sd, seg, i);
         float mm[8], o[8];
-        ld8(m + e * C + c, mm);
+        ld8_any(m + e * C + c, mm);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const float d = mm[q] - mean[q];

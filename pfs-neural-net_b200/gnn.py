@@ -310,6 +310,7 @@ class GNN(torch.nn.Module):
         self.decoder_e = MLP(Fdim, Fdim, 1)
         self.decoder_s = MLP(Fdim, Fdim, T)
         self._last_edge_index = None
+        self._head_checked = None
 
     def forward(self, graph):
         x_s, x_t = graph.x_s, graph.x_t
@@ -321,15 +322,24 @@ class GNN(torch.nn.Module):
         self._last_edge_index = edge_index
         return BipartiteData(edge_index, x_s, x_t, x_e, x_u)
 
-    def _head_topology(self, x_e, edge_index):
+    def _head_classes(self, x_e, class_hours, edge_index):
+        """int64 class index of every edge for the integer times: row 1 of the graph's `edge_index` (the last forward's,
+        or the one passed).  The time head itself never looks at the topology, so no CSR is built and the class count
+        comes from `class_hours`, not from the model."""
         if edge_index is None:
             edge_index = self._last_edge_index
         if edge_index is None:
-            raise RuntimeError("edge_prediction needs the graph's edge_index (run forward first or pass it)")
-        T = self.decoder_s[2].out_features
-        E = x_e.shape[-2]
-        S = int(edge_index[0].max().item()) + 1 if E % T else E // T
-        return get_topology(edge_index, S, T)
+            raise RuntimeError("integer_times needs the graph's edge_index (run forward first or pass it)")
+        E, T = x_e.shape[-2], class_hours.shape[0]
+        if edge_index.dim() != 2 or edge_index.shape[0] != 2 or edge_index.shape[1] != E:
+            raise ValueError("edge_index %s does not match x_e with %d edges" % (tuple(edge_index.shape), E))
+        key = (edge_index.data_ptr(), edge_index._version, E, T)
+        if self._head_checked != key:                    # one range check (a host sync) per edge_index tensor
+            tgt = edge_index[1]
+            if int(tgt.min()) < 0 or int(tgt.max()) >= T:
+                raise IndexError("edge_index names classes outside class_hours (%d entries)" % T)
+            self._head_checked = key
+        return edge_index[1].contiguous()
 
     def edge_prediction(self, x_e, scale=1, edge_index=None):
         """softplus(decoder_e(x_e)) * scale, [E, 1] (reference src/gnn.py:307-312; `round` is the
@@ -350,14 +360,16 @@ class GNN(torch.nn.Module):
         """(time, visits, time_int): visits = round-half-even(time / T_i[tgt]), time_int = visits * T_i.
         This is the "rounded integer time" this build defines (reference src/train.py:257)."""
         d = self.decoder_e
+        tgt = self._head_classes(x_e, class_hours, edge_index)
         if pw.supported(x_e.shape[-1], x_e.dtype):
-            topo = self._head_topology(x_e.unsqueeze(0), edge_index)
-            return pw.integer_times(topo.wide(), x_e, d[0].weight, d[0].bias, d[2].weight, d[2].bias, scale, class_hours)
+            if x_e.dim() != 2:
+                raise RuntimeError("the bf16 wide path takes one graph per call (2-D tensors)")
+            return pw.integer_times(tgt.to(torch.int32), x_e, d[0].weight, d[0].bias, d[2].weight, d[2].bias, scale, class_hours)
         single = x_e.dim() == 2
         xe3 = x_e.unsqueeze(0) if single else x_e
-        topo = self._head_topology(xe3, edge_index)
+        topo = _FlatTopology(xe3.shape[1], x_e.device, dense=False)
         out = pf.integer_times(topo, xe3, d[0].weight, d[0].bias, d[2].weight, d[2].bias, scale,
-                               class_hours.to(torch.float32))
+                               class_hours.to(torch.float32), edge_tgt=tgt)
         return tuple(o[0] for o in out) if single else out
 
     def node_prediction(self, x_s, scale=1):
@@ -374,8 +386,8 @@ class GNN(torch.nn.Module):
 class _FlatTopology:
     """Topology stand-in for per-edge ops that never look at src/tgt (the time head)."""
 
-    def __init__(self, E, dev):
-        self.E, self.S, self.T, self.dense, self.device = int(E), int(E), 1, True, dev
+    def __init__(self, E, dev, dense=True):
+        self.E, self.S, self.T, self.dense, self.device = int(E), int(E), 1, dense, dev
         self._ws = None
 
     def struct(self, G, F):

@@ -22,6 +22,18 @@ from . import wide_ops as wo
 from . import shard as _shard
 
 BF16, F32 = torch.bfloat16, torch.float32
+# Where fp32 is kept between the tensor-core GEMMs (north-star bf16 tolerance 1e-2):
+#   z32  -- the EdgeModel pre-BatchNorm output z [E,F]: statistics AND the normalised x_e' are computed from fp32 z
+#   m32  -- the SModel messages m [E,2F]: the moment statistics (E[m^2] - mean^2, third / fourth central moments over
+#           std^3 / std^4 amplify a 2^-9 rounding of m) and their backward read fp32 m
+#   at32 -- the TModel hidden activations feeding the class sums (fp32 copy next to the bf16 one kept for the mask)
+#   node32 -- node-level GEMM operands (O(S + T) rows: the SModel statistics and hidden layer, the TModel class sums,
+#           aggregate and hidden layer) enter their bf16 GEMMs as [hi | lo] pairs against [W | W] (wide_ops.split), i.e.
+#           to ~2^-17 instead of 2^-9; at T = 512 the node-level GEMMs are ~1 % of the step's FLOPs
+# PFS_WIDE_PREC=<comma list> overrides the default set (A/B runs of tools/wide_error_table.py); "none" = all bf16.
+import os as _os
+_PREC_DEFAULT = "z32,m32,at32,node32"
+PREC = set(filter(None, _os.environ.get("PFS_WIDE_PREC", _PREC_DEFAULT).replace("none", "").split(",")))
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 SLOPE = 0.1
@@ -144,7 +156,8 @@ class WideEdgeFunction(torch.autograd.Function):
             Pt = wo.gemm_nt(x_t, w1[:, F:2 * F], bias=uvec[0].contiguous(), want="f32")         # [T,4F] fp32
             a1 = wo.gemm_nt(x_e, w1[:, 2 * F:3 * F], tab0=Ps, idx0=wt.src, div0=wt.div, tab1=Pt, idx1=wt.tgt,
                             mod1=wt.div, act=True)                                              # [E,4F] bf16
-        z = wo.gemm_nt(a1, w2, bias=_f32(b2))                                                   # [E,F] bf16
+        z32 = "z32" in PREC and normed
+        z = wo.gemm_nt(a1, w2, bias=_f32(b2), want="f32" if z32 else "bf16")                    # [E,F]
         saved_small = {}
         if normed:
             g, b = gamma.float(), beta.float()
@@ -169,7 +182,8 @@ class WideEdgeFunction(torch.autograd.Function):
                 shift = a * (b - rmf - a * rmf) + b
                 saved_small = dict(a=a)
             saved_small.update(A=A.contiguous(), shift=shift.contiguous())
-            out = wo.rowmap(0, z, saved_small["A"], saved_small["shift"], out=z)     # in place: z is not needed again
+            # bf16 z is normalised in place (it is not needed again); fp32 z goes to a fresh bf16 x_e'
+            out = wo.rowmap(0, z, saved_small["A"], saved_small["shift"], out=None if z32 else z)
         else:
             out = z
         ctx.topo, ctx.training, ctx.normed, ctx.small = topo, training, normed, saved_small
@@ -256,12 +270,21 @@ class WideSourceFunction(torch.autograd.Function):
         else:
             Qt = wo.gemm_nt(x_t, w1[:, :F], bias=_f32(b1), want="f32")                          # [T,2F] fp32
             a_s = wo.gemm_nt(x_e, w1[:, F:], tab1=Qt, idx1=wt.tgt, mod1=wt.div, act=True)       # [E,2F]
-        m = wo.gemm_nt(a_s, w2, bias=_f32(b2))                                                  # messages [E,2F]
+        m = wo.gemm_nt(a_s, w2, bias=_f32(b2), want="f32" if "m32" in PREC else "bf16")         # messages [E,2F]
         moments = wo.moments_fwd(wt.fibres, m)                                                  # [S,5,2F] fp32
-        hcat = wo.source_hcat(x_s, moments)                                                     # [S,9F] bf16
         b3eff = wo.gemm_nt(u, w3[:, 9 * F:], bias=_f32(b3), want="f32")                         # [1,10F]
-        a3 = wo.gemm_nt(hcat, w3[:, :9 * F], bias=b3eff[0].contiguous(), act=True)              # [S,10F] bf16
-        y = wo.gemm_nt(a3, w4, bias=_f32(b4), want="f32")                                       # [S,F] fp32
+        if "node32" in PREC:
+            hc = wo.source_hcat(x_s, moments, with_lo=True)                                     # [S,17F] = [hcat | lo(stats)]
+            hcat = hc[:, :9 * F]
+            a3c = wo.split(wo.gemm_nt(hc, torch.cat([w3[:, :9 * F], w3[:, F:9 * F]], 1), bias=b3eff[0].contiguous(),
+                                      act=True, want="f32"))                                    # [S,20F] = [a3 | lo(a3)]
+            a3 = a3c[:, :10 * F]
+            y = wo.gemm_nt(a3c, torch.cat([w4, w4], 1), bias=_f32(b4), want="f32")              # [S,F] fp32
+            del hc, a3c
+        else:
+            hcat = wo.source_hcat(x_s, moments)                                                 # [S,9F] bf16
+            a3 = wo.gemm_nt(hcat, w3[:, :9 * F], bias=b3eff[0].contiguous(), act=True)          # [S,10F] bf16
+            y = wo.gemm_nt(a3, w4, bias=_f32(b4), want="f32")                                   # [S,F] fp32
         bn = None
         if normed:
             out, mu, r, n = _single_bn_fwd(y, S, training, gamma, beta, rm, rv, nbt)
@@ -331,19 +354,36 @@ class WideTargetFunction(torch.autograd.Function):
         x_s, x_t, x_e, u, w1, w2, w3, w4 = (t.contiguous() for t in (x_s, x_t, x_e, u, w1, w2, w3, w4))
         T, F = x_t.shape
         Rs = wo.gemm_nt(x_s, w1[:, :F], bias=_f32(b1), want="f32")                              # [S,2F] fp32
+        want = "both" if "at32" in PREC else "bf16"
         if wt.tiled_dense:
-            a_t = wo.gemm_nt(x_e, w1[:, F:], bias_rows=Rs, bias_rows_div=wt.T, act=True)        # R_s[src] is tile-constant
+            a_t = wo.gemm_nt(x_e, w1[:, F:], bias_rows=Rs, bias_rows_div=wt.T, act=True, want=want)   # R_s[src] is tile-constant
         else:
-            a_t = wo.gemm_nt(x_e, w1[:, F:], tab0=Rs, idx0=wt.src, div0=wt.div, act=True)       # [E,2F] bf16
-        asum32 = _shard.allreduce_sum(wo.segsum(wt.classes, a_t, want="f32"))                   # [T,2F]
-        asum = _bf(asum32)
+            a_t = wo.gemm_nt(x_e, w1[:, F:], tab0=Rs, idx0=wt.src, div0=wt.div, act=True, want=want)  # [E,2F] bf16
+        a_t, a_sum_in = a_t if want == "both" else (a_t, a_t)
+        asum32 = _shard.allreduce_sum(wo.segsum(wt.classes, a_sum_in, want="f32"))              # [T,2F]
+        del a_sum_in
         cnt = _shard.allreduce_sum(wt.class_count)
-        hcat = torch.empty(T, 3 * F, dtype=BF16, device=x_t.device)
-        hcat[:, :F].copy_(x_t)
-        wo.gemm_nt(asum, w2, bias=_f32(b2), bias_rowscale=cnt, out_bf16=hcat[:, F:], want="none")   # agg = W2 asum + cnt b2
         b3eff = wo.gemm_nt(u, w3[:, 3 * F:], bias=_f32(b3), want="f32")
-        a3 = wo.gemm_nt(hcat, w3[:, :3 * F], bias=b3eff[0].contiguous(), act=True)              # [T,4F] bf16
-        y = wo.gemm_nt(a3, w4, bias=_f32(b4), want="f32")                                       # [T,F] fp32
+        if "node32" in PREC:
+            asum_c = wo.split(asum32)                                                           # [T,4F] = [asum | lo]
+            asum = asum_c[:, :2 * F]
+            agg32 = wo.gemm_nt(asum_c, torch.cat([w2, w2], 1), bias=_f32(b2), bias_rowscale=cnt, want="f32")
+            hc = torch.empty(T, 5 * F, dtype=BF16, device=x_t.device)                           # [x_t | agg | lo(agg)]
+            hc[:, :F].copy_(x_t)
+            wo.split(agg32, out=hc[:, F:])
+            hcat = hc[:, :3 * F]
+            a3c = wo.split(wo.gemm_nt(hc, torch.cat([w3[:, :3 * F], w3[:, F:3 * F]], 1), bias=b3eff[0].contiguous(),
+                                      act=True, want="f32"))                                    # [T,8F] = [a3 | lo(a3)]
+            a3 = a3c[:, :4 * F]
+            y = wo.gemm_nt(a3c, torch.cat([w4, w4], 1), bias=_f32(b4), want="f32")              # [T,F] fp32
+            del asum_c, hc, a3c
+        else:
+            asum = _bf(asum32)
+            hcat = torch.empty(T, 3 * F, dtype=BF16, device=x_t.device)
+            hcat[:, :F].copy_(x_t)
+            wo.gemm_nt(asum, w2, bias=_f32(b2), bias_rowscale=cnt, out_bf16=hcat[:, F:], want="none")   # agg = W2 asum + cnt b2
+            a3 = wo.gemm_nt(hcat, w3[:, :3 * F], bias=b3eff[0].contiguous(), act=True)          # [T,4F] bf16
+            y = wo.gemm_nt(a3, w4, bias=_f32(b4), want="f32")                                   # [T,F] fp32
         bn = None
         if normed:
             with _shard.replicated():                     # class rows are replicated on every shard
@@ -497,10 +537,12 @@ class WideTimeHeadFunction(torch.autograd.Function):
         return None, g_x_e, _like(g_w1, w1), _like(g_b1, b1), _like(g_w2.reshape(w2.shape), w2), _like(g_b2.reshape(b2.shape), b2)
 
 
-def integer_times(wt, x_e, w1, b1, w2, b2, scale, class_hours):
-    """(time, visits, time_int), fp32 [E] each: the integer definition of DESIGN.md section 8 on the wide path."""
+def integer_times(tgt, x_e, w1, b1, w2, b2, scale, class_hours):
+    """(time, visits, time_int), fp32 [E] each: the integer definition of DESIGN.md section 8 on the wide path;
+    `tgt` = int32 class of every edge."""
     with torch.no_grad():
         a = wo.gemm_nt(x_e.contiguous(), w1.contiguous(), bias=_f32(b1), act=True)
         _, time, visits, time_int = wo.head_fwd(a, _f32(w2.reshape(-1)), _f32(b2.reshape(-1)), scale,
-                                                class_hours=class_hours.float().contiguous(), tgt=wt.tgt, T=wt.T)
+                                                class_hours=class_hours.float().contiguous(), tgt=tgt.contiguous(),
+                                                T=int(class_hours.shape[0]))
     return time, visits, time_int

@@ -174,9 +174,9 @@ def rowmap(kind, x, a, b, v=None, p0=None, p1=None, c2=None, out=None):
 
 
 def segsum(seg, x, want="f32"):
-    """Segmented row sums of x (bf16) -> fp32 and/or bf16 [nseg, C]."""
+    """Segmented row sums of x (bf16 or fp32) -> fp32 and/or bf16 [nseg, C]."""
     x = _rows2d(x, "x")
-    _chk(x, BF16, "x")
+    _chk(x, None, "x")
     C = x.shape[1]
     dev = x.device
     o32 = torch.empty(seg.nseg, C, dtype=F32, device=dev) if want in ("f32", "both") else None
@@ -184,7 +184,7 @@ def segsum(seg, x, want="f32"):
     lib = _abi.load_library()
     ws = _workspace(dev, lib.pfs_wide_segsum_workspace(ct.byref(seg.struct), C))
     with torch.cuda.device(dev):
-        _abi.check(lib.pfs_wide_segsum(ct.byref(seg.struct), x.data_ptr(), x.stride(0), C, _abi.ptr(o32), _abi.ptr(o16),
+        _abi.check(lib.pfs_wide_segsum(ct.byref(seg.struct), x.data_ptr(), _DT[x.dtype], x.stride(0), C, _abi.ptr(o32), _abi.ptr(o16),
                                        ws.data_ptr(), ws.numel(), _stream(dev)), "pfs_wide_segsum")
     if want == "both":
         return o32, o16
@@ -192,24 +192,40 @@ def segsum(seg, x, want="f32"):
 
 
 def moments_fwd(seg, m):
-    _chk(m, BF16, "m")
+    _chk(m, None, "m")
     m = m.contiguous()
     C = m.shape[1]
     out = torch.empty(seg.nseg, 5, C, dtype=F32, device=m.device)
     with torch.cuda.device(m.device):
-        _abi.check(_abi.load_library().pfs_wide_moments_fwd(ct.byref(seg.struct), m.data_ptr(), C, out.data_ptr(),
+        _abi.check(_abi.load_library().pfs_wide_moments_fwd(ct.byref(seg.struct), m.data_ptr(), _DT[m.dtype], C, out.data_ptr(),
                                                             _stream(m.device)), "pfs_wide_moments_fwd")
     return out
 
 
-def source_hcat(x_s, moments):
+def source_hcat(x_s, moments, with_lo=False):
+    """[x_s | mean | std | skew | kurt] bf16 [S, 9F]; with_lo: [S, 17F], the statistics' bf16 remainders appended."""
     _chk(x_s, BF16, "x_s")
     x_s = x_s.contiguous()
     S, F = x_s.shape
-    out = torch.empty(S, 9 * F, dtype=BF16, device=x_s.device)
+    out = torch.empty(S, (17 if with_lo else 9) * F, dtype=BF16, device=x_s.device)
     with torch.cuda.device(x_s.device):
         _abi.check(_abi.load_library().pfs_wide_source_hcat(x_s.data_ptr(), moments.data_ptr(), S, F, out.data_ptr(),
-                                                            _stream(x_s.device)), "pfs_wide_source_hcat")
+                                                            out.stride(0), int(with_lo), _stream(x_s.device)),
+                   "pfs_wide_source_hcat")
+    return out
+
+
+def split(x, out=None):
+    """fp32 [R, C] -> bf16 [R, 2C] = [hi | lo] with x = hi + lo to ~2^-17 (node-level GEMM operands)."""
+    x = _rows2d(x, "x")
+    _chk(x, F32, "x")
+    R, C = x.shape
+    if out is None:
+        out = torch.empty(R, 2 * C, dtype=BF16, device=x.device)
+    out = _rows2d(out, "out")
+    with torch.cuda.device(x.device):
+        _abi.check(_abi.load_library().pfs_wide_split(x.data_ptr(), x.stride(0), R, C, out.data_ptr(), out.stride(0),
+                                                      _stream(x.device)), "pfs_wide_split")
     return out
 
 
@@ -227,11 +243,11 @@ def source_coef(seg, dh, moments, F):
 
 
 def source_dm(m, moments, coef, src, T):
-    _chk(m, BF16, "m")
+    _chk(m, None, "m")
     E, C = m.shape
     out = torch.empty(E, C, dtype=BF16, device=m.device)
     with torch.cuda.device(m.device):
-        _abi.check(_abi.load_library().pfs_wide_source_dm(m.data_ptr(), moments.data_ptr(), coef.data_ptr(), _abi.ptr(src),
+        _abi.check(_abi.load_library().pfs_wide_source_dm(m.data_ptr(), _DT[m.dtype], moments.data_ptr(), coef.data_ptr(), _abi.ptr(src),
                                                           int(T), E, C, out.data_ptr(), _stream(m.device)),
                    "pfs_wide_source_dm")
     return out
@@ -239,11 +255,11 @@ def source_dm(m, moments, coef, src, T):
 
 def source_dm_seg(seg, m, moments, coef):
     """source_dm with one CTA per fibre segment."""
-    _chk(m, BF16, "m")
+    _chk(m, None, "m")
     E, C = m.shape
     out = torch.empty(E, C, dtype=BF16, device=m.device)
     with torch.cuda.device(m.device):
-        _abi.check(_abi.load_library().pfs_wide_source_dm_seg(ct.byref(seg.struct), m.data_ptr(), moments.data_ptr(),
+        _abi.check(_abi.load_library().pfs_wide_source_dm_seg(ct.byref(seg.struct), m.data_ptr(), _DT[m.dtype], moments.data_ptr(),
                                                               coef.data_ptr(), C, out.data_ptr(), _stream(m.device)),
                    "pfs_wide_source_dm_seg")
     return out
