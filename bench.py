@@ -10,8 +10,14 @@ gets a gradient.  configs[1] (ONE such graph) needs ~1 us of HBM time, below a k
 so the throughput configuration is the 256-graph batch; the single graph is a
 parity-test case (tests/test_gpu_parity.py::test_full_size_graph_c2).
 
-N > 1 (launched by torchrun, one rank per GPU): data parallel over graph batches, 256 graphs PER
-GPU (weak scaling), weights replicated, one NCCL all-reduce of the flat gradient bucket per step.
+N > 1 (launched by torchrun, one rank per GPU): data parallel over graph batches as BASELINE configs[2]
+states it -- the batch of 256 graphs is split 256/N per GPU (STRONG scaling), weights replicated, one
+NCCL all-reduce of the flat gradient bucket per step.  The step (forward, backward, bucket pack,
+all-reduce) is captured once as a CUDA graph and replayed: at 32 graphs per GPU the ~40 kernel launches
+of a step would otherwise be bound by the host.  The weak-scaling run (256 graphs per GPU) of round 1 is
+kept as the extra key `weak`.  Extra keys of the default run: `c2` (BASELINE configs[1], ONE graph, with
+and without an L2 flush between steps) and `c4` (a 3-step record of BASELINE configs[3], Fdim 128 bf16,
+fibre-sharded over the N GPUs).
 
 Printed JSON line: see the keys at the bottom.  `value` = edges of all ranks / device time (CUDA
 events, max over ranks, inputs resident in HBM); `e2e` = the same through the nn.Module API with
@@ -44,12 +50,17 @@ KERNEL_ROWS = {
     "k_target_edge_bwd": (2, 2), "k_source_node_fwd": (0, 22), "k_source_node_bwd": (0, 32),
     "k_source_node_fwd_mma": (0, 22), "k_source_node_bwd_mma": (0, 32),
 }
-# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` captures of
-# the default C3 workload (profiles/r01_ncu_full_c3_top7.txt, r01_ncu_full_fma_path.txt); reported as `roofline.traffic`
-# for that workload only
-KERNEL_TRAFFIC_C3 = {"k_edge_bwd": 1404.0e6, "k_edge_bwd2": 1405.4e6, "k_source_edge_bwd": 1341.0e6, "k_source_node_bwd": 766.2e6,
-                     "k_source_node_bwd_mma": 766.5e6, "k_source_node_fwd_mma": 497.7e6, "k_edge_fwd": 655.6e6,
-                     "k_source_edge_fwd": 502.8e6, "k_target_edge_bwd": 955.4e6}
+# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) come from profiles/ncu_traffic.json, written by
+# tools/ncu_traffic.py from an `ncu --set full` capture of the default C3 workload and stamped with the commit the
+# capture was taken at; a kernel that is not in the file reports traffic null
+def kernel_traffic():
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
 # executed multiply-accumulates per edge / per fibre, forward + backward, in units of F^2
 MAC_PER_EDGE_F2 = 60
 MAC_PER_FIBRE_F2 = 318
@@ -61,7 +72,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--graphs", type=int, default=256, help="graphs per GPU")
+    ap.add_argument("--graphs", type=int, default=256, help="graphs of the whole batch (split over the GPUs)")
+    ap.add_argument("--no-graph", action="store_true", help="c3: launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-extras", action="store_true", help="c3: skip the weak / c2 / c4 extra records")
     ap.add_argument("--fibres", type=int, default=2394)
     ap.add_argument("--classes", type=int, default=12)
     ap.add_argument("--fdim", type=int, default=10)
@@ -180,8 +193,9 @@ def cpu_reference(args, seconds, steps=None, warmup=1):
         elif time.perf_counter() - t_begin >= seconds and len(times) >= 3:
             break
     total = sum(times)
-    return E * len(times) / total, ncores, "%d of the %d graphs (%dx%d, Fdim %d, fp32), one after the other, %.1f s" % (
-        len(times), args.graphs, S, T, F, total), total / len(times)
+    return E * len(times) / total, ncores, ("%d forward+backward passes of one %dx%d graph (Fdim %d, fp32), one after the other as the "
+                                            "reference runs its graphs; the batch is %d such graphs; %.1f s of CPU work"
+                                            % (len(times), S, T, F, args.graphs, total)), total / len(times)
 
 
 def run_reference(args):
@@ -195,11 +209,12 @@ def run_reference(args):
     ms_per_step = sec_per_graph * per_step_graphs * 1e3
     line = {
         "impl": "reference", "metric": METRIC, "value": eps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C3: 256 x complete bipartite 2394x12, Fdim 10, Block fwd+bwd (each CPU step = a bounded "
-                               "sample of %d graphs)" % per_step_graphs,
-                   "graphs_per_gpu": args.graphs, "fibres": args.fibres, "classes": args.classes, "fdim": args.fdim},
+        "config": {"workload": "C3: batch of %d complete bipartite %dx%d graphs, Fdim %d, one Block fwd+bwd, train mode (CPU: each "
+                               "step is a bounded sample of %d graphs of the batch, one after the other on all host cores)"
+                               % (args.graphs, args.fibres, args.classes, args.fdim, per_step_graphs),
+                   "global_graphs": args.graphs, "fibres": args.fibres, "classes": args.classes, "fdim": args.fdim},
         "cpu_baseline": {"value": eps, "unit": UNIT, "cores": ncores, "kind": "port", "sample": sample},
         "e2e": {"value": eps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
@@ -210,12 +225,12 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------
 # end-to-end leg shared by all workloads
 # ---------------------------------------------------------------------------------------------
-def pipelined_e2e(dev, host, like, run_step, timed, k):
-    """Every step copies ITS inputs from pinned host memory and returns its loss to the host.  The copies run on a
-    second stream into a double-buffered device input set, so the H2D of step i+1 overlaps the kernels of step i; the
-    loss goes back through a pinned buffer and is read one step late (an event per step), so the host never stalls the
-    device inside the timed region.  All k copies-in and k reads-back happen inside it.  Returns ms per step."""
-    dbufs = [[torch.empty_like(x) for x in like] for _ in range(2)]
+def pipelined_e2e(dev, host, sets, steppers, timed, k):
+    """Every step copies ITS inputs from pinned host memory and returns its result to the host.  The copies run on a
+    second stream into one of two device input sets (sets[i] is read by steppers[i], a callable returning the step's
+    device scalar), so the H2D of step i+1 overlaps the kernels of step i; the result goes back through a pinned buffer
+    and is read one step late (an event per step), so the host never stalls the device inside the timed region.  All k
+    copies-in and k reads-back happen inside it.  Returns ms per step."""
     copy_stream = torch.cuda.Stream(dev)
     copied = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
@@ -226,7 +241,7 @@ def pipelined_e2e(dev, host, like, run_step, timed, k):
     def issue_copy(slot):
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[slot])          # the step that last used this slot is done with it
-            for d, h in zip(dbufs[slot], host):
+            for d, h in zip(sets[slot], host):
                 d.copy_(h, non_blocking=True)
             copied[slot].record(copy_stream)
 
@@ -240,11 +255,11 @@ def pipelined_e2e(dev, host, like, run_step, timed, k):
             if i + 1 < n:
                 issue_copy(slot ^ 1)                          # next step's inputs (copied afresh every step)
             cur.wait_event(copied[slot])
-            loss = run_step(dbufs[slot])
+            loss = steppers[slot]()
             consumed[slot].record(cur)
             loss_host[slot].copy_(loss.detach().float().reshape(1), non_blocking=True)   # device -> host result
             loss_ready[slot].record(cur)
-            if i > 0:                                         # read the previous step's loss on the host
+            if i > 0:                                         # read the previous step's result on the host
                 loss_ready[slot ^ 1].synchronize()
                 losses.append(float(loss_host[slot ^ 1][0]))
         last = (n - 1) & 1
@@ -252,7 +267,7 @@ def pipelined_e2e(dev, host, like, run_step, timed, k):
         losses.append(float(loss_host[last][0]))
 
     run(2)
-    ms, _ = timed(lambda: run(k), 1)
+    ms = timed(lambda: run(k), 1)
     return ms / k
 
 
@@ -275,6 +290,82 @@ def build_block(F, dev):
     return blk.to(dev).train()
 
 
+def numa_bind(local_rank):
+    """Bind this rank to the CPUs of its GPU's NUMA node before any pinned buffer is allocated (first touch then puts
+    the buffers on that node): with every rank on node 0 the host->device feed of 8 GPUs collapsed in round 1."""
+    info = {"node": None}
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
+            node = int(f.read().strip())
+        info["pci"] = bdf
+        info["node"] = node
+        if node >= 0:
+            with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+                cpus = set()
+                for part in f.read().strip().split(","):
+                    lo, _, hi = part.partition("-")
+                    cpus.update(range(int(lo), int(hi or lo) + 1))
+            cpus &= os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                info["cpus_bound"] = len(cpus)
+    except Exception as e:          # best effort: an unknown topology leaves the affinity alone
+        info["error"] = str(e)[:80]
+    return info
+
+
+class BlockStepper:
+    """One data-parallel step of the layer: Block forward + backward w.r.t. all four outputs on static inputs, then
+    the flat-bucket all-reduce; optionally captured as a CUDA graph (the NCCL all-reduce is a node of the graph)."""
+
+    def __init__(self, blk, ei, xs, ups, bucket, dev, use_graph, warmup=3, pool=None):
+        self.blk, self.ei, self.xs, self.ups, self.bucket, self.dev = blk, ei, xs, ups, bucket, dev
+        self.out = None
+        self.graph = None
+        if use_graph:
+            cur = torch.cuda.current_stream(dev)
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for _ in range(warmup):
+                    self.eager()
+            cur.wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, pool=pool):
+                self.eager()
+        else:
+            for _ in range(warmup):
+                self.eager()
+
+    def eager(self):
+        for p in self.blk.parameters():
+            p.grad = None
+        xs = [x.detach().requires_grad_(True) for x in self.xs]
+        _, o_s, o_t, o_e, o_u = self.blk((self.ei, xs[0], xs[1], xs[2], xs[3]))
+        torch.autograd.backward([o_s, o_t, o_e, o_u], self.ups)
+        self.bucket.all_reduce()
+        self.out = o_u.detach().sum()        # the step's result (what the end-to-end leg reads back); no autograd graph kept
+        return self.out
+
+    def __call__(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.eager()
+        return self.out
+
+
+def make_inputs(G, S, T, E, F, dev, seed):
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    shapes = [(G, S, F), (G, T, F), (G, E, F), (G, 1, F)]
+    ins = [torch.randn(s, generator=gen, device=dev) for s in shapes]
+    ups = [torch.linspace(0.5, 1.5, s[1] * s[2], device=dev).reshape(1, s[1], s[2]).expand(s).contiguous() for s in shapes]
+    return ins, ups
+
+
 def run_ours(args):
     import torch.distributed as dist
     from pfs_neural_net_b200 import _abi, dp
@@ -285,18 +376,21 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the message-passing layer has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = numa_bind(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _abi.load_library()
-    G, S, T, F = args.graphs, args.fibres, args.classes, args.fdim
+    S, T, F = args.fibres, args.classes, args.fdim
     E = S * T
+    G_total = args.graphs
+    G = max(1, G_total // world)                 # BASELINE configs[2]: the batch is split over the GPUs
     blk = build_block(F, dev)
     bucket = dp.GradBucket(blk.parameters())
     if world > 1:
         dp.broadcast_parameters(blk)
     if args.workload == "c5a":
         # BASELINE configs[4]: general sparse edge_index, 10% density, shuffled (SURVEY.md 8d "C5")
-        G, S, T = 1, 100000, 512
+        G, G_total, S, T = 1, world, 100000, 512
         gsp = torch.Generator().manual_seed(7)
         e = torch.nonzero(torch.rand(S * T, generator=gsp) < 0.1).flatten()
         e = e[torch.randperm(e.numel(), generator=gsp)]
@@ -304,19 +398,8 @@ def run_ours(args):
         E = int(e.numel())
     else:
         ei = torch.cartesian_prod(torch.arange(S), torch.arange(T)).T.contiguous().to(dev)   # reference src/train.py:94
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    shapes = [(G, S, F), (G, T, F), (G, E, F), (G, 1, F)]
-    ins = [torch.randn(s, generator=gen, device=dev) for s in shapes]
-    ups = [torch.linspace(0.5, 1.5, s[1] * s[2], device=dev).reshape(1, s[1], s[2]).expand(s).contiguous() for s in shapes]
-
-    def step(xs):
-        for p in blk.parameters():
-            p.grad = None
-        xs = [x.requires_grad_(True) for x in xs]
-        _, o_s, o_t, o_e, o_u = blk((ei, xs[0], xs[1], xs[2], xs[3]))
-        torch.autograd.backward([o_s, o_t, o_e, o_u], ups)
-        bucket.all_reduce()
-        return o_u
+    use_graph = not args.no_graph
+    ins, ups = make_inputs(G, S, T, E, F, dev, 1234 + rank)
 
     def barrier():
         if world > 1:
@@ -326,40 +409,43 @@ def run_ours(args):
     def timed(fn, k):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n0 = lib.pfs_launch_count()
         e0.record()
         for _ in range(k):
             fn()
         e1.record()
         torch.cuda.synchronize(dev)
         ms = e0.elapsed_time(e1)
-        launches = lib.pfs_launch_count() - n0
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         barrier()
-        return ms, launches
+        return ms
 
-    detached = [x.detach() for x in ins]
+    # kernels of one step (counted on an eager step: a graph replay launches the same kernels without host calls)
+    eager = BlockStepper(blk, ei, ins, ups, bucket, dev, use_graph=False, warmup=max(args.warmup, 3))
+    n0 = lib.pfs_launch_count()
+    eager()
+    launches_per_step = int(lib.pfs_launch_count() - n0)
+    stepper = BlockStepper(blk, ei, ins, ups, bucket, dev, use_graph=True, warmup=1) if use_graph else eager
     for _ in range(max(args.warmup, 3)):
-        step([x.detach() for x in detached])
+        stepper()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ms, launches = timed(lambda: step([x.detach() for x in detached]), args.steps)
+    ms = timed(stepper, args.steps)
     clocks = sampler.stop()
     ms_per_step = ms / args.steps
     edges_total = float(E) * G * world
     value = edges_total / (ms_per_step * 1e-3)
 
-    # ---- per-kernel durations (CUDA events on the launch stream), same steps --------------------
+    # ---- per-kernel durations (CUDA events on the launch stream), eager steps ------------------------
     hbm_gbs, peak_src, sm_max = measured_peaks()
     roofline, kernels = None, None
     if not args.no_profile:
         lib.pfs_profile_enable(1)
         torch.cuda.synchronize(dev)
         for _ in range(args.steps):
-            step([x.detach() for x in detached])
+            eager()
         torch.cuda.synchronize(dev)
         rep = _abi.profile_report()
         lib.pfs_profile_enable(0)
@@ -374,11 +460,13 @@ def run_ours(args):
             bytes_per_launch = 4.0 * F * (per_e * E + per_s * S) * G
             dur_s = tms / n * 1e-3
             achieved = bytes_per_launch / dur_s / 1e9
+            tr = kernel_traffic()
+            same = args.workload == "c3" and (G, S, T, F) == (256, 2394, 12, 10)
             roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s",
                         "frac": achieved / hbm_gbs,
-                        "traffic": KERNEL_TRAFFIC_C3.get(top) if (args.workload == "c3" and (G, S, T, F) == (256, 2394, 12, 10))
-                        else None,
-                        "traffic_source": "ncu --set full capture under profiles/ (bytes per launch)", "peak_source": peak_src,
+                        "traffic": tr.get("kernels", {}).get(top) if same else None,
+                        "traffic_source": ("ncu --set full capture at commit %s (%s)" % (tr.get("commit"), tr.get("file")))
+                        if same and tr else None, "peak_source": peak_src,
                         "avg_launch_ms": tms / n, "algorithmic_bytes_per_launch": bytes_per_launch,
                         "share_of_step": tms / tot, "binding": "fp32_fma (see fma)"}
     step_bytes = ((5.0 * F * 4 + (16 if args.workload == "c5a" else 0)) * E + 6.0 * (S + T) * F * 4) * G
@@ -392,24 +480,37 @@ def run_ours(args):
                      "unit": "GB/s", "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_gbs,
                      "algorithmic_bytes_per_step": step_bytes}
 
-    # ---- end to end: pinned host inputs in, loss out, every step (pipelined_e2e) ----------------------
+    # ---- end to end: pinned host inputs in, result out, every step ---------------------------------------
+    # two input sets, each with its own captured step: the H2D copy of step i+1 (copy stream) overlaps step i
     e2e = None
     if not args.no_e2e:
         host = [x.detach().cpu().pin_memory() for x in ins]
         h2d = sum(h.numel() * h.element_size() for h in host)
-
-        def e2e_step(dbuf):
-            for p in blk.parameters():
-                p.grad = None
-            xs = [d.detach().requires_grad_(True) for d in dbuf]
-            _, o_s, o_t, o_e, o_u = blk((ei, xs[0], xs[1], xs[2], xs[3]))
-            torch.autograd.backward([o_s, o_t, o_e, o_u], ups)      # the same upstream gradients as the device-timed step
-            bucket.all_reduce()
-            return o_u.sum()                                        # the step's result read back by the host
-
-        ms_e = pipelined_e2e(dev, host, detached, e2e_step, timed, max(3, args.steps))
+        sets = [ins, [torch.empty_like(x) for x in ins]]
+        pool = stepper.graph.pool() if use_graph else None
+        steppers = [stepper, BlockStepper(blk, ei, sets[1], ups, bucket, dev, use_graph=use_graph, warmup=1, pool=pool)]
+        ms_e = pipelined_e2e(dev, host, sets, steppers, timed, max(3, args.steps))
         e2e = {"value": edges_total / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-               "ms_per_step": ms_e, "pipelined": E2E_NOTE}
+               "ms_per_step": ms_e, "pipelined": E2E_NOTE, "h2d_gbs_per_gpu": h2d / (ms_e * 1e-3) / 1e9,
+               "result_read_back": "sum of the updated global features (4 bytes), as a training loop reads its loss"}
+        del steppers, sets, host
+
+    extras = {}
+    if args.workload == "c3" and not args.no_extras:
+        # ---- weak scaling (round 1's definition: 256 graphs per GPU), N > 1 only; at N = 1 it IS the headline ----
+        if world > 1:
+            stepper = eager = None
+            torch.cuda.empty_cache()
+            ins_w, ups_w = make_inputs(G_total, S, T, E, F, dev, 1234 + rank)
+            st_w = BlockStepper(blk, ei, ins_w, ups_w, bucket, dev, use_graph=use_graph, warmup=3)
+            ms_w = timed(st_w, args.steps) / args.steps
+            extras["weak"] = {"graphs_per_gpu": G_total, "ms_per_step": ms_w, "value": float(E) * G_total * world / (ms_w * 1e-3),
+                              "unit": UNIT, "scaling": "weak"}
+            del st_w, ins_w, ups_w
+            torch.cuda.empty_cache()
+        # ---- C2: BASELINE configs[1], ONE 2394x12 graph (latency-bound by construction) ----
+        if world == 1:
+            extras["c2"] = c2_record(args, blk, ei, bucket, dev, lib, hbm_gbs)
 
     # ---- CPU baseline (rank 0, N = 1) ------------------------------------------------------------------
     cpu = None
@@ -417,24 +518,80 @@ def run_ours(args):
         eps, ncores, sample, _ = cpu_reference(args, seconds=args.cpu_seconds)
         cpu = {"value": eps, "unit": UNIT, "cores": ncores, "kind": "port", "sample": sample}
 
+    # ---- C4 (Fdim 128, bf16, tcgen05 path): a short record inside the driver-run line ----------------------
+    if args.workload == "c3" and not args.no_extras:
+        stepper = eager = ins = ups = None            # release the C3 tensors and the captured graph's pool
+        torch.cuda.empty_cache()
+        try:
+            extras["c4"] = wide_record(args, "c4", world, rank, local_rank, dev, steps=3, warmup=3, with_e2e=False,
+                                       with_cpu=False, with_profile=True)
+        except Exception as e:                       # the headline line must survive a failure of the extra
+            extras["c4"] = {"error": repr(e)[:200]}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": ("C3: %d x complete bipartite %dx%d per GPU, Fdim %d, one Block fwd+bwd, train mode"
-                                    % (G, S, T, F)) if args.workload == "c3" else
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if args.workload == "c3" else "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": ("C3: batch of %d complete bipartite %dx%d graphs split over %d GPU(s) (%d per GPU), Fdim %d, "
+                                    "one Block fwd+bwd, train mode" % (G * world, S, T, world, G, F)) if args.workload == "c3" else
                                    ("C5a: 10%% Bernoulli edge list of %d x %d (%d edges, shuffled; CSR/CSC segmented "
                                     "reductions), Fdim %d fp32, one Block fwd+bwd" % (S, T, E, F)),
                        "graphs_per_gpu": G, "global_graphs": G * world, "fibres": S, "classes": T, "fdim": F,
                        "edges_per_step": edges_total, "parallelism": "dp%d" % world,
-                       "l2": "inputs larger than L2 (x_e %.0f MB per step)" % (G * E * F * 4 / 1e6)},
+                       "launch": "one CUDA-graph replay per step (forward, backward, bucket pack, NCCL all-reduce)" if use_graph
+                       else "eager launches",
+                       "l2": "inputs larger than L2 (x_e %.0f MB per step per GPU)" % (G * E * F * 4 / 1e6)
+                       if G * E * F * 4 > 126e6 else
+                       "x_e is %.0f MB per GPU, below the 126 MB L2: every step reads the inputs the previous step left "
+                       "in L2 (see c2 for the flushed variant of one graph)" % (G * E * F * 4 / 1e6)},
             "roofline": roofline, "step_roofline": step_roofline, "fma": fma, "kernels": kernels,
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+            "gpu_launches_per_step": launches_per_step, "clocks": clocks, "numa": numa,
         }
+        line.update(extras)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def c2_record(args, blk, ei, bucket, dev, lib, hbm_gbs):
+    """BASELINE configs[1]: one complete 2394x12 graph, Fdim 10, one Block forward+backward; graph replay and eager,
+    with the inputs left in L2 by the previous step and with an L2 flush (a 512 MB write) before every step."""
+    S, T, F = args.fibres, args.classes, args.fdim
+    E = S * T
+    ins, ups = make_inputs(1, S, T, E, F, dev, 4321)
+    out = {"workload": "C2: one complete bipartite %dx%d graph, Fdim %d, fp32, one Block fwd+bwd" % (S, T, F), "edges": E}
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    n = 50
+    for mode in ("graph", "eager"):
+        st = BlockStepper(blk, ei, ins, ups, bucket, dev, use_graph=(mode == "graph"), warmup=3)
+        for _ in range(5):
+            st()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            st()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        warm = e0.elapsed_time(e1) / n
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(20)]
+        for a, b in evs:
+            flush.zero_()                      # evicts the inputs and the workspace from the 126 MB L2
+            a.record()
+            st()
+            b.record()
+        torch.cuda.synchronize(dev)
+        cold = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+        out[mode] = {"ms_per_step": warm, "edges_per_s": E / (warm * 1e-3), "ms_per_step_l2_flushed": cold,
+                     "edges_per_s_l2_flushed": E / (cold * 1e-3)}
+        del st
+    alg = (5.0 * F * 4) * E + 6.0 * (S + T) * F * 4
+    out["hbm_frac_l2_flushed"] = alg / (out["graph"]["ms_per_step_l2_flushed"] * 1e-3) / 1e9 / hbm_gbs
+    out["note"] = ("6.3 MB of algorithmic traffic = ~1 us of HBM time: the step is bound by the dependent chain of its kernels "
+                   "(launch / drain latency), not by bandwidth or FLOPs")
+    return out
 
 
 # ---------------------------------------------------------------------------------------------
@@ -444,10 +601,10 @@ WIDE_MAC_PER_EDGE_F2 = 48     # executed: fwd 16 F^2 (five GEMMs), bwd 32 F^2 (i
 WIDE_MAC_PER_FIBRE_F2 = 318
 
 
-def wide_graph(args, rank, world, dev):
+def wide_graph(args, workload, rank, world, dev):
     """(edge_index of this rank's shard, S_local, T, E_local, description)."""
     T, S = args.wide_classes, args.wide_fibres
-    if args.workload == "c4":
+    if workload == "c4":
         ei = torch.cartesian_prod(torch.arange(S), torch.arange(T)).T.contiguous().to(dev)
         return ei, S, T, S * T, "C4: complete bipartite %d x %d (fibre range of %d per GPU), Fdim %d, bf16" % (
             S * world, T, S, args.wide_fdim)
@@ -487,7 +644,6 @@ def cpu_reference_wide(args, S_sub, seconds):
 
 def run_wide(args):
     import torch.distributed as dist
-    from pfs_neural_net_b200 import _abi, gnn, shard
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -507,12 +663,26 @@ def run_wide(args):
         raise SystemExit("bench.py needs a CUDA device: the message-passing layer has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    sharded = world > 1 and args.workload == "c4"
+    numa_bind(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    rec = wide_record(args, args.workload, world, rank, local_rank, dev, steps=args.steps, warmup=args.warmup,
+                      with_e2e=not args.no_e2e, with_cpu=not args.no_cpu_baseline, with_profile=not args.no_profile)
+    if rank == 0:
+        print(json.dumps(rec))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def wide_record(args, workload, world, rank, local_rank, dev, steps, warmup, with_e2e, with_cpu, with_profile):
+    """One bench record of a wide workload (c4: fibre-sharded over the ranks; c5: replicas); the process group, if
+    any, is already initialised.  Returns the record on every rank (rank 0 prints it)."""
+    import torch.distributed as dist
+    from pfs_neural_net_b200 import _abi, gnn, shard
+    sharded = world > 1 and workload == "c4"
     lib = _abi.load_library()
     F = args.wide_fdim
-    ei, S, T, E, desc = wide_graph(args, rank, world, dev)
+    ei, S, T, E, desc = wide_graph(args, workload, rank, world, dev)
     torch.manual_seed(0)
     blk = gnn.Block(F)
     g = torch.Generator().manual_seed(1)
@@ -562,16 +732,16 @@ def run_wide(args):
         return ms, launches
 
     detached = [x.detach() for x in ins]
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         step([x.detach() for x in detached])
     shard.reset_traffic()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ms, launches = timed(lambda: step([x.detach() for x in detached]), args.steps)
+    ms, launches = timed(lambda: step([x.detach() for x in detached]), steps)
     clocks = sampler.stop()
     coll_calls, coll_bytes = shard.traffic()
-    ms_per_step = ms / args.steps
-    edges_total = float(E) * (world if args.workload == "c4" or world == 1 else world)
+    ms_per_step = ms / steps
+    edges_total = float(E) * (world if workload == "c4" or world == 1 else world)
     value = edges_total / (ms_per_step * 1e-3)
     hbm_gbs, peak_src, sm_max = measured_peaks()
     try:
@@ -582,10 +752,10 @@ def run_wide(args):
         tensor_peak, tpeak_src = 1387.0, "fallback (B200_PROFILING.md)"
     flops = 2.0 * F * F * (WIDE_MAC_PER_EDGE_F2 * E + WIDE_MAC_PER_FIBRE_F2 * S)
     kernels, roofline = None, None
-    if not args.no_profile:
+    if with_profile:
         lib.pfs_profile_enable(1)
         torch.cuda.synchronize(dev)
-        nprof = min(args.steps, 5)
+        nprof = min(steps, 5)
         for _ in range(nprof):
             step([x.detach() for x in detached])
         torch.cuda.synchronize(dev)
@@ -601,13 +771,13 @@ def run_wide(args):
                     "frac": achieved / tensor_peak if achieved else None, "traffic": None, "peak_source": tpeak_src,
                     "gemm_ms_per_step": gemm_ms, "share_of_step": gemm_ms * nprof / tot,
                     "executed_flops_per_step": flops}
-    step_bytes = (5.0 * F * 2 + (0 if args.workload == "c4" else 16)) * E + 6.0 * (S + T) * F * 2
+    step_bytes = (5.0 * F * 2 + (0 if workload == "c4" else 16)) * E + 6.0 * (S + T) * F * 2
     step_roofline = {"bound": "hbm", "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9, "peak": hbm_gbs, "unit": "GB/s",
                      "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_gbs, "algorithmic_bytes_per_step": step_bytes}
     tensor = {"executed_tflops": flops / (ms_per_step * 1e-3) / 1e12, "peak_tflops": tensor_peak,
               "frac": flops / (ms_per_step * 1e-3) / 1e12 / tensor_peak, "peak_source": tpeak_src}
     e2e = None
-    if not args.no_e2e:
+    if with_e2e:
         host = [x.detach().cpu().pin_memory() for x in ins]
         h2d = sum(h.numel() * h.element_size() for h in host)
 
@@ -620,44 +790,47 @@ def run_wide(args):
                 torch.autograd.backward([o_s, o_t, o_e, o_u], ups)
             return o_u.float().sum()
 
-        ms_e = pipelined_e2e(dev, host, detached, e2e_step, timed, max(3, args.steps))
+        sets = [detached, [torch.empty_like(x) for x in detached]]
+        ms_e = pipelined_e2e(dev, host, sets, [lambda: e2e_step(sets[0]), lambda: e2e_step(sets[1])],
+                             lambda fn, k: timed(fn, k)[0], max(3, steps))
         e2e = {"value": edges_total / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                "ms_per_step": ms_e, "pipelined": E2E_NOTE}
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and with_cpu:
         eps, ncores, sample = cpu_reference_wide(args, 48, seconds=args.cpu_seconds)
         cpu = {"value": eps, "unit": UNIT, "cores": ncores, "kind": "port", "sample": sample}
-    if rank == 0:
-        print(json.dumps({
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-            "data": "synthetic",
-            "config": {"workload": desc, "fibres_per_gpu": S, "classes": T, "fdim": F, "edges_per_step": edges_total,
-                       "parallelism": ("fibre-sharded x%d (class-side all-reduces: %d calls, %d bytes per step)"
-                                       % (world, coll_calls // max(args.steps, 1), coll_bytes // max(args.steps, 1)))
-                       if sharded else "single GPU" if world == 1 else "replicas x%d" % world,
-                       "l2": "inputs larger than L2 (x_e %.0f MB per step)" % (E * F * 2 / 1e6)},
-            "roofline": roofline, "step_roofline": step_roofline, "tensor": tensor, "kernels": kernels, "cpu_baseline": cpu,
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}))
-    if world > 1:
-        dist.destroy_process_group()
+    return {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": desc, "fibres_per_gpu": S, "classes": T, "fdim": F, "edges_per_step": edges_total,
+                   "parallelism": ("fibre-sharded x%d (class-side all-reduces: %d calls, %d bytes per step)"
+                                   % (world, coll_calls // max(steps, 1), coll_bytes // max(steps, 1)))
+                   if sharded else "single GPU" if world == 1 else "replicas x%d" % world,
+                   "l2": "inputs larger than L2 (x_e %.0f MB per step)" % (E * F * 2 / 1e6)},
+        "roofline": roofline, "step_roofline": step_roofline, "tensor": tensor, "kernels": kernels, "cpu_baseline": cpu,
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
 
 
 # ---------------------------------------------------------------------------------------------
 # N1: the training loss that follows the path (reference src/train.py:21-80), forward + backward
 # ---------------------------------------------------------------------------------------------
+def complete_bipartite(S, T):
+    """canonical dense edge order of reference src/train.py:94"""
+    return torch.cartesian_prod(torch.arange(S), torch.arange(T)).T.contiguous()
+
+
 def run_loss(args):
-    from pfs_neural_net_b200 import _abi, loss as pl
-    from oracle import block_oracle as bo, loss_oracle as lo
     S, T = args.fibres * args.graphs, args.classes            # one graph with the edge count of the C3 batch
     E = S * T
     g = torch.Generator().manual_seed(1)
     class_info = torch.stack([0.5 + 3 * torch.rand(T, generator=g), 50 + 400 * torch.rand(T, generator=g)], 1)
     if args.impl == "reference":
+        from oracle import loss_oracle as lo                    # CPU arm only
         Sc = 20000
         ncores = os.cpu_count() or 1
         torch.set_num_threads(ncores)
-        ei = bo.complete_bipartite(Sc, T)
+        ei = complete_bipartite(Sc, T)
         time_c, noise_c = 6 * torch.rand(Sc * T, generator=g), torch.rand(Sc * T, generator=g)
         ts = []
         for _ in range(args.warmup + args.steps):
@@ -674,6 +847,7 @@ def run_loss(args):
                           "cpu_baseline": {"value": eps, "unit": UNIT, "cores": ncores, "kind": "port", "sample": "%d steps" % len(ts)},
                           "e2e": {"value": eps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
         return
+    from pfs_neural_net_b200 import _abi, loss as pl
     dev = torch.device("cuda", 0)
     lib = _abi.load_library()
     ci = class_info.to(dev)
@@ -722,16 +896,15 @@ PUBLISHED_TRAIN_ITS = 65.86      # it/s, 1x A100, reference slurm/slurm-2561734.
 
 
 def run_train(args):
-    from oracle import block_oracle as bo
     S, T, F, B = 2000, 12, 10, 3
     g = torch.Generator().manual_seed(1)
     class_info = torch.stack([0.5 + 3 * torch.rand(T, generator=g), 50 + 400 * torch.rand(T, generator=g)], 1)
     x_s = torch.arange(S, dtype=torch.float32).reshape(-1, 1)
     x_e = 2 + 8 * torch.rand(S * T, F, generator=g)
-    ei = bo.complete_bipartite(S, T)
+    ei = complete_bipartite(S, T)
     desc = "reference training step: %d x %d graph, Fdim %d, %d Blocks, loss_function, Adam (src/train.py:136-141)" % (S, T, F, B)
     if args.impl == "reference":
-        from oracle import loss_oracle as lo
+        from oracle import block_oracle as bo, loss_oracle as lo      # CPU arm only
         ncores = os.cpu_count() or 1
         torch.set_num_threads(ncores)
         torch.manual_seed(0)

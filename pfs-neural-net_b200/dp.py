@@ -21,7 +21,12 @@ def shard_graphs(num_graphs, rank, world_size):
 
 
 class GradBucket:
-    """Flat fp32 bucket over `params` (registration order): pack -> all_reduce(sum) -> unpack."""
+    """Flat fp32 bucket over `params` (registration order): pack -> all_reduce(sum) -> the parameters' `.grad`
+    become VIEWS of the reduced bucket (no copy back).
+
+    pack is one multi-tensor copy (plus a zero fill of the slices whose gradient is None on this rank, so that
+    every rank reduces the same layout); nothing is launched per parameter after the collective.  The whole
+    sequence is CUDA-graph capturable (static bucket, no host synchronisation)."""
 
     def __init__(self, params, process_group=None):
         self.params = [p for p in params if p.requires_grad]
@@ -38,29 +43,38 @@ class GradBucket:
         self.group = process_group
 
     def pack(self):
-        have = [(v, p.grad) for v, p in zip(self.views, self.params) if p.grad is not None]
+        have = [(v, p.grad) for v, p in zip(self.views, self.params)
+                if p.grad is not None and p.grad.data_ptr() != v.data_ptr()]
         miss = [v for v, p in zip(self.views, self.params) if p.grad is None]
         if have:
             torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
-        for v in miss:
-            v.zero_()
+        if miss:
+            torch._foreach_zero_(miss)
 
     def unpack(self):
+        """Point every parameter's gradient at its slice of the bucket (fp32 parameters: a view, no copy)."""
         for v, p in zip(self.views, self.params):
-            if p.grad is None:
-                p.grad = v.clone()
+            if p.dtype == torch.float32:
+                p.grad = v
+            elif p.grad is None:
+                p.grad = v.to(p.dtype)
             else:
                 p.grad.copy_(v)
 
+    def world(self):
+        if not (dist.is_available() and dist.is_initialized()):
+            return 1
+        return dist.get_world_size(self.group)
+
     def all_reduce(self, average=False):
-        """Sum (or average) the gradients of all ranks in place; a no-op without an initialised
-        process group or with a single rank."""
-        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
+        """Sum (or average) the gradients of all ranks; a no-op without an initialised process group or with a
+        single rank.  Afterwards `p.grad` is a view of the bucket."""
+        if self.world() == 1:
             return
         self.pack()
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
         if average:
-            self.flat.div_(dist.get_world_size(self.group))
+            self.flat.div_(self.world())
         self.unpack()
 
 
