@@ -94,7 +94,10 @@ def test_fibre_sharded_block_matches_single_gpu():
         for k in full:
             if k.startswith("p."):
                 scale_key = k[:-4] + "weight" if k.endswith("bias") else k
-                den = max(full[k].abs().max().item(), 1e-3 * full[scale_key].abs().max().item())
+                # a bias in front of a train-mode BatchNorm (edge_model.2, node_mlp_2.2) has an analytically zero gradient:
+                # both runs hold rounding noise there, judged on the scale of the weight gradient like the parity tests
+                zero_grad = k.endswith(("edge_model.2.bias", "node_mlp_2.2.bias"))
+                den = max(full[k].abs().max().item(), (1.0 if zero_grad else 1e-3) * full[scale_key].abs().max().item())
                 err = (out[r][k] - full[k]).abs().max().item() / den
                 assert err < 3e-2, (k, err)
             if k.startswith("b.") and not k.endswith("num_batches_tracked"):

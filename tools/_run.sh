@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_dp.py -x -q -m gpu 2>&1 | tail -5 > gpurun_out/r02_pytest3.txt
-python bench.py --steps 10 --warmup 3 > gpurun_out/r02_bench_c3_a.json 2> gpurun_out/r02_bench_c3_a.err
+python -m pytest tests/test_gpu_wide_shard.py -x -q -m gpu 2>&1 | grep -E "Error|assert|err" | head -20 > gpurun_out/r02_pytest_n2b.txt
+PFS_WIDE_PREC=none python -m pytest tests/test_gpu_wide_shard.py -x -q -m gpu 2>&1 | grep -E "Error|assert|err|passed|failed" | head -20 >> gpurun_out/r02_pytest_n2b.txt
