@@ -12,6 +12,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include "edge_model.cuh"
+#include "edge_fwd_tc.cuh"
 #include "node_ops.cuh"
 #include "source_model.cuh"
 #include "source_node_c.cuh"
@@ -135,8 +136,19 @@ int num_sms() {
 template <class Kern>
 int persistent_grid(Kern kern, size_t smem, long long items, int threads = kThreads) {
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm < 1)
+    const cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
+    static const bool dbg = getenv("PFS_DEBUG_GRID") != nullptr;
+    if (dbg) {
+        cudaFuncAttributes fa{};
+        (void)cudaFuncGetAttributes(&fa, kern);
+        fprintf(stderr, "[pfs] occupancy: %d blocks/SM (threads %d, smem %zu, err %s; regs %d, static smem %zu, max dyn %d, local %zu)\n",
+                per_sm, threads, smem, cudaGetErrorString(oe), fa.numRegs, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes,
+                fa.localSizeBytes);
+    }
+    if (oe != cudaSuccess || per_sm < 1) {
+        (void)cudaGetLastError();
         per_sm = 1;
+    }
     long long g = (long long)per_sm * num_sms();
     if (g > kMaxCtas) g = kMaxCtas;
     if (g > items) g = items;
@@ -250,6 +262,19 @@ bool node_bwd_mma_enabled() {
         v = (e && e[0] == '0') ? 0 : 1;
     }
     return v == 1 && node_mma_enabled();
+}
+
+// PFS_EDGE_TC=1 runs the EdgeModel forward of the dense layout on the tcgen05 kernel (edge_fwd_tc.cuh) instead of the
+// FFMA2 kernel.  Off by default: measured at C3 (profiles/r02_edge_tc_vs_fma.txt) the tensor-core version takes 0.75 ms
+// against 0.40 ms -- at K = 10 / 40, N = 40 / 10 the MMAs are bound by re-reading the 128-row A operand from shared
+// memory and by the per-tile issue -> commit -> tcgen05.ld round trips, not by the tensor pipe.
+bool edge_tc_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PFS_EDGE_TC");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
 }
 
 bool edge_bwd_lean_enabled() {
@@ -462,10 +487,31 @@ int edge_fwd_impl(const pfs_edge_args& a, const Topo& tp) {
     const int max_fib = max_fibres_per_tile(tp);
     const bool sc = stage_class_table(tp, H);
     size_t smem = 0;
-    const int nbuf = pick_nbuf([&](int nb) { return sizeof(float) * TileStage<F, 1, H, H>::floats(max_fib, tp.T, sc, nb); }, smem);
-    if (!nbuf) return fail(PFS_ERR_UNSUPPORTED, "edge_fwd: tile staging does not fit shared memory");
-    PFS_TRY(allow_smem(k_edge_fwd<F>, smem));
-    const int grid = persistent_grid(k_edge_fwd<F>, smem, total);
+    // dense layout: both MLP layers on tcgen05 (edge_fwd_tc.cuh) when the tile's node-table rows fit its register
+    // prefetch (2 float4 of P_s rows and 1 of P_t per thread)
+    using TC = EdgeFwdTc<F>;
+    const bool tc = TC::fits && tp.layout == PFS_LAYOUT_DENSE && edge_tc_enabled() && max_fib * (H / 4) <= 2 * kThreads &&
+                    tp.T * (H / 4) <= kThreads && sizeof(float) * TC::floats(max_fib, tp.T) <= kSmemLimit;
+    int nbuf = 1;
+    if (tc) {
+        smem = sizeof(float) * TC::floats(max_fib, tp.T);
+        PFS_TRY(allow_smem(k_edge_fwd_tc<F>, smem));
+    } else {
+        nbuf = pick_nbuf([&](int nb) { return sizeof(float) * TileStage<F, 1, H, H>::floats(max_fib, tp.T, sc, nb); }, smem);
+        if (!nbuf) return fail(PFS_ERR_UNSUPPORTED, "edge_fwd: tile staging does not fit shared memory");
+        PFS_TRY(allow_smem(k_edge_fwd<F>, smem));
+    }
+    // the occupancy calculator reports 1 CTA per SM for a kernel that allocates tensor memory whatever its footprint
+    // (measured: 128 registers, 99 KB -> 1; the FFMA2 kernel with 128 registers, 113 KB -> 2); the tcgen05 kernel takes
+    // 128 of the 512 TMEM columns, so two (three where shared memory allows) CTAs do fit
+    int grid;
+    if (tc) {
+        const int per_sm = smem <= 75 * 1024 ? 3 : smem <= 113 * 1024 ? 2 : 1;
+        grid = per_sm * num_sms();
+        if (grid > total) grid = total;
+    } else {
+        grid = persistent_grid(k_edge_fwd<F>, smem, total);
+    }
     const int nrec = chunk_records(grid, total, tp.ntiles);
     Bump ws(a.workspace, a.workspace_bytes);
     float* uvec = ws.f((size_t)tp.G * H);
@@ -475,18 +521,21 @@ int edge_fwd_impl(const pfs_edge_args& a, const Topo& tp) {
     float* wstage = ws.f(kConstFloats);
     if (!ws.ok) return fail(PFS_ERR_WORKSPACE, "edge_fwd: workspace too small (%zu B)", a.workspace_bytes);
     PFS_TRY(edge_tables<F>(a, tp, uvec, Ps, Pt, st));
-    {
+    const bool stats = a.normed && a.training;
+    EdgeFwdParams p{tp, a.x_e, Ps, Pt, a.w1, a.w2, a.b2, a.x_e_out, stats ? part : nullptr, max_fib, sc ? 1 : 0, nrec, nbuf, a.act_save};
+    if (tc) {
+        k_edge_fwd_tc<F><<<grid, kThreads, smem, st>>>(p);     // weights go straight from global into the MMA operands
+        PFS_LAUNCH_CHECK("k_edge_fwd_tc");
+    } else {
         PackList pl{};
         pl.it[0] = PackItem{a.w1, H, 2 * F, F, H, 1, 0};            // W1_e input-major [F][H]
         pl.it[1] = PackItem{a.w2, H, 0, H, F, 1, F * H};            // W2 input-major [H][F]
         pl.it[2] = PackItem{a.b2, 1, 0, 1, F, 0, 2 * F * H};        // b2
         pl.n = 3;
         PFS_TRY(upload_weights(pl, 2 * F * H + F, wstage, st));
+        k_edge_fwd<F><<<grid, kThreads, smem, st>>>(p);
+        PFS_LAUNCH_CHECK("k_edge_fwd");
     }
-    const bool stats = a.normed && a.training;
-    EdgeFwdParams p{tp, a.x_e, Ps, Pt, a.w1, a.w2, a.b2, a.x_e_out, stats ? part : nullptr, max_fib, sc ? 1 : 0, nrec, nbuf};
-    k_edge_fwd<F><<<grid, kThreads, smem, st>>>(p);
-    PFS_LAUNCH_CHECK("k_edge_fwd");
     if (a.normed) {
         PFS_REQUIRE(a.gamma && a.beta && a.bn_save, "normed edge model needs gamma, beta, bn_save");
         PFS_TRY(bn_forward_tail(F, tp.G, tp.E, part, tp.ntiles, 1, a.training, a.gamma, a.beta, a.running_mean,
@@ -509,7 +558,8 @@ int edge_bwd_impl(const pfs_edge_args& a, const Topo& tp) {
     // its tiles fit 113 KB; PFS_EDGE_BWD_LEAN=0 selects the double-buffered one-CTA-per-SM kernel (A/B runs).
     // Measured at C3: 1.21 ms against 1.60 ms.
     const bool lean = SM::lean_fits && edge_bwd_lean_enabled();
-    auto kern = lean ? k_edge_bwd2<F> : k_edge_bwd<F>;
+    const bool saved = lean && a.act_save != nullptr;      // hidden activations saved by the forward: no recompute, no node tables
+    auto kern = lean ? (saved ? k_edge_bwd2<F, true> : k_edge_bwd2<F, false>) : k_edge_bwd<F>;
     const int max_fib = max_fibres_per_tile(tp);
     const bool sc = stage_class_table(tp, H);
     size_t smem_bwd = SM::bytes_lean;
@@ -538,7 +588,7 @@ int edge_bwd_impl(const pfs_edge_args& a, const Topo& tp) {
     float* opart = ws.f((size_t)kMaxCtas * (H * F + H));
     float* wstage = ws.f(kConstFloats);
     if (!ws.ok) return fail(PFS_ERR_WORKSPACE, "edge_bwd: workspace too small (%zu B)", a.workspace_bytes);
-    PFS_TRY(edge_tables<F>(a, tp, uvec, Ps, Pt, st));
+    if (!saved) PFS_TRY(edge_tables<F>(a, tp, uvec, Ps, Pt, st));
     {
         using CW = EdgeBwdConst<F>;
         PackList pl{};
@@ -568,7 +618,8 @@ int edge_bwd_impl(const pfs_edge_args& a, const Topo& tp) {
     }
     const bool dense = tp.layout == PFS_LAYOUT_DENSE;
     EdgeBwdParams p{tp, a.x_e, a.x_e_out, a.g_out, Ps, Pt, coef, a.g_x_e, dPs,
-                    dense ? stage : nullptr, dense ? nullptr : stage, wpart, pstride, max_fib, sc ? 1 : 0, nbuf};
+                    dense ? stage : nullptr, dense ? nullptr : stage, wpart, pstride, max_fib, sc ? 1 : 0, nbuf,
+                    saved ? a.act_save : nullptr};
     kern<<<grid, kThreads, smem_bwd, st>>>(p);
     if (lean) {
         PFS_LAUNCH_CHECK("k_edge_bwd2");
@@ -611,7 +662,8 @@ int source_fwd_impl(const pfs_source_args& a, const Topo& tp) {
     if (!ws.ok) return fail(PFS_ERR_WORKSPACE, "source_fwd: workspace too small (%zu B)", a.workspace_bytes);
     PFS_TRY((node_linear<F, M>(a.x_t, tp.T, tp.G, a.w1, M, 0, a.b1, nullptr, Qt, st)));
     {
-        SourceEdgeFwdParams p{tp, a.x_e, Qt, a.w1, a.w2, a.b2, a.moments};
+        PFS_REQUIRE((a.act_save == nullptr) == (a.msg_save == nullptr), "act_save and msg_save go together");
+        SourceEdgeFwdParams p{tp, a.x_e, Qt, a.w1, a.w2, a.b2, a.moments, a.act_save, a.msg_save};
         PFS_TRY(upload_msg_weights<F>(a.w1, a.w2, a.b2, wstage, st));
         const int grid = persistent_grid(k_source_edge_fwd<F>, 0, total);
         k_source_edge_fwd<F><<<grid, kThreads, 0, st>>>(p);
@@ -678,7 +730,8 @@ int source_bwd_impl(const pfs_source_args& a, const Topo& tp) {
     constexpr bool kNodeC = SourceNodeConst<F>::fits;
     constexpr bool kNodeMma = SourceNodeBwdMma<F>::fits;
     const bool use_mma = kNodeMma && node_bwd_mma_enabled();
-    auto ke = k_source_edge_bwd<F>;
+    const bool saved = a.act_save != nullptr && a.msg_save != nullptr;
+    auto ke = saved ? k_source_edge_bwd<F, true> : k_source_edge_bwd<F, false>;
     PFS_TRY(allow_smem(ke, SME::bytes));
     int gridn = 0;
     if (use_mma) {
@@ -765,11 +818,11 @@ int source_bwd_impl(const pfs_source_args& a, const Topo& tp) {
     PFS_TRY(colsum_all(tot3, tp.G, J, 0, J, a.g_b3, st));
     PFS_TRY(outer_graphs(tot3, a.u, tp.G, J, F, a.g_w3, J, K9, st));
     PFS_TRY((node_linear_bwd<F, J>(tot3, tp.G, a.w3, J, K9, a.g_u, st)));
-    PFS_TRY((node_linear<F, M>(a.x_t, tp.T, tp.G, a.w1, M, 0, a.b1, nullptr, Qt, st)));
+    if (!saved) PFS_TRY((node_linear<F, M>(a.x_t, tp.T, tp.G, a.w1, M, 0, a.b1, nullptr, Qt, st)));
     {
         const bool dense = tp.layout == PFS_LAYOUT_DENSE;
         SourceEdgeBwdParams p{tp, a.x_e, Qt, a.w1, a.w2, a.b2, a.moments, coefA, a.g_x_e, a.g_x_e_add,
-                              dense ? stage : nullptr, dense ? nullptr : stage, wpe, pstride_e};
+                              dense ? stage : nullptr, dense ? nullptr : stage, wpe, pstride_e, a.act_save, a.msg_save};
         PFS_TRY(upload_msg_weights<F>(a.w1, a.w2, a.b2, wstage, st));
         ke<<<gride, kThreads, SME::bytes, st>>>(p);
         PFS_LAUNCH_CHECK("k_source_edge_bwd");
@@ -824,7 +877,7 @@ int target_fwd_impl(const pfs_target_args& a, const Topo& tp) {
     PFS_TRY((node_linear<F, M>(a.x_s, tp.S, tp.G, a.w1, M, 0, a.b1, nullptr, Rs, st)));
     {
         const bool dense = tp.layout == PFS_LAYOUT_DENSE;
-        TargetEdgeFwdParams p{tp, a.x_e, Rs, a.w1, dense ? stage : nullptr, dense ? nullptr : stage};
+        TargetEdgeFwdParams p{tp, a.x_e, Rs, a.w1, dense ? stage : nullptr, dense ? nullptr : stage, a.act_save};
         PFS_TRY(upload_msg_weights<F>(a.w1, nullptr, nullptr, wstage, st));
         const int grid = persistent_grid(k_target_edge_fwd<F>, 0, total);
         k_target_edge_fwd<F><<<grid, kThreads, 0, st>>>(p);
@@ -854,7 +907,8 @@ int target_bwd_impl(const pfs_target_args& a, const Topo& tp) {
     prof_mark(nullptr, st);
     const int total = tp.ntiles * tp.G;
     using SM = TargetEdgeBwdSmem<F>;
-    auto ke = k_target_edge_bwd<F>;
+    const bool saved = a.act_save != nullptr;
+    auto ke = saved ? k_target_edge_bwd<F, true> : k_target_edge_bwd<F, false>;
     PFS_TRY(allow_smem(ke, SM::bytes));
     const int gride = persistent_grid(ke, SM::bytes, total);
     constexpr int pstride_e = M * F;
@@ -892,9 +946,9 @@ int target_bwd_impl(const pfs_target_args& a, const Topo& tp) {
         }
         PFS_TRY(rd.run(gpart, tp.G, ptail, st));
     }
-    PFS_TRY((node_linear<F, M>(a.x_s, tp.S, tp.G, a.w1, M, 0, a.b1, nullptr, Rs, st)));
+    if (!saved) PFS_TRY((node_linear<F, M>(a.x_s, tp.S, tp.G, a.w1, M, 0, a.b1, nullptr, Rs, st)));
     {
-        TargetEdgeBwdParams p{tp, a.x_e, Rs, a.w1, dasum, a.g_x_e, a.g_x_e_add, dRs, wpe, pstride_e};
+        TargetEdgeBwdParams p{tp, a.x_e, Rs, a.w1, dasum, a.g_x_e, a.g_x_e_add, dRs, wpe, pstride_e, a.act_save};
         PFS_TRY(upload_msg_weights<F>(a.w1, nullptr, nullptr, wstage, st));
         ke<<<gride, kThreads, SM::bytes, st>>>(p);
         PFS_LAUNCH_CHECK("k_target_edge_bwd");

@@ -28,6 +28,8 @@ struct SourceEdgeFwdParams {
     const float* Qt;       // [G,T,2F] = x_t . W1[:, :F]^T + b1
     const float *w1, *w2, *b2;
     float* moments;        // [G,S,5,2F]: mean, E[m^2], c2, c3, c4
+    float* act_save;       // [G,E(q),2F] hidden activations for the backward, or null
+    float* msg_save;       // [G,E(q),2F] messages for the backward, or null
 };
 
 template <int F>
@@ -52,6 +54,11 @@ __global__ void __launch_bounds__(kThreads) k_source_edge_fwd(const SourceEdgeFw
                 m[j] = c_w[CW::kB2 + j];
             }
             dense_acc_c<M, M, CW::kW2t>(h, m);
+            if (p.act_save) {
+                const size_t q = ((size_t)t.g * tp.E + t.q0 + threadIdx.x) * M;
+                store_row<M>(p.act_save + q, h);
+                store_row<M>(p.msg_save + q, m);
+            }
 #pragma unroll
             for (int j = 0; j < M; ++j) MT[j * LDT + threadIdx.x] = m[j];
         }
@@ -465,6 +472,7 @@ struct SourceEdgeBwdParams {
     float* dhs_rows;                // general: [G,E(q),2F]
     float* wpartial;                // [ncta][pstride]: dW1_e [2F*F], dW2 [2F*2F], db2 [2F]
     int pstride;
+    const float *act_save, *msg_save;   // [G,E(q),2F] each, saved by the forward (k_source_edge_bwd<F, true>)
 };
 
 template <int F>
@@ -476,7 +484,9 @@ struct SourceEdgeBwdSmem {
     static constexpr size_t bytes = sizeof(float) * (kWeights + kTiles);
 };
 
-template <int F>
+// SAVED: the hidden activations a = lrelu(h) and the messages m are read back (act_save / msg_save of the forward)
+// instead of being recomputed; lrelu' is read off the sign of a
+template <int F, bool SAVED>
 __global__ void __launch_bounds__(kThreads, (F <= 10 ? 2 : 1)) k_source_edge_bwd(const SourceEdgeBwdParams p) {
     using SM = SourceEdgeBwdSmem<F>;
     constexpr int M = 2 * F, LDM = SM::LDM, LDF = SM::LDF;
@@ -507,21 +517,33 @@ __global__ void __launch_bounds__(kThreads, (F <= 10 ? 2 : 1)) k_source_edge_bwd
             if (p.g_add) bulk_prefetch_l2(p.g_add + off, bytes);
             bulk_prefetch_l2(p.coefA + frow * 4 * M, (size_t)tn.nfib * 4 * M * sizeof(float));
             bulk_prefetch_l2(p.moments + frow * 5 * M, (size_t)tn.nfib * 5 * M * sizeof(float));
+            if (SAVED) {
+                bulk_prefetch_l2(p.act_save + off * 2, bytes * 2);
+                bulk_prefetch_l2(p.msg_save + off * 2, bytes * 2);
+            }
         }
         if (threadIdx.x < t.ne) {
             const EdgeRef er = get_edge(tp, t, threadIdx.x);
             const size_t row = ((size_t)t.g * tp.E + er.e) * F;
             float x[F], h[M], m[M];
             load_row<F>(p.xe2 + row, x);
-            load_row<M>(p.Qt + ((size_t)t.g * tp.T + er.tgt) * M, h);
-            dense_acc_c<F, M, CW::kW1t>(x, h);
             float a[M];
+            if constexpr (SAVED) {
+                const size_t q = ((size_t)t.g * tp.E + t.q0 + threadIdx.x) * M;
+                load_row<M>(p.act_save + q, a);
+                load_row<M>(p.msg_save + q, m);
 #pragma unroll
-            for (int j = 0; j < M; ++j) {
-                a[j] = lrelu(h[j]);
-                m[j] = c_w[CW::kB2 + j];
+                for (int j = 0; j < M; ++j) h[j] = a[j];          // only the sign is used below
+            } else {
+                load_row<M>(p.Qt + ((size_t)t.g * tp.T + er.tgt) * M, h);
+                dense_acc_c<F, M, CW::kW1t>(x, h);
+#pragma unroll
+                for (int j = 0; j < M; ++j) {
+                    a[j] = lrelu(h[j]);
+                    m[j] = c_w[CW::kB2 + j];
+                }
+                dense_acc_c<M, M, CW::kW2t>(a, m);
             }
-            dense_acc_c<M, M, CW::kW2t>(a, m);
             // dm = (A0 + A1 m + A2 d^2 + A3 d^3) / count
             int e0, n;
             fibre_range(tp, t, er.src - t.fibre0, e0, n);

@@ -12,8 +12,22 @@ import torch
 
 from . import _abi
 
+import os
+
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
+# PFS_SAVE_ACT=1 keeps the per-edge hidden activations (and the SModel messages) of a training forward for the backward
+# instead of recomputing them (+16F + 16F + 8F bytes per edge of HBM, ~30 % fewer instructions in the three backward edge
+# kernels).  OFF by default -- measured at C3 (profiles/r02_save_act_vs_recompute.txt) it LOSES: the forward kernels slow
+# down by the extra row stores (k_edge_fwd 0.40 -> 0.70 ms, k_source_edge_fwd 0.34 -> 0.48, k_target_edge_fwd 0.15 ->
+# 0.22) and the backward kernels do not speed up (k_edge_bwd2 1.19 -> 1.24 ms): they wait on their per-thread row loads,
+# of which there are now more, not on instruction issue.  Step 5.38 -> 5.82 ms.
+SAVE_ACT = os.environ.get("PFS_SAVE_ACT", "0") == "1"
+
+
+def _want_save(ctx):
+    """a backward will follow (some input needs a gradient and grad mode was on at apply time)"""
+    return SAVE_ACT and any(ctx.needs_input_grad)
 RMS_EPS = float(torch.finfo(torch.float32).eps)    # nn.RMSNorm(eps=None), reference src/gnn.py:203
 
 
@@ -139,28 +153,30 @@ class EdgeFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, topo, training, normed, x_s, x_t, x_e, u, w1, b1, w2, b2, gamma, beta, rm, rv, nbt):
         dev = _dev_check(x_s, x_t, x_e, u, w1, b1, w2, b2, gamma, beta, rm, rv)
+        ctx.save_act = _want_save(ctx)
         x_s, x_t, x_e, u, w1, b1, w2, b2, gamma, beta = (_c(t) for t in (x_s, x_t, x_e, u, w1, b1, w2, b2, gamma, beta))
         G, F = _check_shapes(topo, x_s, x_t, x_e, u)
         lib = _abi.load_library()
         out = torch.empty_like(x_e)
         bn_save = torch.empty(G, 4, F, device=dev, dtype=torch.float32) if normed else None
+        act = torch.empty(G, topo.E, 4 * F, device=dev, dtype=torch.float32) if ctx.save_act else None
         a = _abi.EdgeArgs()
         ws = _fill_common(a, topo, G, F, dict(x_s=x_s, x_t=x_t, x_e=x_e, u=u, w1=w1, b1=b1, w2=w2, b2=b2, gamma=gamma,
                                               beta=beta, running_mean=rm, running_var=rv, num_batches_tracked=nbt,
-                                              x_e_out=out, bn_save=bn_save))
+                                              x_e_out=out, bn_save=bn_save, act_save=act))
         a.training, a.normed, a.eps, a.momentum = int(training), int(normed), BN_EPS, BN_MOMENTUM
         with torch.cuda.device(dev):
             a.stream = _stream(dev)
             _abi.check(lib.pfs_edge_fwd(ct.byref(a)), "pfs_edge_fwd")
         ctx.topo, ctx.training, ctx.normed = topo, training, normed
         ctx.buffers = (rm, rv)
-        ctx.save_for_backward(x_s, x_t, x_e, u, w1, b1, w2, b2, gamma, beta, out, bn_save)
+        ctx.save_for_backward(x_s, x_t, x_e, u, w1, b1, w2, b2, gamma, beta, out, bn_save, act)
         del ws
         return out
 
     @staticmethod
     def backward(ctx, g):
-        x_s, x_t, x_e, u, w1, b1, w2, b2, gamma, beta, out, bn_save = ctx.saved_tensors
+        x_s, x_t, x_e, u, w1, b1, w2, b2, gamma, beta, out, bn_save, act = ctx.saved_tensors
         topo, dev = ctx.topo, x_e.device
         G, F = x_s.shape[0], x_s.shape[2]
         lib = _abi.load_library()
@@ -173,7 +189,7 @@ class EdgeFunction(torch.autograd.Function):
         a = _abi.EdgeArgs()
         rm, rv = ctx.buffers
         named = dict(x_s=x_s, x_t=x_t, x_e=x_e, u=u, w1=w1, b1=b1, w2=w2, b2=b2, gamma=gamma, beta=beta,
-                     running_mean=rm, running_var=rv, x_e_out=out, bn_save=bn_save, g_out=g)
+                     running_mean=rm, running_var=rv, x_e_out=out, bn_save=bn_save, act_save=act, g_out=g)
         named.update(gr)
         ws = _fill_common(a, topo, G, F, named)
         a.training, a.normed, a.eps, a.momentum = int(ctx.training), int(ctx.normed), BN_EPS, BN_MOMENTUM
@@ -191,12 +207,15 @@ class SourceFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, topo, training, normed, x_s, x_t, x_e, u, w1, b1, w2, b2, w3, b3, w4, b4, gamma, beta, rm, rv, nbt, bus=None):
         dev = _dev_check(x_s, x_t, x_e, u, w1, b1, w2, b2, w3, b3, w4, b4, gamma, beta, rm, rv)
+        save_act = _want_save(ctx)
         (x_s, x_t, x_e, u, w1, b1, w2, b2, w3, b3, w4, b4, gamma, beta) = (
             _c(t) for t in (x_s, x_t, x_e, u, w1, b1, w2, b2, w3, b3, w4, b4, gamma, beta))
         G, F = _check_shapes(topo, x_s, x_t, x_e, u)
         lib = _abi.load_library()
         f32 = dict(device=dev, dtype=torch.float32)
         out = torch.empty_like(x_s)
+        act = torch.empty(G, topo.E, 2 * F, **f32) if save_act else None
+        msg = torch.empty(G, topo.E, 2 * F, **f32) if save_act else None
         moments = torch.empty(G, topo.S, 5, 2 * F, **f32)
         hidden = torch.empty(G, topo.S, 10 * F, **f32)
         y_pre = torch.empty(G, topo.S, F, **f32)
@@ -205,7 +224,7 @@ class SourceFunction(torch.autograd.Function):
         ws = _fill_common(a, topo, G, F, dict(
             x_s=x_s, x_t=x_t, x_e=x_e, u=u, w1=w1, b1=b1, w2=w2, b2=b2, w3=w3, b3=b3, w4=w4, b4=b4, gamma=gamma,
             beta=beta, running_mean=rm, running_var=rv, num_batches_tracked=nbt, x_s_out=out, moments=moments,
-            hidden=hidden, y_pre=y_pre, bn_save=bn_save))
+            hidden=hidden, y_pre=y_pre, bn_save=bn_save, act_save=act, msg_save=msg))
         a.training, a.normed, a.eps, a.momentum = int(training), int(normed), BN_EPS, BN_MOMENTUM
         with torch.cuda.device(dev):
             a.stream = _stream(dev)
@@ -214,14 +233,14 @@ class SourceFunction(torch.autograd.Function):
         ctx.bus = bus
         ctx.buffers = (rm, rv)
         ctx.save_for_backward(x_s, x_t, x_e, u, w1, b1, w2, b2, w3, b3, w4, b4, gamma, beta, moments, hidden, y_pre,
-                              bn_save)
+                              bn_save, act, msg)
         del ws
         return out
 
     @staticmethod
     def backward(ctx, g):
         (x_s, x_t, x_e, u, w1, b1, w2, b2, w3, b3, w4, b4, gamma, beta, moments, hidden, y_pre,
-         bn_save) = ctx.saved_tensors
+         bn_save, act, msg) = ctx.saved_tensors
         topo, dev = ctx.topo, x_e.device
         G, F = x_s.shape[0], x_s.shape[2]
         lib = _abi.load_library()
@@ -235,7 +254,7 @@ class SourceFunction(torch.autograd.Function):
         rm, rv = ctx.buffers
         named = dict(x_s=x_s, x_t=x_t, x_e=x_e, u=u, w1=w1, b1=b1, w2=w2, b2=b2, w3=w3, b3=b3, w4=w4, b4=b4,
                      gamma=gamma, beta=beta, running_mean=rm, running_var=rv, moments=moments, hidden=hidden,
-                     y_pre=y_pre, bn_save=bn_save, g_out=g)
+                     y_pre=y_pre, bn_save=bn_save, act_save=act, msg_save=msg, g_out=g)
         add = ctx.bus.addend_for_source(x_e) if ctx.bus is not None else None
         named.update(gr, g_x_e_add=add)
         a = _abi.SourceArgs()
@@ -256,12 +275,14 @@ class TargetFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, topo, training, normed, x_s, x_t, x_e, u, w1, b1, w2, b2, w3, b3, w4, b4, gamma, beta, rm, rv, nbt, bus=None):
         dev = _dev_check(x_s, x_t, x_e, u, w1, b1, w2, b2, w3, b3, w4, b4, gamma, beta, rm, rv)
+        save_act = _want_save(ctx)
         (x_s, x_t, x_e, u, w1, b1, w2, b2, w3, b3, w4, b4, gamma, beta) = (
             _c(t) for t in (x_s, x_t, x_e, u, w1, b1, w2, b2, w3, b3, w4, b4, gamma, beta))
         G, F = _check_shapes(topo, x_s, x_t, x_e, u)
         lib = _abi.load_library()
         f32 = dict(device=dev, dtype=torch.float32)
         out = torch.empty_like(x_t)
+        act = torch.empty(G, topo.E, 2 * F, **f32) if save_act else None
         act_sum = torch.empty(G, topo.T, 2 * F, **f32)
         y_pre = torch.empty(G, topo.T, F, **f32)
         bn_save = torch.empty(G, 4, F, **f32) if normed else None
@@ -269,7 +290,7 @@ class TargetFunction(torch.autograd.Function):
         ws = _fill_common(a, topo, G, F, dict(
             x_s=x_s, x_t=x_t, x_e=x_e, u=u, w1=w1, b1=b1, w2=w2, b2=b2, w3=w3, b3=b3, w4=w4, b4=b4, gamma=gamma,
             beta=beta, running_mean=rm, running_var=rv, num_batches_tracked=nbt, x_t_out=out, act_sum=act_sum,
-            y_pre=y_pre, bn_save=bn_save))
+            y_pre=y_pre, bn_save=bn_save, act_save=act))
         a.training, a.normed, a.eps, a.momentum = int(training), int(normed), BN_EPS, BN_MOMENTUM
         with torch.cuda.device(dev):
             a.stream = _stream(dev)
@@ -277,13 +298,13 @@ class TargetFunction(torch.autograd.Function):
         ctx.topo, ctx.training, ctx.normed = topo, training, normed
         ctx.bus = bus
         ctx.buffers = (rm, rv)
-        ctx.save_for_backward(x_s, x_t, x_e, u, w1, b1, w2, b2, w3, b3, w4, b4, gamma, beta, act_sum, y_pre, bn_save)
+        ctx.save_for_backward(x_s, x_t, x_e, u, w1, b1, w2, b2, w3, b3, w4, b4, gamma, beta, act_sum, y_pre, bn_save, act)
         del ws
         return out
 
     @staticmethod
     def backward(ctx, g):
-        (x_s, x_t, x_e, u, w1, b1, w2, b2, w3, b3, w4, b4, gamma, beta, act_sum, y_pre, bn_save) = ctx.saved_tensors
+        (x_s, x_t, x_e, u, w1, b1, w2, b2, w3, b3, w4, b4, gamma, beta, act_sum, y_pre, bn_save, act) = ctx.saved_tensors
         topo, dev = ctx.topo, x_e.device
         G, F = x_s.shape[0], x_s.shape[2]
         lib = _abi.load_library()
@@ -297,7 +318,7 @@ class TargetFunction(torch.autograd.Function):
         rm, rv = ctx.buffers
         named = dict(x_s=x_s, x_t=x_t, x_e=x_e, u=u, w1=w1, b1=b1, w2=w2, b2=b2, w3=w3, b3=b3, w4=w4, b4=b4,
                      gamma=gamma, beta=beta, running_mean=rm, running_var=rv, act_sum=act_sum, y_pre=y_pre,
-                     bn_save=bn_save, g_out=g)
+                     bn_save=bn_save, act_save=act, g_out=g)
         add = ctx.bus.addend_for_target(x_e) if ctx.bus is not None else None
         named.update(gr, g_x_e_add=add)
         a = _abi.TargetArgs()
