@@ -226,13 +226,12 @@ int upload_weights(const PackList& pl, int nfloats, float* staging, cudaStream_t
     return PFS_OK;
 }
 
-// message-MLP weights of the SModel / TModel edge kernels -> constant bank (common.cuh: MsgEdgeConst)
+// message-MLP weights of the SModel / TModel edge kernels (common.cuh: MsgEdgeConst) appended to a pack list
 template <int F>
-int upload_msg_weights(const float* w1, const float* w2, const float* b2, float* wstage, cudaStream_t st) {
+void add_msg_weights(PackList& pl, const float* w1, const float* w2, const float* b2) {
     using CW = MsgEdgeConst<F>;
     constexpr int M = 2 * F;
-    PackList pl{};
-    int n = 0;
+    int n = pl.n;
     pl.it[n++] = PackItem{w1, M, F, F, M, 1, CW::kW1t};       // W1[:, F:] input-major [F][M]
     pl.it[n++] = PackItem{w1, M, F, F, M, 0, CW::kW1o};       // W1[:, F:] as stored [M][F]
     if (w2) {
@@ -241,7 +240,33 @@ int upload_msg_weights(const float* w1, const float* w2, const float* b2, float*
     }
     if (b2) pl.it[n++] = PackItem{b2, 1, 0, 1, M, 0, CW::kB2};
     pl.n = n;
-    return upload_weights(pl, CW::kFloats, wstage, st);
+}
+
+// Prologue of a module call: node tables + weight packing in ONE launch (node_ops.cuh: k_prep), then ONE copy of the
+// packed weights into the constant bank.  Either part may be empty.
+template <int F, int J>
+int run_prep(int G, const TableJob* jobs, int njobs, const float* W, int ldw, const float* u, const PackList& pl,
+             int nfloats, float* wstage, cudaStream_t st) {
+    if (nfloats > kConstFloats) return fail(PFS_ERR_UNSUPPORTED, "weights (%d floats) exceed the constant bank", nfloats);
+    PrepParams p{};
+    long long maxn = 0;
+    for (int q = 0; q < njobs; ++q) {
+        p.job[q] = jobs[q];
+        const long long n = (long long)jobs[q].rows * G;
+        maxn = n > maxn ? n : maxn;
+    }
+    p.njobs = njobs; p.G = G; p.W = W; p.ldw = ldw; p.u = u; p.pl = pl; p.stage = wstage;
+    p.pack_blocks = pl.n > 0 ? 8 : 0;
+    long long tb = njobs > 0 ? (maxn + kThreads - 1) / kThreads : 0;
+    if (tb > 4LL * num_sms()) tb = 4LL * num_sms();
+    if (njobs > 0 && tb < 1) tb = 1;
+    const int grid = p.pack_blocks + (int)tb;
+    if (grid == 0) return PFS_OK;
+    k_prep<F, J><<<grid, kThreads, 0, st>>>(p);
+    PFS_LAUNCH_CHECK("k_prep");
+    if (pl.n > 0)
+        PFS_CUDA(cudaMemcpyToSymbolAsync(c_w, wstage, sizeof(float) * (size_t)nfloats, 0, cudaMemcpyDeviceToDevice, st));
+    return PFS_OK;
 }
 
 // PFS_NODE_MMA=0 switches the fibre MLP back from the tcgen05 kernel to the FMA kernel (A/B runs)
@@ -365,6 +390,12 @@ int colsum_all(const float* x, long long N, int ld, int off, int J, float* out, 
     PFS_LAUNCH_CHECK("k_colsum_all");
     return PFS_OK;
 }
+// two column blocks of one [N, ld] matrix in one launch: out0 = sum of x[:, off0 : off0 + J], out1 = of x[:, off1 : off1 + J]
+int colsum_pair(const float* x, long long N, int ld, int off0, float* out0, int off1, float* out1, int J, cudaStream_t st) {
+    k_colsum_pair<<<dim3((J + 31) / 32, 2), dim3(32, 8), 0, st>>>(x, N, ld, off0, out0, off1, out1, J);
+    PFS_LAUNCH_CHECK("k_colsum_all");
+    return PFS_OK;
+}
 int colsum_graph(const float* x, int rows, int J, int G, float* out, cudaStream_t st) {
     k_colsum_graph<<<dim3((J + 31) / 32, G), dim3(32, 8), 0, st>>>(x, rows, J, out);
     PFS_LAUNCH_CHECK("k_colsum_graph");
@@ -434,19 +465,11 @@ int bn_forward_tail(int F, int G, long long rows, const float* partial, int ntil
     const int n = G * F;
     if (training) {
         if (rows <= 1) return fail(PFS_ERR_ARG, "Expected more than 1 value per channel when training");
-        if (rec_ncta > 0) {
-            k_bn_finalize_rec<<<(n + 127) / 128, 128, 0, st>>>(partial, rec_ncta, rec_nrec, ntiles, F, G, gamma, beta,
-                                                                eps, twice, save);
-            PFS_LAUNCH_CHECK("k_bn_finalize_rec");
-        } else {
-            k_bn_finalize<<<(n + 127) / 128, 128, 0, st>>>(partial, ntiles, bn_partial_stride(F), F, G, gamma, beta,
-                                                            eps, twice, save);
-            PFS_LAUNCH_CHECK("k_bn_finalize");
-        }
-        if (rm && rv) {
-            k_bn_running<<<F, 32, 0, st>>>(save, F, G, rows, gamma, beta, eps, momentum, twice, rm, rv, nbt);
-            PFS_LAUNCH_CHECK("k_bn_running");
-        }
+        if (F > 32) return fail(PFS_ERR_UNSUPPORTED, "BatchNorm finalisation handles up to 32 features");
+        BnFinalizeAll fa{partial, rec_ncta, rec_nrec, ntiles, bn_partial_stride(F), F, G, twice, gamma, beta, eps, momentum, rows,
+                         save, rm, rv, nbt};
+        k_bn_finalize_all<<<1, 1024, 0, st>>>(fa);
+        PFS_LAUNCH_CHECK("k_bn_finalize_all");
     } else {
         PFS_REQUIRE(rm && rv, "eval-mode BatchNorm needs running_mean / running_var");
         k_bn_eval_coeffs<<<(n + 127) / 128, 128, 0, st>>>(rm, rv, F, G, gamma, beta, eps, twice, save);
@@ -469,13 +492,11 @@ int affine_rows(const float* in, const float* save, int F, long long rows, int G
 // ==========================================================================================
 // EdgeModel
 // ==========================================================================================
+// node tables of the EdgeModel's first-layer split: P_s = x_s . W1_s^T, P_t = x_t . W1_t^T + W1_u . u + b1
 template <int F>
-int edge_tables(const pfs_edge_args& a, const Topo& tp, float* uvec, float* Ps, float* Pt, cudaStream_t st) {
-    constexpr int H = 4 * F;
-    PFS_TRY((node_linear<F, H>(a.u, 1, tp.G, a.w1, H, 3 * F, a.b1, nullptr, uvec, st)));
-    PFS_TRY((node_linear<F, H>(a.x_t, tp.T, tp.G, a.w1, H, F, nullptr, uvec, Pt, st)));
-    PFS_TRY((node_linear<F, H>(a.x_s, tp.S, tp.G, a.w1, H, 0, nullptr, nullptr, Ps, st)));
-    return PFS_OK;
+void edge_table_jobs(const pfs_edge_args& a, const Topo& tp, float* Ps, float* Pt, TableJob (&jobs)[2]) {
+    jobs[0] = TableJob{a.x_s, tp.S, 0, -1, nullptr, Ps};
+    jobs[1] = TableJob{a.x_t, tp.T, F, 3 * F, a.b1, Pt};
 }
 
 template <int F>
@@ -520,19 +541,23 @@ int edge_fwd_impl(const pfs_edge_args& a, const Topo& tp) {
     float* part = ws.f((size_t)grid * nrec * bn_partial_stride(F));
     float* wstage = ws.f(kConstFloats);
     if (!ws.ok) return fail(PFS_ERR_WORKSPACE, "edge_fwd: workspace too small (%zu B)", a.workspace_bytes);
-    PFS_TRY(edge_tables<F>(a, tp, uvec, Ps, Pt, st));
+    (void)uvec;
+    TableJob jobs[2];
+    edge_table_jobs<F>(a, tp, Ps, Pt, jobs);
+    PackList pl{};
+    if (!tc) {
+        pl.it[0] = PackItem{a.w1, H, 2 * F, F, H, 1, 0};            // W1_e input-major [F][H]
+        pl.it[1] = PackItem{a.w2, H, 0, H, F, 1, F * H};            // W2 input-major [H][F]
+        pl.it[2] = PackItem{a.b2, 1, 0, 1, F, 0, 2 * F * H};        // b2
+        pl.n = 3;
+    }
+    PFS_TRY((run_prep<F, H>(tp.G, jobs, 2, a.w1, H, a.u, pl, 2 * F * H + F, wstage, st)));
     const bool stats = a.normed && a.training;
     EdgeFwdParams p{tp, a.x_e, Ps, Pt, a.w1, a.w2, a.b2, a.x_e_out, stats ? part : nullptr, max_fib, sc ? 1 : 0, nrec, nbuf, a.act_save};
     if (tc) {
         k_edge_fwd_tc<F><<<grid, kThreads, smem, st>>>(p);     // weights go straight from global into the MMA operands
         PFS_LAUNCH_CHECK("k_edge_fwd_tc");
     } else {
-        PackList pl{};
-        pl.it[0] = PackItem{a.w1, H, 2 * F, F, H, 1, 0};            // W1_e input-major [F][H]
-        pl.it[1] = PackItem{a.w2, H, 0, H, F, 1, F * H};            // W2 input-major [H][F]
-        pl.it[2] = PackItem{a.b2, 1, 0, 1, F, 0, 2 * F * H};        // b2
-        pl.n = 3;
-        PFS_TRY(upload_weights(pl, 2 * F * H + F, wstage, st));
         k_edge_fwd<F><<<grid, kThreads, smem, st>>>(p);
         PFS_LAUNCH_CHECK("k_edge_fwd");
     }
@@ -588,15 +613,17 @@ int edge_bwd_impl(const pfs_edge_args& a, const Topo& tp) {
     float* opart = ws.f((size_t)kMaxCtas * (H * F + H));
     float* wstage = ws.f(kConstFloats);
     if (!ws.ok) return fail(PFS_ERR_WORKSPACE, "edge_bwd: workspace too small (%zu B)", a.workspace_bytes);
-    if (!saved) PFS_TRY(edge_tables<F>(a, tp, uvec, Ps, Pt, st));
     {
+        (void)uvec;
         using CW = EdgeBwdConst<F>;
+        TableJob jobs[2];
+        edge_table_jobs<F>(a, tp, Ps, Pt, jobs);
         PackList pl{};
         pl.it[0] = PackItem{a.w1, H, 2 * F, F, H, 1, CW::kW1t};     // W1_e input-major [F][H]
         pl.it[1] = PackItem{a.w2, H, 0, H, F, 0, CW::kW2o};         // W2 as stored [F][H]
         pl.it[2] = PackItem{a.w1, H, 2 * F, F, H, 0, CW::kW1o};     // W1_e as stored [H][F]
         pl.n = 3;
-        PFS_TRY(upload_weights(pl, CW::kFloats, wstage, st));
+        PFS_TRY((run_prep<F, H>(tp.G, jobs, saved ? 0 : 2, a.w1, H, a.u, pl, CW::kFloats, wstage, st)));
     }
     const int n = tp.G * F;
     k_edge_bn_bwd_coef<<<(n + 127) / 128, 128, 0, st>>>(0, mode, F, tp.G, tp.ntiles, tp.E, a.bn_save, a.gamma, a.beta,
@@ -613,8 +640,7 @@ int edge_bwd_impl(const pfs_edge_args& a, const Topo& tp) {
                                                              a.beta, a.running_mean, a.running_var, a.eps, statsum, coef,
                                                              dgb);
         PFS_LAUNCH_CHECK("k_edge_bn_bwd_coef/1");
-        PFS_TRY(colsum_all(dgb, tp.G, 2 * F, 0, F, a.g_gamma, st));
-        PFS_TRY(colsum_all(dgb, tp.G, 2 * F, F, F, a.g_beta, st));
+        PFS_TRY(colsum_pair(dgb, tp.G, 2 * F, 0, a.g_gamma, F, a.g_beta, F, st));
     }
     const bool dense = tp.layout == PFS_LAYOUT_DENSE;
     EdgeBwdParams p{tp, a.x_e, a.x_e_out, a.g_out, Ps, Pt, coef, a.g_x_e, dPs,
@@ -660,11 +686,27 @@ int source_fwd_impl(const pfs_source_args& a, const Topo& tp) {
     float* partn = ws.f((size_t)tp.G * ntn * bn_partial_stride(F));
     float* wstage = ws.f(kConstFloats);
     if (!ws.ok) return fail(PFS_ERR_WORKSPACE, "source_fwd: workspace too small (%zu B)", a.workspace_bytes);
-    PFS_TRY((node_linear<F, M>(a.x_t, tp.T, tp.G, a.w1, M, 0, a.b1, nullptr, Qt, st)));
+    {
+        // one prologue: the class table Q_t, the message-MLP weights and the node-MLP weights (disjoint regions of the
+        // constant bank: MsgEdgeConst below SourceNodeConst::kBase), one upload
+        TableJob jobs[2] = {TableJob{a.x_t, tp.T, 0, -1, a.b1, Qt}, TableJob{}};
+        PackList pl{};
+        add_msg_weights<F>(pl, a.w1, a.w2, a.b2);
+        int nfloats = MsgEdgeConst<F>::kFloats;
+        if constexpr (SourceNodeConst<F>::fits) {
+            using CW = SourceNodeConst<F>;
+            constexpr int J = 10 * F, K9 = 9 * F;
+            const bool mma = SourceNodeMma<F>::fits && node_mma_enabled();
+            pl.it[pl.n++] = PackItem{a.w4, J, 0, J, F, 1, CW::kW4t};       // W4 input-major [J][F]
+            pl.it[pl.n++] = PackItem{a.b4, 1, 0, 1, F, 0, CW::kB4};
+            if (!mma) pl.it[pl.n++] = PackItem{a.w3, J, 0, K9, J, 1, CW::kW3t};      // W3[:, :9F] input-major [K9][J] (FMA kernel)
+            nfloats = mma ? CW::kFwdMmaFloats : CW::kFwdFloats;
+        }
+        PFS_TRY((run_prep<F, M>(tp.G, jobs, 1, a.w1, M, a.u, pl, nfloats, wstage, st)));
+    }
     {
         PFS_REQUIRE((a.act_save == nullptr) == (a.msg_save == nullptr), "act_save and msg_save go together");
         SourceEdgeFwdParams p{tp, a.x_e, Qt, a.w1, a.w2, a.b2, a.moments, a.act_save, a.msg_save};
-        PFS_TRY(upload_msg_weights<F>(a.w1, a.w2, a.b2, wstage, st));
         const int grid = persistent_grid(k_source_edge_fwd<F>, 0, total);
         k_source_edge_fwd<F><<<grid, kThreads, 0, st>>>(p);
         PFS_LAUNCH_CHECK("k_source_edge_fwd");
@@ -675,14 +717,6 @@ int source_fwd_impl(const pfs_source_args& a, const Topo& tp) {
                               stats ? partn : nullptr, ntn};
         if constexpr (SourceNodeConst<F>::fits) {
             using SM = SourceNodeFwdSmemC<F>;
-            using CW = SourceNodeConst<F>;
-            constexpr int J = 10 * F, K9 = 9 * F;
-            PackList pl{};
-            pl.it[0] = PackItem{a.w3, J, 0, K9, J, 1, CW::kW3t};      // W3[:, :9F] input-major [K9][J]
-            pl.it[1] = PackItem{a.w4, J, 0, J, F, 1, CW::kW4t};       // W4 input-major [J][F]
-            pl.it[2] = PackItem{a.b4, 1, 0, 1, F, 0, CW::kB4};
-            pl.n = 3;
-            PFS_TRY(upload_weights(pl, CW::kFwdFloats, wstage, st));
             if (SourceNodeMma<F>::fits && node_mma_enabled()) {
                 // first layer on tcgen05 (3xTF32), see source_node_mma.cuh
                 auto kern = k_source_node_fwd_mma<F>;
@@ -765,6 +799,21 @@ int source_bwd_impl(const pfs_source_args& a, const Topo& tp) {
     float* opart = ws.f((size_t)kMaxCtas * (M * F + M));
     float* wstage = ws.f(kConstFloats);
     if (!ws.ok) return fail(PFS_ERR_WORKSPACE, "source_bwd: workspace too small (%zu B)", a.workspace_bytes);
+    {
+        // one prologue for the whole backward: Q_t (unless the activations were saved), the node-MLP weights and the
+        // message-MLP weights (disjoint regions of the constant bank), one upload
+        TableJob jobs[2] = {TableJob{a.x_t, tp.T, 0, -1, a.b1, Qt}, TableJob{}};
+        PackList pl{};
+        add_msg_weights<F>(pl, a.w1, a.w2, a.b2);
+        int nfloats = MsgEdgeConst<F>::kFloats;
+        if constexpr (kNodeC) {
+            using CW = SourceNodeConst<F>;
+            pl.it[pl.n++] = PackItem{a.w4, J, 0, J, F, 0, CW::kW4o};       // W4 as stored [F][J]
+            if (!use_mma) pl.it[pl.n++] = PackItem{a.w3, J, 0, K9, J, 0, CW::kW3o};      // W3[:, :9F] as stored [J][K9] (FMA kernel)
+            nfloats = use_mma ? CW::kBwdMmaFloats : CW::kBwdFloats;
+        }
+        PFS_TRY((run_prep<F, M>(tp.G, jobs, saved ? 0 : 1, a.w1, M, a.u, pl, nfloats, wstage, st)));
+    }
     if (mode != 0) {
         int nchunk = (tp.S + 4095) / 4096;           // one CTA per 4096 fibres of a graph (1 for the C3 graphs)
         if (nchunk > 64) nchunk = 64;
@@ -775,19 +824,12 @@ int source_bwd_impl(const pfs_source_args& a, const Topo& tp) {
             k_bn_bwd_stats_final<<<(tp.G * 2 * F + 127) / 128, 128, 0, st>>>(bnpart, nchunk, 2 * F, tp.G, bnstat);
             PFS_LAUNCH_CHECK("k_bn_bwd_stats_final");
         }
-        PFS_TRY(colsum_all(bnstat, tp.G, 2 * F, F, F, a.g_gamma, st));
-        PFS_TRY(colsum_all(bnstat, tp.G, 2 * F, 0, F, a.g_beta, st));
+        PFS_TRY(colsum_pair(bnstat, tp.G, 2 * F, F, a.g_gamma, 0, a.g_beta, F, st));
     }
     {
         SourceNodeBwdParams p{tp.G, tp.S, ntn, mode, a.eps, a.x_s, a.moments, a.hidden, a.y_pre, a.g_out, a.bn_save,
                               bnstat, a.w3, a.w4, a.g_x_s, coefA, tot3p, wpn, pstride_n};
         if constexpr (kNodeC) {
-            using CW = SourceNodeConst<F>;
-            PackList pl{};
-            pl.it[0] = PackItem{a.w4, J, 0, J, F, 0, CW::kW4o};       // W4 as stored [F][J]
-            pl.it[1] = PackItem{a.w3, J, 0, K9, J, 0, CW::kW3o};      // W3[:, :9F] as stored [J][K9]
-            pl.n = 2;
-            PFS_TRY(upload_weights(pl, CW::kBwdFloats, wstage, st));
             bool launched = false;
             if constexpr (kNodeMma) {
                 if (use_mma) {
@@ -818,12 +860,10 @@ int source_bwd_impl(const pfs_source_args& a, const Topo& tp) {
     PFS_TRY(colsum_all(tot3, tp.G, J, 0, J, a.g_b3, st));
     PFS_TRY(outer_graphs(tot3, a.u, tp.G, J, F, a.g_w3, J, K9, st));
     PFS_TRY((node_linear_bwd<F, J>(tot3, tp.G, a.w3, J, K9, a.g_u, st)));
-    if (!saved) PFS_TRY((node_linear<F, M>(a.x_t, tp.T, tp.G, a.w1, M, 0, a.b1, nullptr, Qt, st)));
     {
         const bool dense = tp.layout == PFS_LAYOUT_DENSE;
         SourceEdgeBwdParams p{tp, a.x_e, Qt, a.w1, a.w2, a.b2, a.moments, coefA, a.g_x_e, a.g_x_e_add,
                               dense ? stage : nullptr, dense ? nullptr : stage, wpe, pstride_e, a.act_save, a.msg_save};
-        PFS_TRY(upload_msg_weights<F>(a.w1, a.w2, a.b2, wstage, st));
         ke<<<gride, kThreads, SME::bytes, st>>>(p);
         PFS_LAUNCH_CHECK("k_source_edge_bwd");
     }
@@ -874,11 +914,15 @@ int target_fwd_impl(const pfs_target_args& a, const Topo& tp) {
     if (a.normed && a.training && tp.T <= 1)
         return fail(PFS_ERR_ARG, "Expected more than 1 value per channel when training");
     if (a.normed && !a.training) PFS_REQUIRE(a.running_mean && a.running_var, "eval-mode BatchNorm needs running buffers");
-    PFS_TRY((node_linear<F, M>(a.x_s, tp.S, tp.G, a.w1, M, 0, a.b1, nullptr, Rs, st)));
+    {
+        TableJob jobs[2] = {TableJob{a.x_s, tp.S, 0, -1, a.b1, Rs}, TableJob{}};
+        PackList pl{};
+        add_msg_weights<F>(pl, a.w1, nullptr, nullptr);
+        PFS_TRY((run_prep<F, M>(tp.G, jobs, 1, a.w1, M, a.u, pl, MsgEdgeConst<F>::kFloats, wstage, st)));
+    }
     {
         const bool dense = tp.layout == PFS_LAYOUT_DENSE;
         TargetEdgeFwdParams p{tp, a.x_e, Rs, a.w1, dense ? stage : nullptr, dense ? nullptr : stage, a.act_save};
-        PFS_TRY(upload_msg_weights<F>(a.w1, nullptr, nullptr, wstage, st));
         const int grid = persistent_grid(k_target_edge_fwd<F>, 0, total);
         k_target_edge_fwd<F><<<grid, kThreads, 0, st>>>(p);
         PFS_LAUNCH_CHECK("k_target_edge_fwd");
@@ -946,10 +990,14 @@ int target_bwd_impl(const pfs_target_args& a, const Topo& tp) {
         }
         PFS_TRY(rd.run(gpart, tp.G, ptail, st));
     }
-    if (!saved) PFS_TRY((node_linear<F, M>(a.x_s, tp.S, tp.G, a.w1, M, 0, a.b1, nullptr, Rs, st)));
+    {
+        TableJob jobs[2] = {TableJob{a.x_s, tp.S, 0, -1, a.b1, Rs}, TableJob{}};
+        PackList pl{};
+        add_msg_weights<F>(pl, a.w1, nullptr, nullptr);
+        PFS_TRY((run_prep<F, M>(tp.G, jobs, saved ? 0 : 1, a.w1, M, a.u, pl, MsgEdgeConst<F>::kFloats, wstage, st)));
+    }
     {
         TargetEdgeBwdParams p{tp, a.x_e, Rs, a.w1, dasum, a.g_x_e, a.g_x_e_add, dRs, wpe, pstride_e, a.act_save};
-        PFS_TRY(upload_msg_weights<F>(a.w1, nullptr, nullptr, wstage, st));
         ke<<<gride, kThreads, SM::bytes, st>>>(p);
         PFS_LAUNCH_CHECK("k_target_edge_bwd");
     }

@@ -37,6 +37,77 @@ __global__ void __launch_bounds__(kThreads) k_node_linear(const float* __restric
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Prologue of a module call in ONE launch: the per-node tables of the first-layer split (up to two: e.g. the
+// EdgeModel's P_s = x_s . W1_s^T and P_t = x_t . W1_t^T + W1_u . u + b1) and the packing of the module's small MLP
+// weights into the staging buffer of the constant bank.  The first `pack_blocks` CTAs pack, the others run the
+// table rows thread-per-row with the weight slices broadcast from shared memory.
+// ------------------------------------------------------------------------------------------
+struct TableJob {
+    const float* x;     // [G, rows, F]
+    int rows;           // rows per graph
+    int koff;           // first column of W contracted with x
+    int ukoff;          // first column of W contracted with the graph's global row u[g] (added to every row), or -1
+    const float* bias;  // [J] or null
+    float* out;         // [G, rows, J]
+};
+struct PrepParams {
+    TableJob job[2];
+    int njobs, G;
+    const float* W;     // [J, ldw] first-layer weight matrix
+    int ldw;
+    const float* u;     // [G, F]
+    PackList pl;
+    float* stage;
+    int pack_blocks;
+};
+template <int F, int J>
+__global__ void __launch_bounds__(kThreads) k_prep(const PrepParams p) {
+    if ((int)blockIdx.x < p.pack_blocks) {
+        for (int q = 0; q < p.pl.n; ++q) {
+            const PackItem& it = p.pl.it[q];
+            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < it.J * it.K; i += p.pack_blocks * blockDim.x) {
+                const int j = i / it.K, k = i - j * it.K;
+                const float v = __ldg(it.W + (size_t)j * it.ld + it.koff + k);
+                p.stage[it.dst_off + (it.transpose ? k * it.J + j : j * it.K + k)] = v;
+            }
+        }
+        return;
+    }
+    __shared__ __align__(16) float Wt[2][F * J];
+    __shared__ __align__(16) float Wu[F * J];
+    __shared__ float bs[2][J];
+    const int nb = gridDim.x - p.pack_blocks, b = blockIdx.x - p.pack_blocks;
+    bool any_u = false;
+    for (int q = 0; q < p.njobs; ++q) {
+        load_w_inmajor<F, J>(Wt[q], p.W, p.ldw, p.job[q].koff);
+        for (int i = threadIdx.x; i < J; i += blockDim.x) bs[q][i] = p.job[q].bias ? __ldg(p.job[q].bias + i) : 0.f;
+        if (p.job[q].ukoff >= 0) {
+            load_w_inmajor<F, J>(Wu, p.W, p.ldw, p.job[q].ukoff);
+            any_u = true;
+        }
+    }
+    (void)any_u;
+    __syncthreads();
+    for (int q = 0; q < p.njobs; ++q) {
+        const TableJob& jb = p.job[q];
+        const long long N = (long long)jb.rows * p.G;
+        for (long long n = (long long)b * kThreads + threadIdx.x; n < N; n += (long long)nb * kThreads) {
+            float xr[F], y[J];
+            load_row<F>(jb.x + n * F, xr);
+#pragma unroll
+            for (int j = 0; j < J; ++j) y[j] = bs[q][j];
+            if (jb.ukoff >= 0) {
+                float ur[F];
+                load_row<F>(p.u + (n / jb.rows) * F, ur);
+                dense_acc<F, J>(Wu, ur, y);
+            }
+            dense_acc<F, J>(Wt[q], xr, y);
+            store_row<J>(jb.out + n * J, y);
+        }
+    }
+}
+
 // dx[n][k] (+)= sum_j W[j][koff + k] * d[n][j]     (backward of the map above w.r.t. x)
 template <int K, int J, bool ACCUM>
 __global__ void __launch_bounds__(kThreads) k_node_linear_bwd(const float* __restrict__ d, long long N,
@@ -171,6 +242,25 @@ __global__ void k_colsum_all(const float* __restrict__ x, long long N, int ld, i
                              float* __restrict__ out) {
     // blockDim = (32 columns, 8 row lanes); column j of the result is x[:, off + j] of a [N, ld] matrix
     __shared__ float red[8][33];
+    const int j = blockIdx.x * 32 + threadIdx.x;
+    float s = 0.f;
+    if (j < J)
+        for (long long n = threadIdx.y; n < N; n += 8) s += x[n * ld + off + j];
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && j < J) {
+        float t = 0.f;
+        for (int r = 0; r < 8; ++r) t += red[r][threadIdx.x];
+        out[j] = t;
+    }
+}
+
+// the same for two column blocks in one launch (blockIdx.y picks the block): the gamma / beta gradient pairs
+__global__ void k_colsum_pair(const float* __restrict__ x, long long N, int ld, int off0, float* __restrict__ out0, int off1,
+                              float* __restrict__ out1, int J) {
+    __shared__ float red[8][33];
+    const int off = blockIdx.y ? off1 : off0;
+    float* out = blockIdx.y ? out1 : out0;
     const int j = blockIdx.x * 32 + threadIdx.x;
     float s = 0.f;
     if (j < J)
@@ -388,6 +478,106 @@ __global__ void k_bn_finalize_rec(const float* __restrict__ partial, int ncta, i
     s[F + f] = (float)var;
     s[2 * F + f] = (float)scale;
     s[3 * F + f] = (float)(bt - scale * mean);
+}
+
+// finalisation (either partial format) AND the running-buffer update in one single-CTA launch: the per-graph
+// statistics are a few thousand values, two dependent latency-bound launches cost more than the work
+struct BnFinalizeAll {
+    const float* partial;
+    int rec_ncta, rec_nrec;      // rec_ncta > 0: per-CTA graph-segment records, else per-tile partials
+    int ntiles, pstride, F, G, twice;
+    const float *gamma, *beta;
+    float eps, momentum;
+    long long n_rows;
+    float* save;
+    float *rm, *rv;
+    long long* nbt;
+};
+__global__ void __launch_bounds__(1024) k_bn_finalize_all(const BnFinalizeAll a) {
+    const int F = a.F, G = a.G;
+    for (int i = threadIdx.x; i < G * F; i += blockDim.x) {
+        const int g = i / F, f = i - g * F;
+        double n = 0.0, mean = 0.0, m2 = 0.0;
+        if (a.rec_ncta > 0) {
+            const long long total = (long long)a.ntiles * G;
+            long long c_lo = (long long)g * a.ntiles * a.rec_ncta / total - 1;
+            long long c_hi = ((long long)(g + 1) * a.ntiles * a.rec_ncta) / total + 1;
+            if (c_lo < 0) c_lo = 0;
+            if (c_hi > a.rec_ncta - 1) c_hi = a.rec_ncta - 1;
+            const int stride = 2 * F + 2;
+            for (long long c = c_lo; c <= c_hi; ++c)
+                for (int r = 0; r < a.rec_nrec; ++r) {
+                    const float* p = a.partial + ((size_t)c * a.rec_nrec + r) * stride;
+                    const double nb = p[2 * F];
+                    if (nb <= 0.0 || (int)p[2 * F + 1] != g) continue;
+                    const double mb = p[f], sb = p[F + f];
+                    const double tot = n + nb, delta = mb - mean;
+                    mean += delta * (nb / tot);
+                    m2 += sb + delta * delta * (n * nb / tot);
+                    n = tot;
+                }
+        } else {
+            const float* p = a.partial + (size_t)g * a.ntiles * a.pstride;
+            for (int t = 0; t < a.ntiles; ++t) {
+                const double nb = p[(size_t)t * a.pstride + 2 * F];
+                if (nb <= 0.0) continue;
+                const double mb = p[(size_t)t * a.pstride + f], sb = p[(size_t)t * a.pstride + F + f];
+                const double tot = n + nb, delta = mb - mean;
+                mean += delta * (nb / tot);
+                m2 += sb + delta * delta * (n * nb / tot);
+                n = tot;
+            }
+        }
+        const double var = n > 0 ? m2 / n : 0.0;
+        const double gm = a.gamma[f], bt = a.beta[f];
+        const double r1 = 1.0 / sqrt(var + (double)a.eps);
+        double scale;
+        if (a.twice) {
+            const double var2 = gm * gm * var * r1 * r1;
+            scale = gm * gm * r1 / sqrt(var2 + (double)a.eps);
+        } else {
+            scale = gm * r1;
+        }
+        float* s = a.save + (size_t)g * 4 * F;
+        s[f] = (float)mean;
+        s[F + f] = (float)var;
+        s[2 * F + f] = (float)scale;
+        s[3 * F + f] = (float)(bt - scale * mean);
+    }
+    if (!a.rm || !a.rv) return;
+    __syncthreads();               // one CTA: its own global writes are visible to it after the barrier
+    const int f = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (f >= F) return;
+    const double mom = a.momentum, keep = 1.0 - mom, unb = (double)a.n_rows / (double)(a.n_rows - 1);
+    const double step = a.twice ? keep * keep : keep;
+    double am = 0.0, av = 0.0;
+    for (int g = lane; g < G; g += 32) {
+        const double mean = a.save[(size_t)g * 4 * F + f], var = a.save[(size_t)g * 4 * F + F + f];
+        double cm, cv;
+        if (a.twice) {
+            const double gm = a.gamma[f];
+            const double var2 = gm * gm * var / (var + (double)a.eps);
+            cm = keep * mom * mean + mom * (double)a.beta[f];
+            cv = keep * mom * var * unb + mom * var2 * unb;
+        } else {
+            cm = mom * mean;
+            cv = mom * var * unb;
+        }
+        const double w = pow(step, (double)(G - 1 - g));
+        am += w * cm;
+        av += w * cv;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        am += __shfl_xor_sync(0xffffffffu, am, o);
+        av += __shfl_xor_sync(0xffffffffu, av, o);
+    }
+    if (lane == 0) {
+        const double d = pow(step, (double)G);
+        a.rm[f] = (float)(d * (double)a.rm[f] + am);
+        a.rv[f] = (float)(d * (double)a.rv[f] + av);
+        if (f == 0 && a.nbt) *a.nbt += (long long)G * (a.twice ? 2 : 1);
+    }
 }
 
 // eval mode: coefficients from the running buffers (same for every graph)

@@ -18,10 +18,14 @@ constexpr int kNodeRowsC = 128;      // fibres per node tile (2 per lane)
 template <int F>
 struct SourceNodeConst {
     static constexpr int K9 = 9 * F, J = 10 * F;
-    // forward: W3 input-major [K9][J], W4 input-major [J][F], b4 [F]
-    static constexpr int kW3t = 0, kW4t = K9 * J, kB4 = K9 * J + J * F, kFwdFloats = K9 * J + J * F + F;
-    // backward: W4 as stored [F][J] (dh3_j += W4[f][j] dy_f), W3 as stored, first 9F columns [J][K9]
-    static constexpr int kW4o = 0, kW3o = F * J, kBwdFloats = F * J + J * K9;
+    // The node-MLP constants sit ABOVE the message-MLP constants (MsgEdgeConst, at most 2 * 16 * 32 + 2 * 32 * 32 + 32
+    // floats at Fdim 16) so that one upload per module call serves the edge kernel and the node kernel.
+    static constexpr int kBase = 4096;
+    // forward: W4 input-major [J][F], b4 [F], then (FMA fallback only) W3 input-major [K9][J]
+    static constexpr int kW4t = kBase, kB4 = kBase + J * F, kW3t = kBase + J * F + F, kFwdMmaFloats = kBase + J * F + F,
+                         kFwdFloats = kBase + J * F + F + K9 * J;
+    // backward: W4 as stored [F][J] (dh3_j += W4[f][j] dy_f), then (FMA fallback only) W3 as stored, first 9F columns [J][K9]
+    static constexpr int kW4o = kBase, kW3o = kBase + F * J, kBwdMmaFloats = kBase + F * J, kBwdFloats = kBase + F * J + J * K9;
     static constexpr bool fits = kFwdFloats <= kConstFloats && kBwdFloats <= kConstFloats;
 };
 
