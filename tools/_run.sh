@@ -1,4 +1,3 @@
 mkdir -p gpurun_out
-timeout 120 python bench.py --steps 20 --warmup 3 --graphs 32 --no-e2e --no-cpu-baseline --no-extras > gpurun_out/r02_bench_g32.json 2> gpurun_out/r02_bench_g32.err
-timeout 120 python bench.py --steps 20 --warmup 3 --graphs 64 --no-e2e --no-cpu-baseline --no-extras --no-profile > gpurun_out/r02_bench_g64.json 2> gpurun_out/r02_bench_g64.err
-timeout 300 python -m pytest tests -x -q -m gpu -k "wide" -s 2>&1 | grep -E "passed|failed|worst|top |Error|c4-shape" | cut -c1-260 > gpurun_out/r02_pytest_wide3.txt
+timeout 300 python -m pytest tests/test_gpu_train_step.py -x -q -m gpu -s 2>&1 | grep -E "trajectory vs|passed|failed|^E|loss curve|ref " | cut -c1-250 > gpurun_out/r02_pytest_n2.txt
+timeout 120 python bench.py --workload train --steps 50 --warmup 5 > gpurun_out/r02_bench_train.json 2> gpurun_out/r02_bench_train.err
