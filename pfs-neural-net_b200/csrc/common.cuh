@@ -650,41 +650,67 @@ struct RunningStats {
 // in-tile segment sums over a shared-memory tile X[edge][LD] (W features, 4 per thread, 16-byte loads;
 // the edges of a segment are added in their order, so the result does not depend on the mapping)
 // ------------------------------------------------------------------------------------------
-// out[lf * W + k] = sum over the edges of local fibre lf; `out` points at the row of the tile's first fibre
-template <int W, int LD>
+// out[lf * W + k] = sum over the edges of local fibre lf; `out` points at the row of the tile's first fibre.
+// Threads [T0, T0 + NT) of the CTA take part (whole warps).  Two running sums per thread (even / odd edges, added at
+// the end) halve the dependent FADD chain and keep 8 loads in flight: these sums are latency-bound, not
+// bandwidth-bound (ncu source view of k_edge_bwd2: 16 % of the stall samples sat on their FADDs).
+template <int W, int LD, int T0 = 0, int NT = kThreads>
 __device__ __forceinline__ void tile_fibre_sums(const Topo& tp, const Tile& t, const float* X, float* __restrict__ out) {
-    static_assert(W % 4 == 0 && LD % 4 == 0, "16-byte rows");
+    static_assert(W % 4 == 0 && LD % 4 == 0 && T0 % 32 == 0 && NT % 32 == 0, "16-byte rows, whole warps");
     constexpr int W4 = W / 4;
-    for (int i = threadIdx.x; i < t.nfib * W4; i += kThreads) {
+    const int tt = (int)threadIdx.x - T0;
+    if (tt < 0 || tt >= NT) return;
+    for (int i = tt; i < t.nfib * W4; i += NT) {
         const int lf = i / W4, k = (i - lf * W4) * 4;
         int e0, n;
         fibre_range(tp, t, lf, e0, n);
         const float4* x = reinterpret_cast<const float4*>(X + e0 * LD + k);
-        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s;
+        int e = 0;
 #pragma unroll 4
-        for (int e = 0; e < n; ++e) {
+        for (; e + 1 < n; e += 2) {
+            const float4 v = x[e * (LD / 4)], v1 = x[(e + 1) * (LD / 4)];
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            s1.x += v1.x; s1.y += v1.y; s1.z += v1.z; s1.w += v1.w;
+        }
+        if (e < n) {
             const float4 v = x[e * (LD / 4)];
             s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
         }
+        s.x += s1.x; s.y += s1.y; s.z += s1.z; s.w += s1.w;
         *reinterpret_cast<float4*>(out + (size_t)lf * W + k) = s;
     }
 }
-// dense layout (edge lf * T + c belongs to class c): cp[c * W + k] = sum over the tile's fibres
-template <int W, int LD>
+// dense layout (edge lf * T + c belongs to class c): cp[c * W + k] = sum over the tile's fibres.  A lane pair shares
+// one (class, 4 features) item: even lane = even fibres, odd lane = odd fibres, one shuffle adds them -- twice the
+// threads busy on half the chain (T * W / 4 items alone leave most of the CTA idle when there are few classes).
+template <int W, int LD, int T0 = 0, int NT = kThreads>
 __device__ __forceinline__ void tile_class_sums(const Topo& tp, const Tile& t, const float* X, float* __restrict__ cp) {
-    static_assert(W % 4 == 0 && LD % 4 == 0, "16-byte rows");
+    static_assert(W % 4 == 0 && LD % 4 == 0 && T0 % 32 == 0 && NT % 32 == 0, "16-byte rows, whole warps");
     constexpr int W4 = W / 4;
+    const int tt = (int)threadIdx.x - T0;
+    if (tt < 0 || tt >= NT) return;
     const int stride = tp.T * (LD / 4);
-    for (int i = threadIdx.x; i < tp.T * W4; i += kThreads) {
-        const int c = i / W4, k = (i - c * W4) * 4;
+    const int items = tp.T * W4 * 2;
+    for (int base = 0; base < items; base += NT) {      // uniform trip count per warp: the shuffle below is warp-wide
+        const int i = base + tt;
+        const bool on = i < items;
+        const int half = i & 1, ci = on ? (i >> 1) : 0;
+        const int c = ci / W4, k = (ci - c * W4) * 4;
         const float4* x = reinterpret_cast<const float4*>(X + c * LD + k);
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (on) {
 #pragma unroll 4
-        for (int lf = 0; lf < t.nfib; ++lf) {
-            const float4 v = x[lf * stride];
-            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            for (int lf = half; lf < t.nfib; lf += 2) {
+                const float4 v = x[lf * stride];
+                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            }
         }
-        *reinterpret_cast<float4*>(cp + c * W + k) = s;
+        s.x += __shfl_xor_sync(0xffffffffu, s.x, 1);
+        s.y += __shfl_xor_sync(0xffffffffu, s.y, 1);
+        s.z += __shfl_xor_sync(0xffffffffu, s.z, 1);
+        s.w += __shfl_xor_sync(0xffffffffu, s.w, 1);
+        if (on && half == 0) *reinterpret_cast<float4*>(cp + c * W + k) = s;
     }
 }
 
@@ -737,8 +763,27 @@ struct OuterAcc {
                 for (int c = 0; c < TK; ++c) acc[a][c] = fmaf(d[a], x[c], acc[a][c]);
         }
     }
-    template <int N>
+    // A = alignment of p in floats the CALLER guarantees (4: 16 bytes, 2: 8 bytes, 1: none), 0 = test the address at
+    // run time.  The run-time test costs two S2R (shared window of the generic address), two branches and a
+    // duplicated load sequence per row in the hot loop (profiles/r02_outer_align.txt): the edge kernels pass A.
+    template <int N, int A = 0>
     static __device__ __forceinline__ void load_vec_smem(const float* p, float (&v)[N]) {
+        if constexpr (A == 4 && N % 4 == 0) {
+#pragma unroll
+            for (int i = 0; i < N / 4; ++i) {
+                const float4 t = reinterpret_cast<const float4*>(p)[i];
+                v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+            }
+        } else if constexpr ((A == 2 || A == 4) && N % 2 == 0) {
+#pragma unroll
+            for (int i = 0; i < N / 2; ++i) {
+                const float2 t = reinterpret_cast<const float2*>(p)[i];
+                v[2 * i] = t.x; v[2 * i + 1] = t.y;
+            }
+        } else if constexpr (A != 0) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) v[i] = p[i];
+        } else {
         // widest aligned loads the address allows (p's alignment is uniform over the loop)
         if ((N % 4 == 0) && ((((uintptr_t)p) & 15) == 0)) {
 #pragma unroll
@@ -756,24 +801,28 @@ struct OuterAcc {
 #pragma unroll
             for (int i = 0; i < N; ++i) v[i] = p[i];
         }
+        }
     }
     // two rows per iteration: both rows' loads are in flight before the first FMA needs them
+    // AD / AX: alignment (floats) of D + r * ldD + j0 and X + r * ldX + k0 guaranteed by the caller for every row and
+    // block (0 = run-time test, see load_vec_smem)
+    template <int AD = 0, int AX = 0>
     __device__ __forceinline__ void accumulate(const float* D, int ldD, const float* X, int ldX, int rows) {
         if (!live) return;
         int r = grp;
         for (; r + GROUPS < rows; r += 2 * GROUPS) {
             float d0[TJ], x0[TK], d1[TJ], x1[TK];
-            load_vec_smem<TJ>(D + r * ldD + j0, d0);
-            load_vec_smem<TK>(X + r * ldX + k0, x0);
-            load_vec_smem<TJ>(D + (r + GROUPS) * ldD + j0, d1);
-            load_vec_smem<TK>(X + (r + GROUPS) * ldX + k0, x1);
+            load_vec_smem<TJ, AD>(D + r * ldD + j0, d0);
+            load_vec_smem<TK, AX>(X + r * ldX + k0, x0);
+            load_vec_smem<TJ, AD>(D + (r + GROUPS) * ldD + j0, d1);
+            load_vec_smem<TK, AX>(X + (r + GROUPS) * ldX + k0, x1);
             fma_row(d0, x0);
             fma_row(d1, x1);
         }
         if (r < rows) {
             float d0[TJ], x0[TK];
-            load_vec_smem<TJ>(D + r * ldD + j0, d0);
-            load_vec_smem<TK>(X + r * ldX + k0, x0);
+            load_vec_smem<TJ, AD>(D + r * ldD + j0, d0);
+            load_vec_smem<TK, AX>(X + r * ldX + k0, x0);
             fma_row(d0, x0);
         }
     }
@@ -834,24 +883,24 @@ struct OuterAccX {
                 A[slot(a + 1, c)] = v.y;
             }
     }
-    template <int NA>
+    template <int AD = 0, int AX = 0, int NA>
     __device__ __forceinline__ void accumulate(float (&A)[NA], const float* D, int ldD, const float* X, int ldX, int rows) const {
         if (!live) return;
         using Base = OuterAcc<J, K, TJ, TK, T0, NT>;
         int r = grp;
         for (; r + GROUPS < rows; r += 2 * GROUPS) {
             float d0[TJ], x0[TK], d1[TJ], x1[TK];
-            Base::template load_vec_smem<TJ>(D + r * ldD + j0, d0);
-            Base::template load_vec_smem<TK>(X + r * ldX + k0, x0);
-            Base::template load_vec_smem<TJ>(D + (r + GROUPS) * ldD + j0, d1);
-            Base::template load_vec_smem<TK>(X + (r + GROUPS) * ldX + k0, x1);
+            Base::template load_vec_smem<TJ, AD>(D + r * ldD + j0, d0);
+            Base::template load_vec_smem<TK, AX>(X + r * ldX + k0, x0);
+            Base::template load_vec_smem<TJ, AD>(D + (r + GROUPS) * ldD + j0, d1);
+            Base::template load_vec_smem<TK, AX>(X + (r + GROUPS) * ldX + k0, x1);
             fma_row(A, d0, x0);
             fma_row(A, d1, x1);
         }
         if (r < rows) {
             float d0[TJ], x0[TK];
-            Base::template load_vec_smem<TJ>(D + r * ldD + j0, d0);
-            Base::template load_vec_smem<TK>(X + r * ldX + k0, x0);
+            Base::template load_vec_smem<TJ, AD>(D + r * ldD + j0, d0);
+            Base::template load_vec_smem<TK, AX>(X + r * ldX + k0, x0);
             fma_row(A, d0, x0);
         }
     }

@@ -418,7 +418,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_edge_bwd2(const EdgeBwdParams p
     AccW2 accw2;
     accw1.init();
     accw2.init();
-    float dzs = 0.f;                 // db2 partial of thread (row part = tid / F < 4, column tid % F)
+    constexpr int kDzParts = kThreads / F;   // db2 partial of thread (row part = tid / F < kDzParts, column tid % F)
+    float dzs = 0.f;
     const int dz_col = threadIdx.x % F, dz_part = threadIdx.x / F;
     const float* esrc[1] = {p.x_e};
     const int total = tp.ntiles * tp.G;
@@ -464,22 +465,32 @@ __global__ void __launch_bounds__(kThreads, 2) k_edge_bwd2(const EdgeBwdParams p
             store_row<F>(p.g_x_e + row, dx);
         }
         __syncthreads();
-        accw1.accumulate(acc, DH, LDH, XE, F, t.ne);
-        accw2.accumulate(acc, DZ, LDF, A1, LDH, t.ne);
-        if (dz_part < 4)
-            for (int r = dz_part; r < t.ne; r += 4) dzs += DZ[r * LDF + dz_col];
-        tile_fibre_sums<H, LDH>(tp, t, DH, p.dPs + ((size_t)t.g * tp.S + t.fibre0) * H);
-        if (p.class_part) tile_class_sums<H, LDH>(tp, t, DH, p.class_part + (size_t)tile * tp.T * H);
+        // The two halves of the CTA run the FFMA2-bound outer products and the latency-bound segment sums in OPPOSITE
+        // order, so every scheduler always holds a warp of each kind (warp w and warp w + 4 share a scheduler).
+        if (threadIdx.x < kThreads / 2) {
+            accw1.template accumulate<4, 1>(acc, DH, LDH, XE, F, t.ne);       // DH rows, j0: 16-byte aligned; x_e rows: 40 B
+            tile_fibre_sums<H, LDH, 0, kThreads / 2>(tp, t, DH, p.dPs + ((size_t)t.g * tp.S + t.fibre0) * H);
+        } else {
+            if (p.class_part) tile_class_sums<H, LDH, kThreads / 2, kThreads / 2>(tp, t, DH, p.class_part + (size_t)tile * tp.T * H);
+            accw2.template accumulate<2, 4>(acc, DZ, LDF, A1, LDH, t.ne);      // dz pairs: 8 bytes; a1 rows, k0: 16 bytes
+        }
+        if (dz_part < kDzParts)
+            for (int r = dz_part; r < t.ne; r += kDzParts) dzs += DZ[r * LDF + dz_col];
         __syncthreads();
     }
     float* out = p.wpartial + (size_t)blockIdx.x * p.pstride;
     accw1.flush(acc, DH, out, F, 0);
     accw2.flush(acc, DH, out + H * F, H, 0);
-    {   // db2 = sum dz: the four row parts of each column, fixed order
+    {   // db2 = sum dz: the row parts of each column, fixed order
         float* red = DH;
-        if (dz_part < 4) red[threadIdx.x] = dzs;
+        if (dz_part < kDzParts) red[threadIdx.x] = dzs;
         __syncthreads();
-        if (threadIdx.x < F) out[2 * H * F + threadIdx.x] = (red[threadIdx.x] + red[F + threadIdx.x]) + (red[2 * F + threadIdx.x] + red[3 * F + threadIdx.x]);
+        if (threadIdx.x < F) {
+            float s = 0.f;
+#pragma unroll
+            for (int q = 0; q < kDzParts; ++q) s += red[q * F + threadIdx.x];
+            out[2 * H * F + threadIdx.x] = s;
+        }
     }
 }
 
