@@ -451,7 +451,7 @@ def run_ours(args):
         lib.pfs_profile_enable(0)
         tot = sum(v[1] for v in rep.values())
         kernels = {k: {"launches": v[0], "ms_per_step": v[1] / args.steps, "share": v[1] / tot}
-                   for k, v in sorted(rep.items(), key=lambda kv: -kv[1][1])[:12]}
+                   for k, v in sorted(rep.items(), key=lambda kv: -kv[1][1])[:None if os.environ.get("PFS_BENCH_ALL_KERNELS") else 12]}
         cand = [k for k in rep if k in KERNEL_ROWS]
         if cand:
             top = max(cand, key=lambda k: rep[k][1])
@@ -613,9 +613,16 @@ def wide_graph(args, workload, rank, world, dev):
     keep = torch.rand(S * T, generator=g) < 0.1
     e = torch.nonzero(keep).flatten()
     e = e[torch.randperm(e.numel(), generator=g)]
-    ei = torch.stack([e // T, e % T]).contiguous().to(dev)
-    return ei, S, T, int(e.numel()), "C5b: 10%% Bernoulli edge list of %d x %d, shuffled, Fdim %d, bf16 (CSR/CSC path)" % (
-        S, T, args.wide_fdim)
+    ei = torch.stack([e // T, e % T]).contiguous()
+    desc = "C5b: 10%% Bernoulli edge list of %d x %d (%d edges), shuffled, Fdim %d, bf16 (CSR/CSC path)" % (
+        S, T, int(e.numel()), args.wide_fdim)
+    if world > 1:
+        # the SAME graph split by fibre range over the ranks (strong scaling): every rank keeps the edges of its fibres
+        from pfs_neural_net_b200 import shard
+        ei, sl, pos = shard.partition_fibres(ei, S, world, rank)
+        S = sl.stop - sl.start
+        desc += ", fibre-range sharded: rank %d holds %d fibres / %d edges" % (rank, S, int(pos.numel()))
+    return ei.to(dev), S, T, int(ei.shape[1]), desc
 
 
 def cpu_reference_wide(args, S_sub, seconds):
@@ -675,11 +682,11 @@ def run_wide(args):
 
 
 def wide_record(args, workload, world, rank, local_rank, dev, steps, warmup, with_e2e, with_cpu, with_profile):
-    """One bench record of a wide workload (c4: fibre-sharded over the ranks; c5: replicas); the process group, if
-    any, is already initialised.  Returns the record on every rank (rank 0 prints it)."""
+    """One bench record of a wide workload (c4: one fibre slab of the complete graph per rank, weak scaling; c5: the
+    sparse graph partitioned by fibre range, strong scaling); the process group, if any, is already initialised.  Returns the record on every rank (rank 0 prints it)."""
     import torch.distributed as dist
     from pfs_neural_net_b200 import _abi, gnn, shard
-    sharded = world > 1 and workload == "c4"
+    sharded = world > 1                     # c4: a fibre slab of the complete graph per rank; c5: partition_fibres
     lib = _abi.load_library()
     F = args.wide_fdim
     ei, S, T, E, desc = wide_graph(args, workload, rank, world, dev)
@@ -741,7 +748,12 @@ def wide_record(args, workload, world, rank, local_rank, dev, steps, warmup, wit
     clocks = sampler.stop()
     coll_calls, coll_bytes = shard.traffic()
     ms_per_step = ms / steps
-    edges_total = float(E) * (world if workload == "c4" or world == 1 else world)
+    if world > 1 and workload == "c5":      # shard sizes differ: the job's edges are the sum over the ranks
+        t = torch.tensor([float(E)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t)
+        edges_total = float(t.item())
+    else:
+        edges_total = float(E) * world
     value = edges_total / (ms_per_step * 1e-3)
     hbm_gbs, peak_src, sm_max = measured_peaks()
     try:
@@ -801,12 +813,12 @@ def wide_record(args, workload, world, rank, local_rank, dev, steps, warmup, wit
         cpu = {"value": eps, "unit": UNIT, "cores": ncores, "kind": "port", "sample": sample}
     return {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-        "data": "synthetic",
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if workload == "c5" else "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": desc, "fibres_per_gpu": S, "classes": T, "fdim": F, "edges_per_step": edges_total,
                    "parallelism": ("fibre-sharded x%d (class-side all-reduces: %d calls, %d bytes per step)"
                                    % (world, coll_calls // max(steps, 1), coll_bytes // max(steps, 1)))
-                   if sharded else "single GPU" if world == 1 else "replicas x%d" % world,
+                   if sharded else "single GPU",
                    "l2": "inputs larger than L2 (x_e %.0f MB per step)" % (E * F * 2 / 1e6)},
         "roofline": roofline, "step_roofline": step_roofline, "tensor": tensor, "kernels": kernels, "cpu_baseline": cpu,
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}

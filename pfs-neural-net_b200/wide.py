@@ -65,10 +65,23 @@ class WideTopology:
             self.classes = wo.Segments(2, self.T, ptr=a["csc_colptr"], lst=self.csc_eid)
             cp = a["csc_colptr"]
             self.class_count = (cp[1:] - cp[:-1]).to(F32)
+        self._class_count_total = {}
         self.div = self.T      # dense: src = e // T, tgt = e % T
         # canonical order with whole 128-edge tiles inside one fibre: the class rows of a tile are contiguous, so
         # x_t[tgt] is a second GEMM operand and P_s[src] a per-tile bias row -- no gathered tables at all
         self.tiled_dense = bool(topo.canonical and self.T % 128 == 0)
+
+
+    def class_count_total(self):
+        """Edges per class over all fibre shards: a property of the partition, exchanged once per process group."""
+        if not _shard.active():
+            return self.class_count
+        key = _shard.group_key()
+        hit = self._class_count_total.get(key)
+        if hit is None:
+            hit = _shard.allreduce_sum(self.class_count.clone())
+            self._class_count_total[key] = hit
+        return hit
 
 
 # ------------------------------------------------------------------------------------------------ helpers
@@ -126,8 +139,8 @@ def _single_bn_fwd(y, rows, training, gamma, beta, rm, rv, nbt):
 def _single_bn_bwd(gout, y, mu, r, n, training, gamma):
     """dy (bf16) and the affine gradients of a BatchNorm1d whose input y (fp32) was saved."""
     g = gamma.float()
-    st = wo.colstats(1, gout, v=y, p0=mu, p1=r)
-    sg, sgx = _shard.allreduce_sum(st[0]), _shard.allreduce_sum(st[1])
+    st = _shard.allreduce_sum(wo.colstats(1, gout, v=y, p0=mu, p1=r))          # [2,F]: one exchange
+    sg, sgx = st[0], st[1]
     a = (g * r).contiguous()
     if training:
         dy = wo.rowmap(1, gout, a, (sg / n).contiguous(), v=y, p0=mu, p1=r, c2=(sgx / n).contiguous())
@@ -209,8 +222,8 @@ class WideEdgeFunction(torch.autograd.Function):
                 r1, r2, var, n = sm["r1"], sm["r2"], sm["var"], sm["n"]
                 g2 = gm * gm * r2
                 inv = torch.where(g2 != 0, 1.0 / g2, torch.zeros_like(g2)).contiguous()        # xhat1 = (x_e' - beta) inv
-                st = wo.colstats(1, g, v=xe2, p0=bt.contiguous(), p1=inv)
-                sg, sgx = _shard.allreduce_sum(st[0]), _shard.allreduce_sum(st[1])
+                st = _shard.allreduce_sum(wo.colstats(1, g, v=xe2, p0=bt.contiguous(), p1=inv))
+                sg, sgx = st[0], st[1]
                 gbar, mgx = sg / n, sgx / n
                 s = gm * r2
                 q = var * r1 * r1
@@ -223,8 +236,8 @@ class WideEdgeFunction(torch.autograd.Function):
                 a, shift = sm["a"], sm["shift"]
                 c = torch.rsqrt(rv + BN_EPS)
                 invA = torch.where(A != 0, 1.0 / A, torch.zeros_like(A)).contiguous()
-                st = wo.colstats(1, g, v=xe2, p0=shift, p1=invA)                                # sum g, sum g z
-                sg, sgz = _shard.allreduce_sum(st[0]), _shard.allreduce_sum(st[1])
+                st = _shard.allreduce_sum(wo.colstats(1, g, v=xe2, p0=shift, p1=invA))          # sum g, sum g z
+                sg, sgz = st[0], st[1]
                 dz = wo.rowmap(0, g, A, torch.zeros_like(A))
                 g_gamma = c * (2 * a * (sgz - rm * sg) + (bt - rm) * sg)
                 g_beta = (a + 1) * sg
@@ -248,9 +261,11 @@ class WideEdgeFunction(torch.autograd.Function):
         g_x_e = wo.gemm_nt(dh1, w1t[2 * F:3 * F])
         g_u = wo.gemm_nt(tot16, w1t[3 * F:])
         # fibre-local parameter gradients are partial under sharding; class-side ones are already global
-        g_w1[:, :F] = _shard.allreduce_sum(g_w1[:, :F].contiguous())
-        g_w1[:, 2 * F:3 * F] = _shard.allreduce_sum(g_w1[:, 2 * F:3 * F].contiguous())
-        g_w2, g_b2 = _shard.allreduce_sum(g_w2), _shard.allreduce_sum(g_b2)
+        # (one packed exchange for all of them)
+        if _shard.active():
+            w1s, w1e, g_w2, g_b2 = _shard.allreduce_packed([g_w1[:, :F], g_w1[:, 2 * F:3 * F], g_w2, g_b2])
+            g_w1[:, :F] = w1s
+            g_w1[:, 2 * F:3 * F] = w1e
         return (None, None, None, g_x_s, g_x_t, g_x_e, g_u, _like(g_w1, w1), _like(tot, b1), _like(g_w2, w2),
                 _like(g_b2, b2), None if g_gamma is None else _like(g_gamma, gamma),
                 None if g_beta is None else _like(g_beta, beta), None, None, None)
@@ -335,8 +350,10 @@ class WideSourceFunction(torch.autograd.Function):
         g_x_t = wo.gemm_nt(dQt, w1t[:F])
         g_x_e = wo.gemm_nt(dhs, w1t[F:])
         # fibre-local partial sums under sharding
-        g_w1[:, F:] = _shard.allreduce_sum(g_w1[:, F:].contiguous())
-        g_w2, g_b2, g_w3, g_w4, g_b4, tot3, g_u = (_shard.allreduce_sum(t) for t in (g_w2, g_b2, g_w3, g_w4, g_b4, tot3, g_u))
+        if _shard.active():
+            w1e, g_w2, g_b2, g_w3, g_w4, g_b4, tot3, g_u = _shard.allreduce_packed(
+                [g_w1[:, F:], g_w2, g_b2, g_w3, g_w4, g_b4, tot3, g_u])
+            g_w1[:, F:] = w1e
         return (None, None, None, g_x_s, g_x_t, g_x_e, _like(g_u, u), _like(g_w1, w1), _like(g_b1, b1), _like(g_w2, w2),
                 _like(g_b2, b2), _like(g_w3, w3), _like(tot3, b3), _like(g_w4, w4), _like(g_b4, b4),
                 None if g_gamma is None else _like(g_gamma, gamma), None if g_beta is None else _like(g_beta, beta),
@@ -362,7 +379,7 @@ class WideTargetFunction(torch.autograd.Function):
         a_t, a_sum_in = a_t if want == "both" else (a_t, a_t)
         asum32 = _shard.allreduce_sum(wo.segsum(wt.classes, a_sum_in, want="f32"))              # [T,2F]
         del a_sum_in
-        cnt = _shard.allreduce_sum(wt.class_count)
+        cnt = wt.class_count_total()                             # edges per class over ALL shards (cached per topology)
         b3eff = wo.gemm_nt(u, w3[:, 3 * F:], bias=_f32(b3), want="f32")
         if "node32" in PREC:
             asum_c = wo.split(asum32)                                                           # [T,4F] = [asum | lo]
@@ -429,11 +446,11 @@ class WideTargetFunction(torch.autograd.Function):
         dht = wo.gather_mask(dasum, wt.tgt, wt.div, a_t)         # [E,2F] bf16
         w1t = wo.transpose(w1)
         dRs = wo.segsum(wt.fibres, dht, want="bf16")             # [S,2F]
-        g_b1 = _shard.allreduce_sum(_colsum(dRs))
+        g_b1 = _colsum(dRs)
         g_w1 = torch.empty(M2, M2, dtype=F32, device=g.device)
         wo.gemm_tn(dRs, x_s, out=g_w1[:, :F])
         wo.gemm_tn(dht, x_e, out=g_w1[:, F:])
-        g_w1 = _shard.allreduce_sum(g_w1)
+        g_b1, g_w1 = _shard.allreduce_packed([g_b1, g_w1])
         g_x_s = wo.gemm_nt(dRs, w1t[:F])
         g_x_e = wo.gemm_nt(dht, w1t[F:])
         return (None, None, None, g_x_s, g_x_t, g_x_e, _like(g_u, u), _like(g_w1, w1), _like(g_b1, b1), _like(g_w2, w2),
@@ -462,7 +479,7 @@ class WideGlobalFunction(torch.autograd.Function):
         x_s, x_t, u, w1, w2 = (t.contiguous() for t in (x_s, x_t, u, w1, w2))
         S, F = x_s.shape
         T = x_t.shape[0]
-        n_s = _shard.allreduce_sum(torch.tensor([float(S)], device=x_s.device))
+        n_s = float(_shard.total_count(S))                       # fibres over all shards (host int, cached)
         mean_s = _shard.allreduce_sum(_colsum(x_s)) / n_s
         mean_t = _colsum(x_t) / T
         hcat = torch.cat([u.float().reshape(1, F), mean_s[None], mean_t[None]], 1)
@@ -533,7 +550,7 @@ class WideTimeHeadFunction(torch.autograd.Function):
         g_w1 = wo.gemm_tn(da, x_e)
         g_b1 = _colsum(da)
         g_x_e = wo.gemm_nt(da, wo.transpose(w1))
-        g_w1, g_b1, g_w2, g_b2 = (_shard.allreduce_sum(t) for t in (g_w1, g_b1, g_w2, g_b2))
+        g_w1, g_b1, g_w2, g_b2 = _shard.allreduce_packed([g_w1, g_b1, g_w2, g_b2])
         return None, g_x_e, _like(g_w1, w1), _like(g_b1, b1), _like(g_w2.reshape(w2.shape), w2), _like(g_b2.reshape(b2.shape), b2)
 
 

@@ -1,7 +1,10 @@
-"""Fibre-range sharding of one graph over 2 GPUs (NCCL): every rank runs the wide Block on its fibre
-range inside shard.fibre_sharded(); outputs, input gradients and the (all-reduced) parameter
-gradients must match the single-GPU run of the whole graph.  Needs >= 2 CUDA devices
-(`gpurun --gpus 2`); skipped otherwise."""
+"""Fibre-range sharding of one graph over 2 ranks: every rank runs the wide Block on its fibre range inside
+shard.fibre_sharded(); outputs, input gradients and the (all-reduced) parameter gradients must match the
+single-GPU run of the whole graph.  Two cases: the complete graph of BASELINE config C4 (a slab of the canonical
+order per rank) and a general sparse edge list as in config C5 (shard.partition_fibres, CSR/CSC path, unequal
+shard sizes, classes without local edges).
+With >= 2 CUDA devices the ranks use one GPU each over NCCL; on a 1-GPU box both ranks share cuda:0 and exchange
+through gloo (host-staged all-reduce of the same CUDA tensors) so the sharded product path is still exercised."""
 import os
 import socket
 
@@ -31,12 +34,22 @@ def _setup():
     return ins, ups, state
 
 
-def _run(dev, state, ins, ups, S_local, ctx):
+def _sparse_graph():
+    """10 % Bernoulli edge list, shuffled; fibre 3 and class 5 have no edges at all."""
+    g = torch.Generator().manual_seed(33)
+    keep = torch.rand(S * T, generator=g) < 0.1
+    e = torch.nonzero(keep).flatten()
+    e = e[(e // T != 3) & (e % T != 5)]
+    e = e[torch.randperm(e.numel(), generator=g)]
+    return torch.stack([e // T, e % T]).contiguous()
+
+
+def _run(dev, state, ei, ins, ups, ctx):
     from pfs_neural_net_b200 import gnn
     blk = gnn.Block(F).to(torch.bfloat16)
     blk.load_state_dict(state, strict=True)
     blk = blk.to(dev).train()
-    ei = bo.complete_bipartite(S_local, T).to(dev)
+    ei = ei.to(dev)
     x = [t.to(dev).requires_grad_(True) for t in ins]
     with ctx():
         _, o_s, o_t, o_e, o_u = blk((ei, *x))
@@ -48,43 +61,60 @@ def _run(dev, state, ins, ups, S_local, ctx):
     return {k: v.detach().float().cpu() for k, v in res.items()}
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, sparse, ngpu):
     import contextlib
     from pfs_neural_net_b200 import shard
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-    torch.cuda.set_device(rank)
-    dev = torch.device("cuda", rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    dev = torch.device("cuda", rank if ngpu >= world else 0)
+    torch.cuda.set_device(dev)
+    if ngpu >= world:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
     ins, ups, state = _setup()
-    h = S // world
-    sl, el = slice(rank * h, (rank + 1) * h), slice(rank * h * T, (rank + 1) * h * T)
+    if sparse:
+        ei = _sparse_graph()
+        E = ei.shape[1]
+        ins = (ins[0], ins[1], ins[2][:E], ins[3])
+        ups = (ups[0], ups[1], ups[2][:E], ups[3])
+        local, sl, el = shard.partition_fibres(ei, S, world, rank)
+    else:
+        ei = bo.complete_bipartite(S, T)
+        h = S // world
+        sl, el = slice(rank * h, (rank + 1) * h), slice(rank * h * T, (rank + 1) * h * T)
+        local = bo.complete_bipartite(h, T)
     loc_in = (ins[0][sl], ins[1], ins[2][el], ins[3])
     loc_up = (ups[0][sl], ups[1], ups[2][el], ups[3])
-    res = _run(dev, state, loc_in, loc_up, h, shard.fibre_sharded)
+    shard.reset_traffic()
+    res = _run(dev, state, local, loc_in, loc_up, shard.fibre_sharded)
+    res["_el"] = el if sparse else torch.arange(el.start, el.stop)
+    res["_sl"] = torch.arange(sl.start, sl.stop)
+    res["_calls"] = torch.tensor(shard.traffic()[0])
     out[rank] = res
     if rank == 0:
-        out["full"] = _run(dev, state, ins, ups, S, contextlib.nullcontext)
+        out["full"] = _run(dev, state, ei, ins, ups, contextlib.nullcontext)
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_fibre_sharded_block_matches_single_gpu():
-    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 CUDA devices")
+@pytest.mark.parametrize("sparse", [False, True], ids=["dense_c4", "sparse_c5"])
+def test_fibre_sharded_block_matches_single_gpu(sparse):
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
     world = 2
+    ngpu = torch.cuda.device_count()
     with mp.Manager() as mgr:
         out = mgr.dict()
-        mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, _free_port(), out, sparse, ngpu), nprocs=world, join=True)
         out = dict(out)
     full = out["full"]
-    h = S // world
 
     def close(a, b, what, tol=2e-2):
         err = (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
         assert err < tol, (what, err)
 
     for r in range(world):
-        sl, el = slice(r * h, (r + 1) * h), slice(r * h * T, (r + 1) * h * T)
+        sl, el = out[r]["_sl"], out[r]["_el"]
         close(out[r]["o_s"], full["o_s"][sl], "x_s")
         close(out[r]["o_e"], full["o_e"][el], "x_e")
         close(out[r]["g_s"], full["g_s"][sl], "grad x_s")
@@ -97,11 +127,23 @@ def test_fibre_sharded_block_matches_single_gpu():
                 # a bias in front of a train-mode BatchNorm (edge_model.2, node_mlp_2.2) has an analytically zero gradient:
                 # both runs hold rounding noise there, judged on the scale of the weight gradient like the parity tests
                 zero_grad = k.endswith(("edge_model.2.bias", "node_mlp_2.2.bias"))
-                den = max(full[k].abs().max().item(), (1.0 if zero_grad else 1e-3) * full[scale_key].abs().max().item())
+                # the bias of the SModel message MLP's last layer shifts every message of a fibre alike: std, skew and
+                # kurtosis do not see it, so three of the four moment branches contribute per-fibre sums that cancel
+                # analytically and only the mean branch survives (measured: |g_b| = 0.05 |g_W|); the rounding noise of
+                # the cancelled part is judged on a tenth of the weight-gradient scale
+                part_zero = k.endswith("s_model.node_mlp_1.2.bias")
+                den = max(full[k].abs().max().item(),
+                          (1.0 if zero_grad else 0.1 if part_zero else 1e-3) * full[scale_key].abs().max().item())
                 err = (out[r][k] - full[k]).abs().max().item() / den
+                if os.environ.get("PFS_SHARD_TEST_VERBOSE"):
+                    print("rank %d %-40s err %.3e  |g| %.3e  |g_w| %.3e" % (r, k, err, full[k].abs().max().item(),
+                                                                          full[scale_key].abs().max().item()))
+                    continue
                 assert err < 3e-2, (k, err)
             if k.startswith("b.") and not k.endswith("num_batches_tracked"):
                 close(out[r][k], full[k], k)
+        # collectives of one Block forward + backward: 11 exchanges + the one-time shard-size / class-count exchanges
+        assert int(out[r]["_calls"]) <= 16, int(out[r]["_calls"])
     # every rank ends with the same (global) parameter gradients
     for k in full:
         if k.startswith("p."):

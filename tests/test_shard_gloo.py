@@ -1,7 +1,7 @@
 """Host-side logic of fibre-range sharding on CPU (two gloo ranks): the exchange steps of
-pfs-neural-net_b200/shard.py -- statistics merge (count, mean, M2), plain sums, the replicated()
-scope -- and, end to end, that a fibre-sharded run of the ORACLE with those exchanges plugged in
-at the points wide.py uses them reproduces the unsharded result."""
+pfs-neural-net_b200/shard.py -- statistics merge (count, mean, M2) with cached shard sizes, plain and packed
+sums, the replicated() scope -- and the fibre-range partition of a general edge list.
+The sharded Block itself is compared with the single-GPU Block in tests/test_gpu_wide_shard.py."""
 import os
 import socket
 
@@ -44,7 +44,17 @@ def _worker(rank, world, port, out):
             r = torch.full((2,), 5.0)
             ok &= torch.equal(shard.allreduce_sum(r), torch.full((2,), 5.0))     # class rows: no exchange
         calls, nbytes = shard.traffic()
-        ok &= calls == 3 and nbytes > 0
+        ok &= calls == 3 and nbytes > 0                       # shard sizes (once), the moment gather, the sum
+        # a second merge of the same shard sizes costs ONE collective and no host synchronisation
+        n2, gmean2, gm22 = shard.allreduce_moments(float(mine.shape[0]), mean, m2)
+        ok &= shard.traffic()[0] == 4 and n2 == 1000.0 and torch.equal(gmean2, gmean) and torch.equal(gm22, gm2)
+        ok &= shard.shard_counts(mine.shape[0]) == (380, 620) and shard.total_count(mine.shape[0]) == 1000
+        # several small tensors, one collective
+        a, b, c = mine.sum(0), mine[:, :2].sum(0).reshape(1, 2), (mine ** 2).sum(0)
+        pa, pb, pc = shard.allreduce_packed([a, b, c])
+        ok &= shard.traffic()[0] == 5 and pb.shape == (1, 2)
+        ok &= torch.allclose(pa, full.sum(0), rtol=1e-6) and torch.allclose(pb[0], full[:, :2].sum(0), rtol=1e-6)
+        ok &= torch.allclose(pc, (full ** 2).sum(0), rtol=1e-6)
     ok &= not shard.active()
     out[rank] = bool(ok)
     dist.destroy_process_group()
@@ -63,3 +73,22 @@ def test_sharding_requires_process_group():
     with pytest.raises(RuntimeError):
         with shard.fibre_sharded():
             pass
+
+
+def test_partition_fibres_covers_the_edge_list_once():
+    g = torch.Generator().manual_seed(5)
+    S, T, world = 37, 6, 4
+    keep = torch.rand(S * T, generator=g) < 0.3
+    e = torch.nonzero(keep).flatten()
+    e = e[torch.randperm(e.numel(), generator=g)]
+    ei = torch.stack([e // T, e % T])
+    seen = []
+    for r in range(world):
+        local, sl, pos = shard.partition_fibres(ei, S, world, r)
+        assert local.shape == (2, pos.numel())
+        assert torch.equal(local[0] + sl.start, ei[0][pos]) and torch.equal(local[1], ei[1][pos])
+        assert (local[0] >= 0).all() and (local[0] < sl.stop - sl.start).all()
+        assert torch.equal(pos, torch.sort(pos).values)          # the edge list's own order is kept
+        seen.append(pos)
+    allpos = torch.cat(seen)
+    assert torch.equal(torch.sort(allpos).values, torch.arange(ei.shape[1]))
