@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define PFS_ABI_VERSION 4
+#define PFS_ABI_VERSION 5
 
 enum {
     PFS_OK = 0,
@@ -147,6 +147,15 @@ typedef struct pfs_edge_args {
     float *g_w1, *g_b1, *g_w2, *g_b2, *g_gamma, *g_beta;
     void* workspace; size_t workspace_bytes;
     void* stream;
+    /* ABI 5 */
+    int32_t defer_affine;                        /* forward, normed: x_e_out receives the PRE-norm z and bn_save the per-graph
+                                                    (scale, shift); the caller hands bn_save to the next consumer of x_e_out
+                                                    (pfs_source_args.x_e_affine), whose edge pass normalises the rows in place
+                                                    as it reads them -- one pass over [G,E,F] and one launch less per Block */
+    int32_t reserved0;
+    float *table_s, *table_t;                    /* optional [G,S,4F], [G,T,4F]: node tables of the first-layer split.  The
+                                                    forward writes them here instead of its workspace; a backward given the
+                                                    same buffers reads them instead of recomputing them */
 } pfs_edge_args;
 int pfs_edge_fwd(const pfs_edge_args* a);
 int pfs_edge_bwd(const pfs_edge_args* a);
@@ -178,6 +187,11 @@ typedef struct pfs_source_args {
     float *g_w1, *g_b1, *g_w2, *g_b2, *g_w3, *g_b3, *g_w4, *g_b4, *g_gamma, *g_beta;
     void* workspace; size_t workspace_bytes;
     void* stream;
+    /* ABI 5 */
+    const float* x_e_affine;                     /* optional, forward: bn_save [G,4,F] of a pfs_edge_fwd run with defer_affine;
+                                                    x_e then holds the pre-norm z, and the edge pass stores
+                                                    x_e' = scale z + shift back into x_e_norm_out as it goes */
+    float* x_e_norm_out;                         /* [G,E,F], may alias x_e (every row is read and written by one thread) */
 } pfs_source_args;
 int pfs_source_fwd(const pfs_source_args* a);
 int pfs_source_bwd(const pfs_source_args* a);
@@ -207,6 +221,9 @@ typedef struct pfs_target_args {
     float *g_w1, *g_b1, *g_w2, *g_b2, *g_w3, *g_b3, *g_w4, *g_b4, *g_gamma, *g_beta;
     void* workspace; size_t workspace_bytes;
     void* stream;
+    /* ABI 5 */
+    float* table_s;                              /* optional [G,S,2F]: the fibre table of the first-layer split, written by the
+                                                    forward and read back by a backward given the same buffer */
 } pfs_target_args;
 int pfs_target_fwd(const pfs_target_args* a);
 int pfs_target_bwd(const pfs_target_args* a);

@@ -18,7 +18,7 @@ HEADER = os.path.join(os.path.dirname(_HERE), "include", "pfs_b200.h")
 PFS_LAYOUT_DENSE = 0
 PFS_LAYOUT_CSR = 1
 PFS_TILE_EDGES = 256
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 _P = ct.c_void_p
 
@@ -49,6 +49,8 @@ class EdgeArgs(ct.Structure):
         (_P, "x_e_out bn_save act_save g_out g_x_s g_x_t g_x_e g_u g_w1 g_b1 g_w2 g_b2 g_gamma g_beta workspace"),
         (ct.c_size_t, "workspace_bytes"),
         (_P, "stream"),
+        (ct.c_int32, "defer_affine reserved0"),
+        (_P, "table_s table_t"),
     ])
 
 
@@ -62,6 +64,7 @@ class SourceArgs(ct.Structure):
              "g_w1 g_b1 g_w2 g_b2 g_w3 g_b3 g_w4 g_b4 g_gamma g_beta workspace"),
         (ct.c_size_t, "workspace_bytes"),
         (_P, "stream"),
+        (_P, "x_e_affine x_e_norm_out"),
     ])
 
 
@@ -75,6 +78,7 @@ class TargetArgs(ct.Structure):
              "g_w1 g_b1 g_w2 g_b2 g_w3 g_b3 g_w4 g_b4 g_gamma g_beta workspace"),
         (ct.c_size_t, "workspace_bytes"),
         (_P, "stream"),
+        (_P, "table_s"),
     ])
 
 

@@ -536,8 +536,9 @@ int edge_fwd_impl(const pfs_edge_args& a, const Topo& tp) {
     const int nrec = chunk_records(grid, total, tp.ntiles);
     Bump ws(a.workspace, a.workspace_bytes);
     float* uvec = ws.f((size_t)tp.G * H);
-    float* Ps = ws.f((size_t)tp.G * tp.S * H);
-    float* Pt = ws.f((size_t)tp.G * tp.T * H);
+    PFS_REQUIRE((a.table_s == nullptr) == (a.table_t == nullptr), "table_s and table_t go together");
+    float* Ps = a.table_s ? a.table_s : ws.f((size_t)tp.G * tp.S * H);
+    float* Pt = a.table_t ? a.table_t : ws.f((size_t)tp.G * tp.T * H);
     float* part = ws.f((size_t)grid * nrec * bn_partial_stride(F));
     float* wstage = ws.f(kConstFloats);
     if (!ws.ok) return fail(PFS_ERR_WORKSPACE, "edge_fwd: workspace too small (%zu B)", a.workspace_bytes);
@@ -566,7 +567,7 @@ int edge_fwd_impl(const pfs_edge_args& a, const Topo& tp) {
         PFS_TRY(bn_forward_tail(F, tp.G, tp.E, part, tp.ntiles, 1, a.training, a.gamma, a.beta, a.running_mean,
                                 a.running_var, (long long*)a.num_batches_tracked, a.eps, a.momentum, a.bn_save, st,
                                 grid, nrec));
-        PFS_TRY(affine_rows(a.x_e_out, a.bn_save, F, tp.E, tp.G, a.x_e_out, st));
+        if (!a.defer_affine) PFS_TRY(affine_rows(a.x_e_out, a.bn_save, F, tp.E, tp.G, a.x_e_out, st));
     }
     return PFS_OK;
 }
@@ -598,8 +599,10 @@ int edge_bwd_impl(const pfs_edge_args& a, const Topo& tp) {
     constexpr int pstride = 2 * H * F + F;
     Bump ws(a.workspace, a.workspace_bytes);
     float* uvec = ws.f((size_t)tp.G * H);
-    float* Ps = ws.f((size_t)tp.G * tp.S * H);
-    float* Pt = ws.f((size_t)tp.G * tp.T * H);
+    PFS_REQUIRE((a.table_s == nullptr) == (a.table_t == nullptr), "table_s and table_t go together");
+    const bool cached = a.table_s != nullptr;              // node tables kept by the forward: not recomputed
+    float* Ps = cached ? a.table_s : ws.f((size_t)tp.G * tp.S * H);
+    float* Pt = cached ? a.table_t : ws.f((size_t)tp.G * tp.T * H);
     float* coef = ws.f((size_t)tp.G * 6 * F);
     float* statp = ws.f((size_t)total * 2 * F);
     float* dgb = ws.f((size_t)tp.G * 2 * F);
@@ -623,7 +626,7 @@ int edge_bwd_impl(const pfs_edge_args& a, const Topo& tp) {
         pl.it[1] = PackItem{a.w2, H, 0, H, F, 0, CW::kW2o};         // W2 as stored [F][H]
         pl.it[2] = PackItem{a.w1, H, 2 * F, F, H, 0, CW::kW1o};     // W1_e as stored [H][F]
         pl.n = 3;
-        PFS_TRY((run_prep<F, H>(tp.G, jobs, saved ? 0 : 2, a.w1, H, a.u, pl, CW::kFloats, wstage, st)));
+        PFS_TRY((run_prep<F, H>(tp.G, jobs, (saved || cached) ? 0 : 2, a.w1, H, a.u, pl, CW::kFloats, wstage, st)));
     }
     const int n = tp.G * F;
     k_edge_bn_bwd_coef<<<(n + 127) / 128, 128, 0, st>>>(0, mode, F, tp.G, tp.ntiles, tp.E, a.bn_save, a.gamma, a.beta,
@@ -706,7 +709,8 @@ int source_fwd_impl(const pfs_source_args& a, const Topo& tp) {
     }
     {
         PFS_REQUIRE((a.act_save == nullptr) == (a.msg_save == nullptr), "act_save and msg_save go together");
-        SourceEdgeFwdParams p{tp, a.x_e, Qt, a.w1, a.w2, a.b2, a.moments, a.act_save, a.msg_save};
+        if (a.x_e_affine) PFS_REQUIRE(a.x_e_norm_out, "x_e_affine needs x_e_norm_out");
+        SourceEdgeFwdParams p{tp, a.x_e, Qt, a.w1, a.w2, a.b2, a.moments, a.act_save, a.msg_save, a.x_e_affine, a.x_e_norm_out};
         const int grid = persistent_grid(k_source_edge_fwd<F>, 0, total);
         k_source_edge_fwd<F><<<grid, kThreads, 0, st>>>(p);
         PFS_LAUNCH_CHECK("k_source_edge_fwd");
@@ -905,7 +909,7 @@ int target_fwd_impl(const pfs_target_args& a, const Topo& tp) {
     prof_mark(nullptr, st);
     const int total = tp.ntiles * tp.G;
     Bump ws(a.workspace, a.workspace_bytes);
-    float* Rs = ws.f((size_t)tp.G * tp.S * M);
+    float* Rs = a.table_s ? a.table_s : ws.f((size_t)tp.G * tp.S * M);
     float* stage = ws.f(class_stage_floats(tp, M));
     float* cscs = ws.f(csc_scratch_floats(tp, M) + 1);
     float* wstage = ws.f(kConstFloats);
@@ -958,7 +962,8 @@ int target_bwd_impl(const pfs_target_args& a, const Topo& tp) {
     constexpr int pstride_e = M * F;
     constexpr int ptail = tail_partial_floats(F);
     Bump ws(a.workspace, a.workspace_bytes);
-    float* Rs = ws.f((size_t)tp.G * tp.S * M);
+    const bool cached = a.table_s != nullptr;              // R_s kept by the forward: not recomputed
+    float* Rs = cached ? a.table_s : ws.f((size_t)tp.G * tp.S * M);
     float* dasum = ws.f((size_t)tp.G * tp.T * M);
     float* gpart = ws.f((size_t)tp.G * ptail);
     float* dRs = ws.f((size_t)tp.G * tp.S * M);
@@ -994,7 +999,7 @@ int target_bwd_impl(const pfs_target_args& a, const Topo& tp) {
         TableJob jobs[2] = {TableJob{a.x_s, tp.S, 0, -1, a.b1, Rs}, TableJob{}};
         PackList pl{};
         add_msg_weights<F>(pl, a.w1, nullptr, nullptr);
-        PFS_TRY((run_prep<F, M>(tp.G, jobs, saved ? 0 : 1, a.w1, M, a.u, pl, MsgEdgeConst<F>::kFloats, wstage, st)));
+        PFS_TRY((run_prep<F, M>(tp.G, jobs, (saved || cached) ? 0 : 1, a.w1, M, a.u, pl, MsgEdgeConst<F>::kFloats, wstage, st)));
     }
     {
         TargetEdgeBwdParams p{tp, a.x_e, Rs, a.w1, dasum, a.g_x_e, a.g_x_e_add, dRs, wpe, pstride_e, a.act_save};

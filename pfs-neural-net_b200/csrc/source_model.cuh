@@ -30,6 +30,8 @@ struct SourceEdgeFwdParams {
     float* moments;        // [G,S,5,2F]: mean, E[m^2], c2, c3, c4
     float* act_save;       // [G,E(q),2F] hidden activations for the backward, or null
     float* msg_save;       // [G,E(q),2F] messages for the backward, or null
+    const float* xaff;     // [G,4,F] (rows 2, 3: scale, shift) of a deferred EdgeModel norm, or null: xe2 then holds z
+    float* xe_norm_out;    // [G,E,F] where x_e' = scale z + shift is stored (may alias xe2)
 };
 
 template <int F>
@@ -46,6 +48,12 @@ __global__ void __launch_bounds__(kThreads) k_source_edge_fwd(const SourceEdgeFw
             const EdgeRef er = get_edge(tp, t, threadIdx.x);
             float x[F], h[M], m[M];
             load_row<F>(p.xe2 + ((size_t)t.g * tp.E + er.e) * F, x);
+            if (p.xaff) {      // the EdgeModel's (double) BatchNorm affine, deferred to its first consumer
+                const float* sc = p.xaff + (size_t)t.g * 4 * F + 2 * F;
+#pragma unroll
+                for (int j = 0; j < F; ++j) x[j] = fmaf(x[j], __ldg(sc + j), __ldg(sc + F + j));
+                store_row<F>(p.xe_norm_out + ((size_t)t.g * tp.E + er.e) * F, x);
+            }
             load_row<M>(p.Qt + ((size_t)t.g * tp.T + er.tgt) * M, h);
             dense_acc_c<F, M, CW::kW1t>(x, h);
 #pragma unroll

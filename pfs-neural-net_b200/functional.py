@@ -23,6 +23,10 @@ BN_MOMENTUM = 0.1
 # 0.22) and the backward kernels do not speed up (k_edge_bwd2 1.19 -> 1.24 ms): they wait on their per-thread row loads,
 # of which there are now more, not on instruction issue.  Step 5.38 -> 5.82 ms.
 SAVE_ACT = os.environ.get("PFS_SAVE_ACT", "0") == "1"
+# PFS_KEEP_TABLES=0: the backward recomputes the node tables of the first-layer split (P_s, P_t, R_s) instead of reading the
+# forward's; PFS_DEFER_AFFINE=0: the EdgeModel applies its norm itself inside a Block too (A/B runs)
+KEEP_TABLES = os.environ.get("PFS_KEEP_TABLES", "1") == "1"
+DEFER_AFFINE = os.environ.get("PFS_DEFER_AFFINE", "1") == "1"
 
 
 def _want_save(ctx):
@@ -151,7 +155,10 @@ class EdgeFunction(torch.autograd.Function):
     """EdgeModel (reference src/gnn.py:73-101) -> pfs_edge_fwd / pfs_edge_bwd."""
 
     @staticmethod
-    def forward(ctx, topo, training, normed, x_s, x_t, x_e, u, w1, b1, w2, b2, gamma, beta, rm, rv, nbt):
+    def forward(ctx, topo, training, normed, x_s, x_t, x_e, u, w1, b1, w2, b2, gamma, beta, rm, rv, nbt, defer=None):
+        """`defer`: a dict handed in by Block.forward.  When the module is normed the BatchNorm affine is NOT applied here:
+        the returned tensor holds the pre-norm z, defer["affine"] the per-graph (scale, shift), and the next consumer
+        (SourceFunction with edge_affine=...) normalises the rows in place while it reads them."""
         dev = _dev_check(x_s, x_t, x_e, u, w1, b1, w2, b2, gamma, beta, rm, rv)
         ctx.save_act = _want_save(ctx)
         x_s, x_t, x_e, u, w1, b1, w2, b2, gamma, beta = (_c(t) for t in (x_s, x_t, x_e, u, w1, b1, w2, b2, gamma, beta))
@@ -160,23 +167,31 @@ class EdgeFunction(torch.autograd.Function):
         out = torch.empty_like(x_e)
         bn_save = torch.empty(G, 4, F, device=dev, dtype=torch.float32) if normed else None
         act = torch.empty(G, topo.E, 4 * F, device=dev, dtype=torch.float32) if ctx.save_act else None
+        # node tables of the first-layer split, kept for the backward when one will follow (it then skips their recomputation)
+        keep = KEEP_TABLES and any(ctx.needs_input_grad) and not ctx.save_act
+        tab_s = torch.empty(G, topo.S, 4 * F, device=dev, dtype=torch.float32) if keep else None
+        tab_t = torch.empty(G, topo.T, 4 * F, device=dev, dtype=torch.float32) if keep else None
         a = _abi.EdgeArgs()
         ws = _fill_common(a, topo, G, F, dict(x_s=x_s, x_t=x_t, x_e=x_e, u=u, w1=w1, b1=b1, w2=w2, b2=b2, gamma=gamma,
                                               beta=beta, running_mean=rm, running_var=rv, num_batches_tracked=nbt,
-                                              x_e_out=out, bn_save=bn_save, act_save=act))
+                                              x_e_out=out, bn_save=bn_save, act_save=act, table_s=tab_s, table_t=tab_t))
         a.training, a.normed, a.eps, a.momentum = int(training), int(normed), BN_EPS, BN_MOMENTUM
+        deferred = defer is not None and bool(normed) and DEFER_AFFINE
+        a.defer_affine = int(deferred)
         with torch.cuda.device(dev):
             a.stream = _stream(dev)
             _abi.check(lib.pfs_edge_fwd(ct.byref(a)), "pfs_edge_fwd")
+        if deferred:
+            defer["affine"] = bn_save
         ctx.topo, ctx.training, ctx.normed = topo, training, normed
         ctx.buffers = (rm, rv)
-        ctx.save_for_backward(x_s, x_t, x_e, u, w1, b1, w2, b2, gamma, beta, out, bn_save, act)
+        ctx.save_for_backward(x_s, x_t, x_e, u, w1, b1, w2, b2, gamma, beta, out, bn_save, act, tab_s, tab_t)
         del ws
         return out
 
     @staticmethod
     def backward(ctx, g):
-        x_s, x_t, x_e, u, w1, b1, w2, b2, gamma, beta, out, bn_save, act = ctx.saved_tensors
+        x_s, x_t, x_e, u, w1, b1, w2, b2, gamma, beta, out, bn_save, act, tab_s, tab_t = ctx.saved_tensors
         topo, dev = ctx.topo, x_e.device
         G, F = x_s.shape[0], x_s.shape[2]
         lib = _abi.load_library()
@@ -189,7 +204,8 @@ class EdgeFunction(torch.autograd.Function):
         a = _abi.EdgeArgs()
         rm, rv = ctx.buffers
         named = dict(x_s=x_s, x_t=x_t, x_e=x_e, u=u, w1=w1, b1=b1, w2=w2, b2=b2, gamma=gamma, beta=beta,
-                     running_mean=rm, running_var=rv, x_e_out=out, bn_save=bn_save, act_save=act, g_out=g)
+                     running_mean=rm, running_var=rv, x_e_out=out, bn_save=bn_save, act_save=act, g_out=g,
+                     table_s=tab_s, table_t=tab_t)
         named.update(gr)
         ws = _fill_common(a, topo, G, F, named)
         a.training, a.normed, a.eps, a.momentum = int(ctx.training), int(ctx.normed), BN_EPS, BN_MOMENTUM
@@ -198,16 +214,21 @@ class EdgeFunction(torch.autograd.Function):
             _abi.check(lib.pfs_edge_bwd(ct.byref(a)), "pfs_edge_bwd")
         del ws
         return (None, None, None, gr["g_x_s"], gr["g_x_t"], gr["g_x_e"], gr["g_u"], gr["g_w1"], gr["g_b1"],
-                gr["g_w2"], gr["g_b2"], gr["g_gamma"], gr["g_beta"], None, None, None)
+                gr["g_w2"], gr["g_b2"], gr["g_gamma"], gr["g_beta"], None, None, None, None)
 
 
 class SourceFunction(torch.autograd.Function):
     """SModel (reference src/gnn.py:104-154) -> pfs_source_fwd / pfs_source_bwd."""
 
     @staticmethod
-    def forward(ctx, topo, training, normed, x_s, x_t, x_e, u, w1, b1, w2, b2, w3, b3, w4, b4, gamma, beta, rm, rv, nbt, bus=None):
+    def forward(ctx, topo, training, normed, x_s, x_t, x_e, u, w1, b1, w2, b2, w3, b3, w4, b4, gamma, beta, rm, rv, nbt, bus=None,
+                edge_affine=None):
+        """`edge_affine`: bn_save of an EdgeFunction run with a deferred norm -- x_e then holds the pre-norm z and is
+        normalised IN PLACE by the edge pass of this call (every row is read and written by the same thread)."""
         dev = _dev_check(x_s, x_t, x_e, u, w1, b1, w2, b2, w3, b3, w4, b4, gamma, beta, rm, rv)
         save_act = _want_save(ctx)
+        if edge_affine is not None and not x_e.is_contiguous():
+            raise _abi.PfsError("deferred edge norm needs a contiguous x_e")
         (x_s, x_t, x_e, u, w1, b1, w2, b2, w3, b3, w4, b4, gamma, beta) = (
             _c(t) for t in (x_s, x_t, x_e, u, w1, b1, w2, b2, w3, b3, w4, b4, gamma, beta))
         G, F = _check_shapes(topo, x_s, x_t, x_e, u)
@@ -224,7 +245,8 @@ class SourceFunction(torch.autograd.Function):
         ws = _fill_common(a, topo, G, F, dict(
             x_s=x_s, x_t=x_t, x_e=x_e, u=u, w1=w1, b1=b1, w2=w2, b2=b2, w3=w3, b3=b3, w4=w4, b4=b4, gamma=gamma,
             beta=beta, running_mean=rm, running_var=rv, num_batches_tracked=nbt, x_s_out=out, moments=moments,
-            hidden=hidden, y_pre=y_pre, bn_save=bn_save, act_save=act, msg_save=msg))
+            hidden=hidden, y_pre=y_pre, bn_save=bn_save, act_save=act, msg_save=msg,
+            x_e_affine=edge_affine, x_e_norm_out=x_e if edge_affine is not None else None))
         a.training, a.normed, a.eps, a.momentum = int(training), int(normed), BN_EPS, BN_MOMENTUM
         with torch.cuda.device(dev):
             a.stream = _stream(dev)
@@ -266,7 +288,7 @@ class SourceFunction(torch.autograd.Function):
         del ws
         return (None, None, None, gr["g_x_s"], gr["g_x_t"], gr["g_x_e"], gr["g_u"], gr["g_w1"], gr["g_b1"],
                 gr["g_w2"], gr["g_b2"], gr["g_w3"], gr["g_b3"], gr["g_w4"], gr["g_b4"], gr["g_gamma"], gr["g_beta"],
-                None, None, None, None)
+                None, None, None, None, None)
 
 
 class TargetFunction(torch.autograd.Function):
@@ -286,11 +308,13 @@ class TargetFunction(torch.autograd.Function):
         act_sum = torch.empty(G, topo.T, 2 * F, **f32)
         y_pre = torch.empty(G, topo.T, F, **f32)
         bn_save = torch.empty(G, 4, F, **f32) if normed else None
+        keep = KEEP_TABLES and any(ctx.needs_input_grad) and not save_act
+        tab_s = torch.empty(G, topo.S, 2 * F, **f32) if keep else None
         a = _abi.TargetArgs()
         ws = _fill_common(a, topo, G, F, dict(
             x_s=x_s, x_t=x_t, x_e=x_e, u=u, w1=w1, b1=b1, w2=w2, b2=b2, w3=w3, b3=b3, w4=w4, b4=b4, gamma=gamma,
             beta=beta, running_mean=rm, running_var=rv, num_batches_tracked=nbt, x_t_out=out, act_sum=act_sum,
-            y_pre=y_pre, bn_save=bn_save, act_save=act))
+            y_pre=y_pre, bn_save=bn_save, act_save=act, table_s=tab_s))
         a.training, a.normed, a.eps, a.momentum = int(training), int(normed), BN_EPS, BN_MOMENTUM
         with torch.cuda.device(dev):
             a.stream = _stream(dev)
@@ -298,13 +322,13 @@ class TargetFunction(torch.autograd.Function):
         ctx.topo, ctx.training, ctx.normed = topo, training, normed
         ctx.bus = bus
         ctx.buffers = (rm, rv)
-        ctx.save_for_backward(x_s, x_t, x_e, u, w1, b1, w2, b2, w3, b3, w4, b4, gamma, beta, act_sum, y_pre, bn_save, act)
+        ctx.save_for_backward(x_s, x_t, x_e, u, w1, b1, w2, b2, w3, b3, w4, b4, gamma, beta, act_sum, y_pre, bn_save, act, tab_s)
         del ws
         return out
 
     @staticmethod
     def backward(ctx, g):
-        (x_s, x_t, x_e, u, w1, b1, w2, b2, w3, b3, w4, b4, gamma, beta, act_sum, y_pre, bn_save, act) = ctx.saved_tensors
+        (x_s, x_t, x_e, u, w1, b1, w2, b2, w3, b3, w4, b4, gamma, beta, act_sum, y_pre, bn_save, act, tab_s) = ctx.saved_tensors
         topo, dev = ctx.topo, x_e.device
         G, F = x_s.shape[0], x_s.shape[2]
         lib = _abi.load_library()
@@ -318,7 +342,7 @@ class TargetFunction(torch.autograd.Function):
         rm, rv = ctx.buffers
         named = dict(x_s=x_s, x_t=x_t, x_e=x_e, u=u, w1=w1, b1=b1, w2=w2, b2=b2, w3=w3, b3=b3, w4=w4, b4=b4,
                      gamma=gamma, beta=beta, running_mean=rm, running_var=rv, act_sum=act_sum, y_pre=y_pre,
-                     bn_save=bn_save, act_save=act, g_out=g)
+                     bn_save=bn_save, act_save=act, g_out=g, table_s=tab_s)
         add = ctx.bus.addend_for_target(x_e) if ctx.bus is not None else None
         named.update(gr, g_x_e_add=add)
         a = _abi.TargetArgs()

@@ -161,7 +161,7 @@ class EdgeModel(MLP):
         topo = get_topology(edge_index, x_s.shape[1], x_t.shape[1])
         normed, gamma, beta, rm, rv, nbt = _norm_tensors(self)
         out = pf.EdgeFunction.apply(topo, self.training, normed, x_s, x_t, edge_attr, u, self[0].weight, self[0].bias,
-                                    self[2].weight, self[2].bias, gamma, beta, rm, rv, nbt)
+                                    self[2].weight, self[2].bias, gamma, beta, rm, rv, nbt, getattr(self, "_defer", None))
         return out[0] if single else out
 
 
@@ -190,7 +190,8 @@ class SModel(torch.nn.Module):
         m1, m2 = self.node_mlp_1, self.node_mlp_2
         out = pf.SourceFunction.apply(topo, self.training, normed, x_s, x_t, edge_attr, u, m1[0].weight, m1[0].bias,
                                       m1[2].weight, m1[2].bias, m2[0].weight, m2[0].bias, m2[2].weight, m2[2].bias,
-                                      gamma, beta, rm, rv, nbt, getattr(self, "_xe_bus", None))
+                                      gamma, beta, rm, rv, nbt, getattr(self, "_xe_bus", None),
+                                      getattr(self, "_edge_affine", None))
         return out[0] if single else out
 
 
@@ -269,8 +270,18 @@ class Block(torch.nn.Module):
 
     def forward(self, args):
         edge_index, x_s, x_t, x_e, x_u = args
+        # fp32 path: the EdgeModel leaves its BatchNorm affine to the SModel's edge pass, which normalises x_e' in place
+        # while it reads it (one pass over [G, E, F] and one launch less); nothing in between looks at x_e'
+        defer = None
+        if (hasattr(self, "edge_model") and hasattr(self, "s_model") and x_e.is_cuda and x_e.dtype == torch.float32):
+            defer = {}
         if hasattr(self, "edge_model"):
-            x_e = self.edge_model(x_s, x_t, edge_index, x_e, x_u)
+            self.edge_model._defer = defer
+            try:
+                x_e = self.edge_model(x_s, x_t, edge_index, x_e, x_u)
+            finally:
+                self.edge_model._defer = None
+        edge_affine = defer.pop("affine", None) if defer else None
         # fp32 path: the three gradients of x_e' (SModel, TModel, the output) are added up inside the backward
         # kernels instead of by autograd (functional.XeGradBus); the values are the same sum
         bus = None
@@ -282,6 +293,7 @@ class Block(torch.nn.Module):
         try:
             if hasattr(self, "s_model"):
                 self.s_model._xe_bus = bus
+                self.s_model._edge_affine = edge_affine
                 x_s = self.s_model(x_s, x_t, edge_index, x_e_s, x_u)
             if hasattr(self, "t_model"):
                 self.t_model._xe_bus = bus
@@ -289,6 +301,7 @@ class Block(torch.nn.Module):
         finally:
             if hasattr(self, "s_model"):
                 self.s_model._xe_bus = None
+                self.s_model._edge_affine = None
             if hasattr(self, "t_model"):
                 self.t_model._xe_bus = None
         if hasattr(self, "global_model"):
