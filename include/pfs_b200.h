@@ -100,6 +100,8 @@ int pfs_profile_report(char* buf, size_t buflen);
 
 /* Workspace (bytes) sufficient for any forward/backward call on this topology. */
 size_t pfs_workspace_bytes(const pfs_topology* topo);
+/* Edge tiles per graph of this topology (rows of the per-tile statistics buffers edge_bn_stat / bn_stat_in). */
+int32_t pfs_stat_tiles(const pfs_topology* topo);
 
 /* -------------------------------------------------------------------------------------------
  * topology (replaces the implicit advanced-indexing / torch_scatter index handling of
@@ -156,6 +158,10 @@ typedef struct pfs_edge_args {
     float *table_s, *table_t;                    /* optional [G,S,4F], [G,T,4F]: node tables of the first-layer split.  The
                                                     forward writes them here instead of its workspace; a backward given the
                                                     same buffers reads them instead of recomputing them */
+    const float* bn_stat_in;                     /* optional, backward, train mode: [G*tiles][2F] per-tile sums of g_out and
+                                                    g_out (x_e_out - beta) written by the call that produced g_out
+                                                    (pfs_source_args.edge_bn_stat, same topology): the statistics pass over
+                                                    g_out and x_e_out is skipped */
 } pfs_edge_args;
 int pfs_edge_fwd(const pfs_edge_args* a);
 int pfs_edge_bwd(const pfs_edge_args* a);
@@ -192,6 +198,11 @@ typedef struct pfs_source_args {
                                                     x_e then holds the pre-norm z, and the edge pass stores
                                                     x_e' = scale z + shift back into x_e_norm_out as it goes */
     float* x_e_norm_out;                         /* [G,E,F], may alias x_e (every row is read and written by one thread) */
+    const float* edge_bn_shift;                  /* optional, backward: the EdgeModel's norm.bias [F] ... */
+    float* edge_bn_stat;                         /* ... and [G*tiles][2F] (tiles = pfs_stat_tiles(topo)): the edge pass, which
+                                                    stores the complete gradient of x_e (its own + g_x_e_add), also emits the
+                                                    per-tile sums of g and g (x_e - shift) the EdgeModel's BatchNorm backward
+                                                    needs (pfs_edge_args.bn_stat_in) */
 } pfs_source_args;
 int pfs_source_fwd(const pfs_source_args* a);
 int pfs_source_bwd(const pfs_source_args* a);

@@ -50,7 +50,7 @@ class EdgeArgs(ct.Structure):
         (ct.c_size_t, "workspace_bytes"),
         (_P, "stream"),
         (ct.c_int32, "defer_affine reserved0"),
-        (_P, "table_s table_t"),
+        (_P, "table_s table_t bn_stat_in"),
     ])
 
 
@@ -64,7 +64,7 @@ class SourceArgs(ct.Structure):
              "g_w1 g_b1 g_w2 g_b2 g_w3 g_b3 g_w4 g_b4 g_gamma g_beta workspace"),
         (ct.c_size_t, "workspace_bytes"),
         (_P, "stream"),
-        (_P, "x_e_affine x_e_norm_out"),
+        (_P, "x_e_affine x_e_norm_out edge_bn_shift edge_bn_stat"),
     ])
 
 
@@ -150,6 +150,7 @@ SYMBOLS = {
     "pfs_profile_enable": (ct.c_int, [ct.c_int]),
     "pfs_profile_report": (ct.c_int, [ct.c_char_p, ct.c_size_t]),
     "pfs_workspace_bytes": (ct.c_size_t, [ct.POINTER(TopologyStruct)]),
+    "pfs_stat_tiles": (_I32, [ct.POINTER(TopologyStruct)]),
     "pfs_detect_dense": (ct.c_int, [_P, _I64, _I32, _I32, _P, _P]),
     "pfs_build_topology_temp_bytes": (ct.c_size_t, [_I64, _I32, _I32]),
     "pfs_build_topology": (ct.c_int, [_P, _I64, _I32, _I32] + [_P] * 9 + [_P, ct.c_size_t, _P]),

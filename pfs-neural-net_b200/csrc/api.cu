@@ -468,7 +468,7 @@ int bn_forward_tail(int F, int G, long long rows, const float* partial, int ntil
         if (F > 32) return fail(PFS_ERR_UNSUPPORTED, "BatchNorm finalisation handles up to 32 features");
         BnFinalizeAll fa{partial, rec_ncta, rec_nrec, ntiles, bn_partial_stride(F), F, G, twice, gamma, beta, eps, momentum, rows,
                          save, rm, rv, nbt};
-        k_bn_finalize_all<<<1, 1024, 0, st>>>(fa);
+        k_bn_finalize_all<<<(n + 255) / 256, 256, 0, st>>>(fa);
         PFS_LAUNCH_CHECK("k_bn_finalize_all");
     } else {
         PFS_REQUIRE(rm && rv, "eval-mode BatchNorm needs running_mean / running_var");
@@ -629,19 +629,23 @@ int edge_bwd_impl(const pfs_edge_args& a, const Topo& tp) {
         PFS_TRY((run_prep<F, H>(tp.G, jobs, (saved || cached) ? 0 : 2, a.w1, H, a.u, pl, CW::kFloats, wstage, st)));
     }
     const int n = tp.G * F;
-    k_edge_bn_bwd_coef<<<(n + 127) / 128, 128, 0, st>>>(0, mode, F, tp.G, tp.ntiles, tp.E, a.bn_save, a.gamma, a.beta,
+    // statistics of the incoming gradient taken by the kernel that stored it (pfs_source_bwd, edge_bn_stat): train mode only
+    const bool stats_in = a.bn_stat_in != nullptr && mode == 1;
+    k_edge_bn_bwd_coef<<<(n + 127) / 128, 128, 0, st>>>(0, mode, 0, F, tp.G, tp.ntiles, tp.E, a.bn_save, a.gamma, a.beta,
                                                          a.running_mean, a.running_var, a.eps, statsum, coef, dgb);
     PFS_LAUNCH_CHECK("k_edge_bn_bwd_coef/0");
     if (mode != 0) {
-        EdgeBnStatParams sp{tp, a.x_e_out, a.g_out, coef, statp};
-        const int g2 = persistent_grid(k_edge_bn_bwd_stats<F>, 0, total);
-        k_edge_bn_bwd_stats<F><<<g2, kThreads, 0, st>>>(sp);
-        PFS_LAUNCH_CHECK("k_edge_bn_bwd_stats");
-        k_tile_partial_sums<<<tp.G, 256, 0, st>>>(statp, tp.ntiles, 2 * F, statsum);
+        if (!stats_in) {
+            EdgeBnStatParams sp{tp, a.x_e_out, a.g_out, coef, statp};
+            const int g2 = persistent_grid(k_edge_bn_bwd_stats<F>, 0, total);
+            k_edge_bn_bwd_stats<F><<<g2, kThreads, 0, st>>>(sp);
+            PFS_LAUNCH_CHECK("k_edge_bn_bwd_stats");
+        }
+        k_tile_partial_sums<<<tp.G, 256, 0, st>>>(stats_in ? a.bn_stat_in : statp, tp.ntiles, 2 * F, statsum);
         PFS_LAUNCH_CHECK("k_tile_partial_sums");
-        k_edge_bn_bwd_coef<<<(n + 127) / 128, 128, 0, st>>>(1, mode, F, tp.G, tp.ntiles, tp.E, a.bn_save, a.gamma,
-                                                             a.beta, a.running_mean, a.running_var, a.eps, statsum, coef,
-                                                             dgb);
+        k_edge_bn_bwd_coef<<<(n + 127) / 128, 128, 0, st>>>(1, mode, stats_in ? 1 : 0, F, tp.G, tp.ntiles, tp.E, a.bn_save,
+                                                             a.gamma, a.beta, a.running_mean, a.running_var, a.eps, statsum,
+                                                             coef, dgb);
         PFS_LAUNCH_CHECK("k_edge_bn_bwd_coef/1");
         PFS_TRY(colsum_pair(dgb, tp.G, 2 * F, 0, a.g_gamma, F, a.g_beta, F, st));
     }
@@ -769,8 +773,11 @@ int source_bwd_impl(const pfs_source_args& a, const Topo& tp) {
     constexpr bool kNodeMma = SourceNodeBwdMma<F>::fits;
     const bool use_mma = kNodeMma && node_bwd_mma_enabled();
     const bool saved = a.act_save != nullptr && a.msg_save != nullptr;
-    auto ke = saved ? k_source_edge_bwd<F, true> : k_source_edge_bwd<F, false>;
-    PFS_TRY(allow_smem(ke, SME::bytes));
+    const bool stats = a.edge_bn_stat != nullptr;
+    auto ke = saved ? k_source_edge_bwd<F, true, false> : stats ? k_source_edge_bwd<F, false, true> : k_source_edge_bwd<F, false, false>;
+    if (stats && saved) return fail(PFS_ERR_UNSUPPORTED, "edge_bn_stat together with saved activations");
+    const size_t smem_e = stats ? SME::bytes_stats : SME::bytes;
+    PFS_TRY(allow_smem(ke, smem_e));
     int gridn = 0;
     if (use_mma) {
         if constexpr (kNodeMma) {
@@ -785,7 +792,7 @@ int source_bwd_impl(const pfs_source_args& a, const Topo& tp) {
         PFS_TRY(allow_smem(k_source_node_bwd<F>, SourceNodeBwdSmem<F>::bytes));
         gridn = persistent_grid(k_source_node_bwd<F>, SourceNodeBwdSmem<F>::bytes, (long long)ntn * tp.G);
     }
-    const int gride = persistent_grid(ke, SME::bytes, total);
+    const int gride = persistent_grid(ke, smem_e, total);
     constexpr int pstride_n = J * K9 + F * J + F;
     constexpr int pstride_e = M * F + M * M + M;
     Bump ws(a.workspace, a.workspace_bytes);
@@ -809,6 +816,10 @@ int source_bwd_impl(const pfs_source_args& a, const Topo& tp) {
         TableJob jobs[2] = {TableJob{a.x_t, tp.T, 0, -1, a.b1, Qt}, TableJob{}};
         PackList pl{};
         add_msg_weights<F>(pl, a.w1, a.w2, a.b2);
+        if (a.edge_bn_stat) {
+            PFS_REQUIRE(a.edge_bn_shift, "edge_bn_stat needs edge_bn_shift");
+            pl.it[pl.n++] = PackItem{a.edge_bn_shift, 1, 0, 1, F, 0, MsgEdgeConst<F>::kEB};
+        }
         int nfloats = MsgEdgeConst<F>::kFloats;
         if constexpr (kNodeC) {
             using CW = SourceNodeConst<F>;
@@ -821,7 +832,8 @@ int source_bwd_impl(const pfs_source_args& a, const Topo& tp) {
     if (mode != 0) {
         int nchunk = (tp.S + 4095) / 4096;           // one CTA per 4096 fibres of a graph (1 for the C3 graphs)
         if (nchunk > 64) nchunk = 64;
-        k_bn_bwd_stats_rows<<<dim3(nchunk, tp.G), kThreads, sizeof(float) * 2 * kThreads, st>>>(
+        constexpr int kStatThreads = 1024;           // ~100 row lanes per CTA: few rows, many loads in flight per lane
+        k_bn_bwd_stats_rows<<<dim3(nchunk, tp.G), kStatThreads, sizeof(float) * 2 * kStatThreads, st>>>(
             a.g_out, a.y_pre, a.bn_save, tp.S, F, a.eps, nchunk, nchunk > 1 ? bnpart : bnstat);
         PFS_LAUNCH_CHECK("k_bn_bwd_stats_rows");
         if (nchunk > 1) {
@@ -867,8 +879,9 @@ int source_bwd_impl(const pfs_source_args& a, const Topo& tp) {
     {
         const bool dense = tp.layout == PFS_LAYOUT_DENSE;
         SourceEdgeBwdParams p{tp, a.x_e, Qt, a.w1, a.w2, a.b2, a.moments, coefA, a.g_x_e, a.g_x_e_add,
-                              dense ? stage : nullptr, dense ? nullptr : stage, wpe, pstride_e, a.act_save, a.msg_save};
-        ke<<<gride, kThreads, SME::bytes, st>>>(p);
+                              dense ? stage : nullptr, dense ? nullptr : stage, wpe, pstride_e, a.act_save, a.msg_save,
+                              a.edge_bn_stat};
+        ke<<<gride, kThreads, smem_e, st>>>(p);
         PFS_LAUNCH_CHECK("k_source_edge_bwd");
     }
     {
@@ -1187,6 +1200,11 @@ size_t pfs_workspace_bytes(const pfs_topology* t) {
     fl += G * 64 * 2 * F + 64;                                   // chunk partials of the node BatchNorm backward sums
     fl += 4096;
     return fl * sizeof(float) + 64 * 256;
+}
+
+int32_t pfs_stat_tiles(const pfs_topology* t) {
+    if (!t) return 0;
+    return t->layout == PFS_LAYOUT_DENSE ? dense_ntiles(t->S, t->T) : t->ntiles;
 }
 
 int pfs_detect_dense(const int64_t* edge_index, int64_t E, int32_t S, int32_t T, int32_t* flag_dev, void* stream) {

@@ -157,7 +157,9 @@ __global__ void __launch_bounds__(kThreads) k_edge_bn_bwd_stats(const EdgeBnStat
 //   stage 1 (after it): fills c1 = mean g, c2 = mean(g xhat1) * kappa and the per-graph
 //            gamma / beta gradients dgb[g][0..F) , dgb[g][F..2F)
 // mode: 0 = not normed, 1 = train, 2 = eval
-__global__ void k_edge_bn_bwd_coef(int stage, int mode, int F, int G, int ntiles, long long n_rows,
+// unscaled (stage 1, train mode): sums[.][F..2F) holds sum g (x_e_out - beta) (the statistics a previous kernel took
+// while it stored g, pfs_edge_args.bn_stat_in) instead of sum g xhat1; the factor inv is applied here
+__global__ void k_edge_bn_bwd_coef(int stage, int mode, int unscaled, int F, int G, int ntiles, long long n_rows,
                                    const float* __restrict__ save, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, const float* __restrict__ rm,
                                    const float* __restrict__ rv, float eps, const double* __restrict__ sums,
@@ -201,7 +203,9 @@ __global__ void k_edge_bn_bwd_coef(int stage, int mode, int F, int G, int ntiles
         c[4 * F + f] = (float)bt;
         return;
     }
-    const double sg = sums[(size_t)g * 2 * F + f], sgx = sums[(size_t)g * 2 * F + F + f];
+    const double sg = sums[(size_t)g * 2 * F + f];
+    double sgx = sums[(size_t)g * 2 * F + F + f];
+    if (unscaled) sgx *= (gm != 0.0) ? 1.0 / (gm * gm * r2) : 0.0;
     const double n = (double)n_rows;
     const double gbar = sg / n, mgx = sgx / n;
     const double sc = gm * r2, q = var * r1 * r1;

@@ -493,38 +493,52 @@ struct BnFinalizeAll {
     float *rm, *rv;
     long long* nbt;
 };
-__global__ void __launch_bounds__(1024) k_bn_finalize_all(const BnFinalizeAll a) {
+// ticket of the last-CTA pattern below (single-stream contract of the library: one such kernel at a time per device)
+__device__ unsigned int g_bn_ticket = 0;
+
+// Chan-merges up to kBatch records whose loads were issued together (the finalisation is latency-bound: a chain of
+// dependent L2 round trips per record made the single-CTA version take 25 - 50 us)
+__global__ void __launch_bounds__(256) k_bn_finalize_all(const BnFinalizeAll a) {
+    constexpr int kBatch = 4;
     const int F = a.F, G = a.G;
-    for (int i = threadIdx.x; i < G * F; i += blockDim.x) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < G * F) {
         const int g = i / F, f = i - g * F;
         double n = 0.0, mean = 0.0, m2 = 0.0;
+        const float* base;
+        long long stride;
+        int count;
         if (a.rec_ncta > 0) {
             const long long total = (long long)a.ntiles * G;
             long long c_lo = (long long)g * a.ntiles * a.rec_ncta / total - 1;
             long long c_hi = ((long long)(g + 1) * a.ntiles * a.rec_ncta) / total + 1;
             if (c_lo < 0) c_lo = 0;
             if (c_hi > a.rec_ncta - 1) c_hi = a.rec_ncta - 1;
-            const int stride = 2 * F + 2;
-            for (long long c = c_lo; c <= c_hi; ++c)
-                for (int r = 0; r < a.rec_nrec; ++r) {
-                    const float* p = a.partial + ((size_t)c * a.rec_nrec + r) * stride;
-                    const double nb = p[2 * F];
-                    if (nb <= 0.0 || (int)p[2 * F + 1] != g) continue;
-                    const double mb = p[f], sb = p[F + f];
-                    const double tot = n + nb, delta = mb - mean;
-                    mean += delta * (nb / tot);
-                    m2 += sb + delta * delta * (n * nb / tot);
-                    n = tot;
-                }
+            stride = 2 * F + 2;
+            base = a.partial + (size_t)c_lo * a.rec_nrec * stride;      // records of CTAs c_lo .. c_hi are contiguous
+            count = (int)(c_hi - c_lo + 1) * a.rec_nrec;
         } else {
-            const float* p = a.partial + (size_t)g * a.ntiles * a.pstride;
-            for (int t = 0; t < a.ntiles; ++t) {
-                const double nb = p[(size_t)t * a.pstride + 2 * F];
-                if (nb <= 0.0) continue;
-                const double mb = p[(size_t)t * a.pstride + f], sb = p[(size_t)t * a.pstride + F + f];
-                const double tot = n + nb, delta = mb - mean;
-                mean += delta * (nb / tot);
-                m2 += sb + delta * delta * (n * nb / tot);
+            stride = a.pstride;
+            base = a.partial + (size_t)g * a.ntiles * a.pstride;
+            count = a.ntiles;
+        }
+        for (int t0 = 0; t0 < count; t0 += kBatch) {
+            float nb[kBatch], gid[kBatch], mb[kBatch], sb[kBatch];
+#pragma unroll
+            for (int k = 0; k < kBatch; ++k) {
+                const bool in = t0 + k < count;
+                const float* p = base + (size_t)(in ? t0 + k : t0) * stride;
+                nb[k] = in ? p[2 * F] : 0.f;
+                gid[k] = a.rec_ncta > 0 ? p[2 * F + 1] : (float)g;
+                mb[k] = p[f];
+                sb[k] = p[F + f];
+            }
+#pragma unroll
+            for (int k = 0; k < kBatch; ++k) {
+                if (!(nb[k] > 0.f) || (int)gid[k] != g) continue;
+                const double cnt = nb[k], tot = n + cnt, delta = (double)mb[k] - mean;
+                mean += delta * (cnt / tot);
+                m2 += (double)sb[k] + delta * delta * (n * cnt / tot);
                 n = tot;
             }
         }
@@ -545,38 +559,50 @@ __global__ void __launch_bounds__(1024) k_bn_finalize_all(const BnFinalizeAll a)
         s[3 * F + f] = (float)(bt - scale * mean);
     }
     if (!a.rm || !a.rv) return;
-    __syncthreads();               // one CTA: its own global writes are visible to it after the barrier
-    const int f = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (f >= F) return;
+    // running buffers: by the CTA that finishes last, after every CTA's statistics are visible
+    __shared__ int is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(&g_bn_ticket, 1u);
+        is_last = t == gridDim.x - 1;
+        if (is_last) g_bn_ticket = 0;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const int lane = threadIdx.x & 31;
     const double mom = a.momentum, keep = 1.0 - mom, unb = (double)a.n_rows / (double)(a.n_rows - 1);
     const double step = a.twice ? keep * keep : keep;
-    double am = 0.0, av = 0.0;
-    for (int g = lane; g < G; g += 32) {
-        const double mean = a.save[(size_t)g * 4 * F + f], var = a.save[(size_t)g * 4 * F + F + f];
-        double cm, cv;
-        if (a.twice) {
-            const double gm = a.gamma[f];
-            const double var2 = gm * gm * var / (var + (double)a.eps);
-            cm = keep * mom * mean + mom * (double)a.beta[f];
-            cv = keep * mom * var * unb + mom * var2 * unb;
-        } else {
-            cm = mom * mean;
-            cv = mom * var * unb;
+    for (int f = threadIdx.x >> 5; f < F; f += blockDim.x >> 5) {
+        double am = 0.0, av = 0.0;
+        for (int g = lane; g < G; g += 32) {
+            const double mean = __ldcg(a.save + (size_t)g * 4 * F + f), var = __ldcg(a.save + (size_t)g * 4 * F + F + f);
+            double cm, cv;
+            if (a.twice) {
+                const double gm = a.gamma[f];
+                const double var2 = gm * gm * var / (var + (double)a.eps);
+                cm = keep * mom * mean + mom * (double)a.beta[f];
+                cv = keep * mom * var * unb + mom * var2 * unb;
+            } else {
+                cm = mom * mean;
+                cv = mom * var * unb;
+            }
+            const double w = pow(step, (double)(G - 1 - g));
+            am += w * cm;
+            av += w * cv;
         }
-        const double w = pow(step, (double)(G - 1 - g));
-        am += w * cm;
-        av += w * cv;
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        am += __shfl_xor_sync(0xffffffffu, am, o);
-        av += __shfl_xor_sync(0xffffffffu, av, o);
-    }
-    if (lane == 0) {
-        const double d = pow(step, (double)G);
-        a.rm[f] = (float)(d * (double)a.rm[f] + am);
-        a.rv[f] = (float)(d * (double)a.rv[f] + av);
-        if (f == 0 && a.nbt) *a.nbt += (long long)G * (a.twice ? 2 : 1);
+        for (int o = 16; o > 0; o >>= 1) {
+            am += __shfl_xor_sync(0xffffffffu, am, o);
+            av += __shfl_xor_sync(0xffffffffu, av, o);
+        }
+        if (lane == 0) {
+            const double d = pow(step, (double)G);
+            a.rm[f] = (float)(d * (double)a.rm[f] + am);
+            a.rv[f] = (float)(d * (double)a.rv[f] + av);
+            if (f == 0 && a.nbt) *a.nbt += (long long)G * (a.twice ? 2 : 1);
+        }
     }
 }
 
@@ -681,6 +707,18 @@ __global__ void k_bn_bwd_stats_rows(const float* __restrict__ gout, const float*
     if (lr < lanes) {
         const float mean = s[f], r = rsqrtf(s[F + f] + eps);
         int rr = r_begin + lr;
+        // four rows (eight loads) in flight per thread: the pass is a chain of memory round trips, not bandwidth
+        for (; rr + 3 * lanes < r_end; rr += 4 * lanes) {
+            const size_t i0 = ((size_t)g * rows + rr) * F + f, st = (size_t)lanes * F;
+            const float g0 = gout[i0], g1 = gout[i0 + st], g2 = gout[i0 + 2 * st], g3 = gout[i0 + 3 * st];
+            const float y0 = y[i0], y1 = y[i0 + st], y2 = y[i0 + 2 * st], y3 = y[i0 + 3 * st];
+            a0 += g0; a1 += g1;
+            b0 += g0 * ((y0 - mean) * r);
+            b1 += g1 * ((y1 - mean) * r);
+            a0 += g2; a1 += g3;
+            b0 += g2 * ((y2 - mean) * r);
+            b1 += g3 * ((y3 - mean) * r);
+        }
         for (; rr + lanes < r_end; rr += 2 * lanes) {
             const size_t i0 = ((size_t)g * rows + rr) * F + f, i1 = i0 + (size_t)lanes * F;
             const float g0 = gout[i0], g1 = gout[i1], y0 = y[i0], y1 = y[i1];

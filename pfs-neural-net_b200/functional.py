@@ -27,6 +27,10 @@ SAVE_ACT = os.environ.get("PFS_SAVE_ACT", "0") == "1"
 # forward's; PFS_DEFER_AFFINE=0: the EdgeModel applies its norm itself inside a Block too (A/B runs)
 KEEP_TABLES = os.environ.get("PFS_KEEP_TABLES", "1") == "1"
 DEFER_AFFINE = os.environ.get("PFS_DEFER_AFFINE", "1") == "1"
+# PFS_FUSE_BN_STATS=1: the SModel backward, which stores the complete gradient of x_e', also takes the statistics the
+# EdgeModel's BatchNorm backward needs from it (pfs_source_args.edge_bn_stat -> pfs_edge_args.bn_stat_in) instead of a pass
+# of its own over g and x_e'.  OFF by default: measured at C3 it does not pay (profiles/r02_bn_stat_fusion.txt).
+FUSE_BN_STATS = os.environ.get("PFS_FUSE_BN_STATS", "0") == "1"
 
 
 def _want_save(ctx):
@@ -85,14 +89,24 @@ class XeGradBus:
     (`g_x_e_add` of pfs_target_bwd / pfs_source_bwd) and marks it used; `XeFanout.backward` adds whatever was not
     fused, so every combination of used / unused branches gives the same sum.  In a training step autograd runs
     the output tap first, then TModel, then SModel, and nothing is left for it to add."""
-    __slots__ = ("g_o", "g_t", "o_used", "t_used")
+    __slots__ = ("g_o", "g_t", "o_used", "t_used", "edge_beta", "stat", "stat_for")
 
     def __init__(self):
+        self.edge_beta = None        # EdgeModel norm.bias when that norm runs in train mode (set by Block.forward)
+        self.stat = self.stat_for = None
         self.clear()
 
     def clear(self):
         self.g_o = self.g_t = None
         self.o_used = self.t_used = False
+
+    def take_stats(self, g):
+        """BatchNorm-backward statistics of `g` if the SModel backward took them while it stored exactly this tensor."""
+        st, key = self.stat, self.stat_for
+        self.stat = self.stat_for = None
+        if st is not None and key == (g.data_ptr(), g._version, tuple(g.shape)):
+            return st
+        return None
 
     def addend_for_target(self, like):
         if (self.g_o is not None and not self.o_used and self.g_o.numel() == like.numel()
@@ -155,7 +169,7 @@ class EdgeFunction(torch.autograd.Function):
     """EdgeModel (reference src/gnn.py:73-101) -> pfs_edge_fwd / pfs_edge_bwd."""
 
     @staticmethod
-    def forward(ctx, topo, training, normed, x_s, x_t, x_e, u, w1, b1, w2, b2, gamma, beta, rm, rv, nbt, defer=None):
+    def forward(ctx, topo, training, normed, x_s, x_t, x_e, u, w1, b1, w2, b2, gamma, beta, rm, rv, nbt, defer=None, bus=None):
         """`defer`: a dict handed in by Block.forward.  When the module is normed the BatchNorm affine is NOT applied here:
         the returned tensor holds the pre-norm z, defer["affine"] the per-graph (scale, shift), and the next consumer
         (SourceFunction with edge_affine=...) normalises the rows in place while it reads them."""
@@ -183,6 +197,7 @@ class EdgeFunction(torch.autograd.Function):
             _abi.check(lib.pfs_edge_fwd(ct.byref(a)), "pfs_edge_fwd")
         if deferred:
             defer["affine"] = bn_save
+        ctx.bus = bus
         ctx.topo, ctx.training, ctx.normed = topo, training, normed
         ctx.buffers = (rm, rv)
         ctx.save_for_backward(x_s, x_t, x_e, u, w1, b1, w2, b2, gamma, beta, out, bn_save, act, tab_s, tab_t)
@@ -205,7 +220,8 @@ class EdgeFunction(torch.autograd.Function):
         rm, rv = ctx.buffers
         named = dict(x_s=x_s, x_t=x_t, x_e=x_e, u=u, w1=w1, b1=b1, w2=w2, b2=b2, gamma=gamma, beta=beta,
                      running_mean=rm, running_var=rv, x_e_out=out, bn_save=bn_save, act_save=act, g_out=g,
-                     table_s=tab_s, table_t=tab_t)
+                     table_s=tab_s, table_t=tab_t,
+                     bn_stat_in=ctx.bus.take_stats(g) if (ctx.bus is not None and ctx.normed and ctx.training) else None)
         named.update(gr)
         ws = _fill_common(a, topo, G, F, named)
         a.training, a.normed, a.eps, a.momentum = int(ctx.training), int(ctx.normed), BN_EPS, BN_MOMENTUM
@@ -214,7 +230,7 @@ class EdgeFunction(torch.autograd.Function):
             _abi.check(lib.pfs_edge_bwd(ct.byref(a)), "pfs_edge_bwd")
         del ws
         return (None, None, None, gr["g_x_s"], gr["g_x_t"], gr["g_x_e"], gr["g_u"], gr["g_w1"], gr["g_b1"],
-                gr["g_w2"], gr["g_b2"], gr["g_gamma"], gr["g_beta"], None, None, None, None)
+                gr["g_w2"], gr["g_b2"], gr["g_gamma"], gr["g_beta"], None, None, None, None, None)
 
 
 class SourceFunction(torch.autograd.Function):
@@ -279,6 +295,15 @@ class SourceFunction(torch.autograd.Function):
                      y_pre=y_pre, bn_save=bn_save, act_save=act, msg_save=msg, g_out=g)
         add = ctx.bus.addend_for_source(x_e) if ctx.bus is not None else None
         named.update(gr, g_x_e_add=add)
+        # the stored g_x_e is the complete gradient of x_e' when the other two branches were fused in: its BatchNorm-backward
+        # statistics for the EdgeModel ride along (EdgeFunction.backward checks that it receives exactly this tensor)
+        stat = None
+        bus = ctx.bus
+        if (FUSE_BN_STATS and bus is not None and bus.edge_beta is not None and bus.o_used and bus.t_used
+                and bus.edge_beta.is_cuda and bus.edge_beta.dtype == torch.float32):
+            t = topo.struct(G, F)
+            stat = torch.empty(G * lib.pfs_stat_tiles(ct.byref(t)), 2 * F, device=dev, dtype=torch.float32)
+            named.update(edge_bn_shift=bus.edge_beta.detach().contiguous(), edge_bn_stat=stat)
         a = _abi.SourceArgs()
         ws = _fill_common(a, topo, G, F, named)
         a.training, a.normed, a.eps, a.momentum = int(ctx.training), int(ctx.normed), BN_EPS, BN_MOMENTUM
@@ -286,6 +311,9 @@ class SourceFunction(torch.autograd.Function):
             a.stream = _stream(dev)
             _abi.check(lib.pfs_source_bwd(ct.byref(a)), "pfs_source_bwd")
         del ws
+        if stat is not None:
+            g_e = gr["g_x_e"]
+            bus.stat, bus.stat_for = stat, (g_e.data_ptr(), g_e._version, tuple(g_e.shape))
         return (None, None, None, gr["g_x_s"], gr["g_x_t"], gr["g_x_e"], gr["g_u"], gr["g_w1"], gr["g_b1"],
                 gr["g_w2"], gr["g_b2"], gr["g_w3"], gr["g_b3"], gr["g_w4"], gr["g_b4"], gr["g_gamma"], gr["g_beta"],
                 None, None, None, None, None)

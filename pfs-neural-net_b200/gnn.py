@@ -161,7 +161,8 @@ class EdgeModel(MLP):
         topo = get_topology(edge_index, x_s.shape[1], x_t.shape[1])
         normed, gamma, beta, rm, rv, nbt = _norm_tensors(self)
         out = pf.EdgeFunction.apply(topo, self.training, normed, x_s, x_t, edge_attr, u, self[0].weight, self[0].bias,
-                                    self[2].weight, self[2].bias, gamma, beta, rm, rv, nbt, getattr(self, "_defer", None))
+                                    self[2].weight, self[2].bias, gamma, beta, rm, rv, nbt, getattr(self, "_defer", None),
+                                    getattr(self, "_xe_bus", None))
         return out[0] if single else out
 
 
@@ -275,21 +276,29 @@ class Block(torch.nn.Module):
         defer = None
         if (hasattr(self, "edge_model") and hasattr(self, "s_model") and x_e.is_cuda and x_e.dtype == torch.float32):
             defer = {}
+        # fp32 path: the three gradients of x_e' (SModel, TModel, the output) are added up inside the backward
+        # kernels instead of by autograd (functional.XeGradBus); the values are the same sum.  The SModel backward, which
+        # stores that sum, also takes the statistics the EdgeModel's BatchNorm backward needs from it.
+        bus = None
+        if (torch.is_grad_enabled() and x_e.is_cuda and x_e.dtype == torch.float32
+                and hasattr(self, "s_model") and hasattr(self, "t_model")):
+            bus = pf.XeGradBus()
+            if hasattr(self, "edge_model") and isinstance(self.edge_model.norm, torch.nn.Module) and self.edge_model.training:
+                bus.edge_beta = self.edge_model.norm.bias
         if hasattr(self, "edge_model"):
             self.edge_model._defer = defer
+            self.edge_model._xe_bus = bus
             try:
                 x_e = self.edge_model(x_s, x_t, edge_index, x_e, x_u)
             finally:
                 self.edge_model._defer = None
+                self.edge_model._xe_bus = None
         edge_affine = defer.pop("affine", None) if defer else None
-        # fp32 path: the three gradients of x_e' (SModel, TModel, the output) are added up inside the backward
-        # kernels instead of by autograd (functional.XeGradBus); the values are the same sum
-        bus = None
         x_e_s = x_e_t = x_e
-        if (torch.is_grad_enabled() and x_e.requires_grad and x_e.is_cuda and x_e.dtype == torch.float32
-                and hasattr(self, "s_model") and hasattr(self, "t_model")):
-            bus = pf.XeGradBus()
+        if bus is not None and x_e.requires_grad:
             x_e_s, x_e_t, x_e = pf.XeFanout.apply(x_e, bus)
+        else:
+            bus = None
         try:
             if hasattr(self, "s_model"):
                 self.s_model._xe_bus = bus
