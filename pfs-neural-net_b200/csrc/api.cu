@@ -369,19 +369,32 @@ int reduce_partials(const float* partial, int ncta, int pstride, int poff, int n
     PFS_LAUNCH_CHECK("k_reduce_partials");
     return PFS_OK;
 }
-// builder for k_reduce_multi
+// builder for k_reduce_multi: segments of any number of partial buffers, one launch
 struct Reducer {
     ReduceList rl{};
+    const float* cur = nullptr;
+    int cur_ncta = 0, cur_pstride = 0;
+    bool overflow = false;
+    void source(const float* partial, int ncta, int pstride) { cur = partial; cur_ncta = ncta; cur_pstride = pstride; }
     void add(int poff, int n, int cols, float* out, int ldo, int coff) {
         if (!out || n <= 0) return;
-        rl.seg[rl.nseg++] = ReduceSeg{poff, n, cols, ldo, coff, out};
+        if (rl.nseg >= kMaxReduceSegs) { overflow = true; return; }
+        rl.seg[rl.nseg++] = ReduceSeg{cur, cur_ncta, cur_pstride, poff, n, cols, ldo, coff, out};
         rl.total += n;
     }
-    int run(const float* partial, int ncta, int pstride, cudaStream_t st) {
+    int run(cudaStream_t st) {
+        if (overflow) return fail(PFS_ERR_UNSUPPORTED, "too many reduction segments in one call");
         if (rl.nseg == 0) return PFS_OK;
-        k_reduce_multi<<<(rl.total + 31) / 32, 32 * kReduceSlices, 0, st>>>(partial, ncta, pstride, rl);
+        k_reduce_multi<<<(rl.total + 31) / 32, 32 * kReduceSlices, 0, st>>>(rl);
         PFS_LAUNCH_CHECK("k_reduce_partials");
+        rl = ReduceList{};
         return PFS_OK;
+    }
+    int run(const float* partial, int ncta, int pstride, cudaStream_t st) {   // single-buffer form
+        for (int q = 0; q < rl.nseg; ++q) {
+            rl.seg[q].partial = partial; rl.seg[q].ncta = ncta; rl.seg[q].pstride = pstride;
+        }
+        return run(st);
     }
 };
 
@@ -406,22 +419,25 @@ int outer_graphs(const float* a, const float* b, int G, int J, int K, float* out
     PFS_LAUNCH_CHECK("k_outer_graphs");
     return PFS_OK;
 }
-// dW[:, coff:coff+K] = D^T X and (optionally) db = column sums of D, over N rows
+// dW[:, coff:coff+K] = D^T X, (optionally) db = column sums of D and (optionally) dx = D . W[:, coff:coff+K], over N rows
+// of a node table's gradient D, in ONE pass over D (the input gradient used to be a k_node_linear_bwd launch of its own)
+// The fixed-order sums of the CTA partials are queued on the caller's Reducer (scratch_partial must stay untouched until
+// the caller runs it).
 template <int J, int K, int TJ, int TK>
-int outer_rows(const float* D, const float* X, long long N, float* scratch_partial, float* dW, int ldo, int coff,
-               float* db, cudaStream_t st) {
+int outer_rows(Reducer& rd, const float* D, const float* X, long long N, float* scratch_partial, float* dW, int ldo, int coff,
+               float* db, cudaStream_t st, const float* W = nullptr, float* dx = nullptr) {
     constexpr size_t smem = outer_rows_smem<J, K, TJ, TK>();
-    auto kern = k_outer_rows<J, K, TJ, TK>;
+    if (N == 0) return PFS_OK;
+    auto kern = dx ? k_outer_rows<J, K, TJ, TK, true> : k_outer_rows<J, K, TJ, TK, false>;
     PFS_TRY(allow_smem(kern, smem));
     const long long tiles = (N + kTile - 1) / kTile;
     const int grid = persistent_grid(kern, smem, tiles);
     constexpr int pstride = J * K + J;
-    kern<<<grid, kThreads, smem, st>>>(D, X, N, scratch_partial, pstride);
+    kern<<<grid, kThreads, smem, st>>>(D, X, N, scratch_partial, pstride, W, ldo, coff, dx);
     PFS_LAUNCH_CHECK("k_outer_rows");
-    Reducer rd;
+    rd.source(scratch_partial, grid, pstride);
     rd.add(0, J * K, K, dW, ldo, coff);
     if (db) rd.add(J * K, J, J, db, J, 0);
-    PFS_TRY(rd.run(scratch_partial, grid, pstride, st));
     return PFS_OK;
 }
 // class-side sums: dense -> second stage over per-tile partials; CSR -> class-sorted segment sums
@@ -614,6 +630,7 @@ int edge_bwd_impl(const pfs_edge_args& a, const Topo& tp) {
     float* tot = ws.f((size_t)tp.G * H);
     float* wpart = ws.f((size_t)grid * pstride);
     float* opart = ws.f((size_t)kMaxCtas * (H * F + H));
+    float* opart2 = ws.f((size_t)((tp.G * tp.T + kTile - 1) / kTile + 1) * (H * F + H));     // class table: few row tiles
     float* wstage = ws.f(kConstFloats);
     if (!ws.ok) return fail(PFS_ERR_WORKSPACE, "edge_bwd: workspace too small (%zu B)", a.workspace_bytes);
     {
@@ -659,18 +676,16 @@ int edge_bwd_impl(const pfs_edge_args& a, const Topo& tp) {
     } else {
         PFS_LAUNCH_CHECK("k_edge_bwd");
     }
-    {
-        Reducer rd;
-        rd.add(0, H * F, F, a.g_w1, H, 2 * F);
-        rd.add(H * F, F * H, H, a.g_w2, H, 0);
-        rd.add(2 * H * F, F, F, a.g_b2, F, 0);
-        PFS_TRY(rd.run(wpart, grid, pstride, st));
-    }
+    Reducer rd;                       // all the final sums of this call go out in one launch at its end
+    rd.source(wpart, grid, pstride);
+    rd.add(0, H * F, F, a.g_w1, H, 2 * F);
+    rd.add(H * F, F * H, H, a.g_w2, H, 0);
+    rd.add(2 * H * F, F, F, a.g_b2, F, 0);
     PFS_TRY(class_sums(tp, stage, H, dPt, cscs, st));
-    PFS_TRY((node_linear_bwd<F, H>(dPs, (long long)tp.G * tp.S, a.w1, H, 0, a.g_x_s, st)));
-    PFS_TRY((node_linear_bwd<F, H>(dPt, (long long)tp.G * tp.T, a.w1, H, F, a.g_x_t, st)));
-    PFS_TRY((outer_rows<H, F, 8, F / 2>(dPs, a.x_s, (long long)tp.G * tp.S, opart, a.g_w1, H, 0, nullptr, st)));
-    PFS_TRY((outer_rows<H, F, 8, F / 2>(dPt, a.x_t, (long long)tp.G * tp.T, opart, a.g_w1, H, F, nullptr, st)));
+    // node-table backward, one pass per table: g_x_s = dPs . W1_s, dW1_s += dPs^T x_s (the same for the class table)
+    PFS_TRY((outer_rows<H, F, 8, F / 2>(rd, dPs, a.x_s, (long long)tp.G * tp.S, opart, a.g_w1, H, 0, nullptr, st, a.w1, a.g_x_s)));
+    PFS_TRY((outer_rows<H, F, 8, F / 2>(rd, dPt, a.x_t, (long long)tp.G * tp.T, opart2, a.g_w1, H, F, nullptr, st, a.w1, a.g_x_t)));
+    PFS_TRY(rd.run(st));
     PFS_TRY(colsum_graph(dPt, tp.T, H, tp.G, tot, st));
     PFS_TRY(colsum_all(tot, tp.G, H, 0, H, a.g_b1, st));
     PFS_TRY(outer_graphs(tot, a.u, tp.G, H, F, a.g_w1, H, 3 * F, st));
@@ -864,13 +879,11 @@ int source_bwd_impl(const pfs_source_args& a, const Topo& tp) {
             PFS_LAUNCH_CHECK("k_source_node_bwd");
         }
     }
-    {
-        Reducer rd;
-        rd.add(0, J * K9, K9, a.g_w3, J, 0);
-        rd.add(J * K9, F * J, J, a.g_w4, J, 0);
-        rd.add(J * K9 + F * J, F, F, a.g_b4, F, 0);
-        PFS_TRY(rd.run(wpn, gridn, pstride_n, st));
-    }
+    Reducer rd;                       // all the final sums of this call go out in one launch at its end
+    rd.source(wpn, gridn, pstride_n);
+    rd.add(0, J * K9, K9, a.g_w3, J, 0);
+    rd.add(J * K9, F * J, J, a.g_w4, J, 0);
+    rd.add(J * K9 + F * J, F, F, a.g_b4, F, 0);
     k_class_reduce<<<dim3((J + 127) / 128, tp.G), 128, 0, st>>>(tot3p, ntn, J, tot3);
     PFS_LAUNCH_CHECK("k_class_reduce(tot3)");
     PFS_TRY(colsum_all(tot3, tp.G, J, 0, J, a.g_b3, st));
@@ -884,16 +897,13 @@ int source_bwd_impl(const pfs_source_args& a, const Topo& tp) {
         ke<<<gride, kThreads, smem_e, st>>>(p);
         PFS_LAUNCH_CHECK("k_source_edge_bwd");
     }
-    {
-        Reducer rd;
-        rd.add(0, M * F, F, a.g_w1, M, F);
-        rd.add(M * F, M * M, M, a.g_w2, M, 0);
-        rd.add(M * F + M * M, M, M, a.g_b2, M, 0);
-        PFS_TRY(rd.run(wpe, gride, pstride_e, st));
-    }
+    rd.source(wpe, gride, pstride_e);
+    rd.add(0, M * F, F, a.g_w1, M, F);
+    rd.add(M * F, M * M, M, a.g_w2, M, 0);
+    rd.add(M * F + M * M, M, M, a.g_b2, M, 0);
     PFS_TRY(class_sums(tp, stage, M, dQt, cscs, st));
-    PFS_TRY((node_linear_bwd<F, M>(dQt, (long long)tp.G * tp.T, a.w1, M, 0, a.g_x_t, st)));
-    PFS_TRY((outer_rows<M, F, 4, F / 2>(dQt, a.x_t, (long long)tp.G * tp.T, opart, a.g_w1, M, 0, a.g_b1, st)));
+    PFS_TRY((outer_rows<M, F, 4, F / 2>(rd, dQt, a.x_t, (long long)tp.G * tp.T, opart, a.g_w1, M, 0, a.g_b1, st, a.w1, a.g_x_t)));
+    PFS_TRY(rd.run(st));
     return PFS_OK;
 }
 
@@ -994,8 +1004,9 @@ int target_bwd_impl(const pfs_target_args& a, const Topo& tp) {
         k_target_tail_bwd<<<tp.G, kThreads, smem, st>>>(p);
         PFS_LAUNCH_CHECK("k_target_tail_bwd");
     }
+    Reducer rd;                       // all the final sums of this call go out in one launch at its end
     {
-        Reducer rd;
+        rd.source(gpart, tp.G, ptail);
         rd.add(tail_off_w2(F), M * M, M, a.g_w2, M, 0);
         rd.add(tail_off_b2(F), M, M, a.g_b2, M, 0);
         rd.add(tail_off_w3(F), H * H, H, a.g_w3, H, 0);
@@ -1006,7 +1017,6 @@ int target_bwd_impl(const pfs_target_args& a, const Topo& tp) {
             rd.add(tail_off_gamma(F), F, F, a.g_gamma, F, 0);
             rd.add(tail_off_beta(F), F, F, a.g_beta, F, 0);
         }
-        PFS_TRY(rd.run(gpart, tp.G, ptail, st));
     }
     {
         TableJob jobs[2] = {TableJob{a.x_s, tp.S, 0, -1, a.b1, Rs}, TableJob{}};
@@ -1019,9 +1029,10 @@ int target_bwd_impl(const pfs_target_args& a, const Topo& tp) {
         ke<<<gride, kThreads, SM::bytes, st>>>(p);
         PFS_LAUNCH_CHECK("k_target_edge_bwd");
     }
-    PFS_TRY(reduce_partials(wpe, gride, pstride_e, 0, M * F, F, a.g_w1, M, F, st));
-    PFS_TRY((node_linear_bwd<F, M>(dRs, (long long)tp.G * tp.S, a.w1, M, 0, a.g_x_s, st)));
-    PFS_TRY((outer_rows<M, F, 4, F / 2>(dRs, a.x_s, (long long)tp.G * tp.S, opart, a.g_w1, M, 0, a.g_b1, st)));
+    rd.source(wpe, gride, pstride_e);
+    rd.add(0, M * F, F, a.g_w1, M, F);
+    PFS_TRY((outer_rows<M, F, 4, F / 2>(rd, dRs, a.x_s, (long long)tp.G * tp.S, opart, a.g_w1, M, 0, a.g_b1, st, a.w1, a.g_x_s)));
+    PFS_TRY(rd.run(st));
     return PFS_OK;
 }
 

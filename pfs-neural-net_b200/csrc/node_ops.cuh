@@ -130,21 +130,28 @@ __global__ void __launch_bounds__(kThreads) k_node_linear_bwd(const float* __res
 }
 
 // ------------------------------------------------------------------------------------------
-// dW[j][k] partial = sum over a CTA's rows of D[n][j] * X[n][k]; bias partial = column sums of D.
+// Backward of a node table  P = X . W[:, koff : koff + K]^T  given D = dL/dP, one pass over D:
+//   dW[j][k] partial = sum over a CTA's rows of D[n][j] * X[n][k]; bias partial = column sums of D;
+//   DX: dx[n][k] = sum_j W[j][koff + k] * D[n][j]   (what k_node_linear_bwd computes in a pass of its own).
 // Persistent CTAs over row tiles of kTile rows; partial p of CTA c at out[c * pstride + ...].
 // Layout inside a CTA partial: [J*K] weights (row-major j, k) then [J] column sums.
+// D tiles are staged with 16-byte loads into 16-byte aligned rows (J % 4 == 0), X tiles with 8-byte loads.
 // ------------------------------------------------------------------------------------------
-template <int J, int K, int TJ, int TK>
+template <int J, int K, int TJ, int TK, bool DX>
 __global__ void __launch_bounds__(kThreads) k_outer_rows(const float* __restrict__ D, const float* __restrict__ X,
-                                                          long long N, float* __restrict__ partial, int pstride) {
-    constexpr int LDD = J + 2, LDX = K + 2;
+                                                          long long N, float* __restrict__ partial, int pstride,
+                                                          const float* __restrict__ W, int ldw, int koff,
+                                                          float* __restrict__ dx) {
+    static_assert(J % 4 == 0 && K % 2 == 0, "16-byte rows of D, 8-byte rows of X");
+    constexpr int LDD = J + 4, LDX = K + 2;
     using Acc = OuterAcc<J, K, TJ, TK>;
-    constexpr int kTileFloats = kTile * (LDD + LDX);
-    constexpr int kScratch = Acc::kScratchFloats;
+    constexpr int AD = (TJ % 4 == 0) ? 4 : (TJ % 2 == 0) ? 2 : 1;
+    constexpr int AX = (LDX % 4 == 0 && TK % 4 == 0) ? 4 : (TK % 2 == 0) ? 2 : 1;
     extern __shared__ __align__(16) float sm[];
     float* Ds = sm;
     float* Xs = sm + kTile * LDD;
-    static_assert(kScratch >= 0 && kTileFloats >= 0, "");
+    float* Wo = Xs + kTile * LDX;          // DX: Wo[j * K + k] = W[j][koff + k]
+    if constexpr (DX) load_w_outmajor<K, J>(Wo, W, ldw, koff);
     Acc acc;
     acc.init();
     float colsum = 0.f;  // thread j < J accumulates column j
@@ -152,20 +159,40 @@ __global__ void __launch_bounds__(kThreads) k_outer_rows(const float* __restrict
     for (long long tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
         const long long n0 = tile * kTile;
         const int rows = (int)min((long long)kTile, N - n0);
-        for (int i = threadIdx.x; i < rows * J; i += kThreads) {
-            const int r = i / J, j = i - r * J;
-            Ds[r * LDD + j] = __ldg(D + (n0 + r) * J + j);
-        }
-        for (int i = threadIdx.x; i < rows * K; i += kThreads) {
-            const int r = i / K, k = i - r * K;
-            Xs[r * LDX + k] = __ldg(X + (n0 + r) * K + k);
+        {
+            constexpr int J4 = J / 4, K2 = K / 2;
+            const float4* src = reinterpret_cast<const float4*>(D + n0 * J);
+            for (int i = threadIdx.x; i < rows * J4; i += kThreads) {
+                const int r = i / J4, c = i - r * J4;
+                *reinterpret_cast<float4*>(Ds + r * LDD + 4 * c) = __ldg(src + i);
+            }
+            const float2* srx = reinterpret_cast<const float2*>(X + n0 * K);
+            for (int i = threadIdx.x; i < rows * K2; i += kThreads) {
+                const int r = i / K2, c = i - r * K2;
+                *reinterpret_cast<float2*>(Xs + r * LDX + 2 * c) = __ldg(srx + i);
+            }
         }
         __syncthreads();
-        acc.accumulate(Ds, LDD, Xs, LDX, rows);
+        if constexpr (DX) {
+            if ((int)threadIdx.x < rows) {
+                float dr[J], y[K];
+                lds_row<J>(Ds + threadIdx.x * LDD, dr);
+#pragma unroll
+                for (int k = 0; k < K; ++k) y[k] = 0.f;
+                dense_acc<J, K>(Wo, dr, y);
+                store_row<K>(dx + (n0 + threadIdx.x) * K, y);
+            }
+        }
+        acc.template accumulate<AD, AX>(Ds, LDD, Xs, LDX, rows);
         if (threadIdx.x < J) {
-            float s = 0.f;
-            for (int r = 0; r < rows; ++r) s += Ds[r * LDD + threadIdx.x];
-            colsum += s;
+            float s0 = 0.f, s1 = 0.f;
+            int r = 0;
+            for (; r + 1 < rows; r += 2) {
+                s0 += Ds[r * LDD + threadIdx.x];
+                s1 += Ds[(r + 1) * LDD + threadIdx.x];
+            }
+            if (r < rows) s0 += Ds[r * LDD + threadIdx.x];
+            colsum += s0 + s1;
         }
         __syncthreads();
     }
@@ -175,8 +202,8 @@ __global__ void __launch_bounds__(kThreads) k_outer_rows(const float* __restrict
 }
 template <int J, int K, int TJ, int TK>
 constexpr size_t outer_rows_smem() {
-    constexpr int LDD = J + 2, LDX = K + 2;
-    constexpr int a = kTile * (LDD + LDX);
+    constexpr int LDD = J + 4, LDX = K + 2;
+    constexpr int a = kTile * (LDD + LDX) + J * K;
     constexpr int b = OuterAcc<J, K, TJ, TK>::kScratchFloats;
     return sizeof(float) * (a > b ? a : b);
 }
@@ -192,12 +219,16 @@ __global__ void k_reduce_partials(const float* __restrict__ partial, int ncta, i
     out[(i / cols) * ldo + coff + (i % cols)] = s;
 }
 
-// several reductions of one partial buffer in one launch (fewer latency-bound launches)
+// several reductions in one launch (fewer latency-bound launches): every segment names its own partial buffer, so
+// all the fixed-order final sums of a module call (edge-kernel partials, node-kernel partials, table-gradient
+// partials) go out together at the end of the call
 struct ReduceSeg {
+    const float* partial;
+    int ncta, pstride;
     int poff, n, cols, ldo, coff;
     float* out;
 };
-constexpr int kMaxReduceSegs = 8;
+constexpr int kMaxReduceSegs = 12;
 struct ReduceList {
     ReduceSeg seg[kMaxReduceSegs];
     int nseg, total;
@@ -205,8 +236,7 @@ struct ReduceList {
 // block = kReduceSlices slices x 32 outputs: slice s adds the partials of CTAs s, s + slices, ... (one short
 // dependent chain each instead of one chain over all CTAs), the slices are then added in a fixed order
 constexpr int kReduceSlices = 8;
-__global__ void __launch_bounds__(32 * kReduceSlices) k_reduce_multi(const float* __restrict__ partial, int ncta, int pstride,
-                                                                     const ReduceList rl) {
+__global__ void __launch_bounds__(32 * kReduceSlices) k_reduce_multi(const ReduceList rl) {
     __shared__ float red[kReduceSlices][33];
     const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
     int i = blockIdx.x * 32 + lane;
@@ -218,7 +248,9 @@ __global__ void __launch_bounds__(32 * kReduceSlices) k_reduce_multi(const float
     }
     float s0 = 0.f, s1 = 0.f;        // fixed association: two interleaved chains per slice
     if (live) {
-        const float* p = partial + rl.seg[q].poff + i;
+        const float* p = rl.seg[q].partial + rl.seg[q].poff + i;
+        const int ncta = rl.seg[q].ncta;
+        const size_t pstride = (size_t)rl.seg[q].pstride;
         int c = slice;
         for (; c + kReduceSlices < ncta; c += 2 * kReduceSlices) {
             s0 += p[(size_t)c * pstride];
