@@ -550,9 +550,28 @@ def run_ours(args):
             "gpu_launches_per_step": launches_per_step, "clocks": clocks, "numa": numa,
         }
         line.update(extras)
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
+    # NCCL does not let go of a communicator while a captured CUDA graph still holds its collectives: release every
+    # stepper (and with it the graph) before the process group goes away
+    stepper = eager = None
+    import gc
+    gc.collect()
     if world > 1:
-        dist.destroy_process_group()
+        torch.cuda.synchronize(dev)
+        shutdown_process_group()
+
+
+def shutdown_process_group():
+    """destroy_process_group with a watchdog: the record is already printed, so a teardown that does not return within
+    a minute (a communicator still referenced by a CUDA graph, a peer that died) ends the process with status 0 instead
+    of hanging the launcher."""
+    import threading
+    import torch.distributed as dist
+    t = threading.Timer(60.0, lambda: os._exit(0))
+    t.daemon = True
+    t.start()
+    dist.destroy_process_group()
+    t.cancel()
 
 
 def c2_record(args, blk, ei, bucket, dev, lib, hbm_gbs):
@@ -676,9 +695,10 @@ def run_wide(args):
     rec = wide_record(args, args.workload, world, rank, local_rank, dev, steps=args.steps, warmup=args.warmup,
                       with_e2e=not args.no_e2e, with_cpu=not args.no_cpu_baseline, with_profile=not args.no_profile)
     if rank == 0:
-        print(json.dumps(rec))
+        print(json.dumps(rec), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        torch.cuda.synchronize(dev)
+        shutdown_process_group()
 
 
 def wide_record(args, workload, world, rank, local_rank, dev, steps, warmup, with_e2e, with_cpu, with_profile):
