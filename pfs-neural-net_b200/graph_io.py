@@ -31,11 +31,28 @@ class _Bag:
         self.__dict__.update(state if isinstance(state, dict) else {"_state": state})
 
 
+# What a graph file may reference: the tensor-rebuild machinery of torch.save and plain containers.  Every other
+# global named by the pickle (torch_geometric / the reference's gnn classes, and anything a crafted file might ask
+# for) becomes an inert attribute bag: loading a graph never imports or calls code the file chooses.
+_ALLOWED = {
+    ("collections", "OrderedDict"), ("builtins", "dict"), ("builtins", "list"), ("builtins", "tuple"), ("builtins", "set"),
+    ("builtins", "int"), ("builtins", "float"), ("builtins", "bool"), ("builtins", "str"), ("builtins", "complex"),
+    ("torch", "Size"), ("torch", "device"), ("torch", "dtype"),
+    ("torch._utils", "_rebuild_tensor_v2"), ("torch._utils", "_rebuild_tensor"), ("torch._utils", "_rebuild_parameter"),
+    ("torch._utils", "_rebuild_device_tensor_from_numpy"), ("torch._tensor", "_rebuild_from_type_v2"),
+    ("torch.serialization", "_get_layout"),
+}
+_ALLOWED_TORCH_ATTRS = ("Storage", "Tensor")     # torch.FloatStorage, torch.LongTensor, ...: legacy type tags
+
+
 class _Unpickler(pickle.Unpickler):
     def find_class(self, module, name):
-        if module.split(".")[0] in ("torch_geometric", "gnn", "torch_scatter"):
-            return type(name, (_Bag,), {})
-        return super().find_class(module, name)
+        if (module, name) in _ALLOWED:
+            return super().find_class(module, name)
+        if module == "torch" and (name.endswith(_ALLOWED_TORCH_ATTRS) or hasattr(torch, name) and isinstance(
+                getattr(torch, name), (torch.dtype, torch.layout, torch.memory_format))):
+            return super().find_class(module, name)
+        return type(name, (_Bag,), {"__module__": module})
 
 
 class _PickleModule:

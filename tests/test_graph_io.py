@@ -57,3 +57,22 @@ def test_host_csr_csc_arrays(tmp_path):
     g.edge_index, g.x_e = ei, torch.zeros(E, 4)
     d = torch.load(gio.save_graph(str(tmp_path / "s.pt"), g))
     assert not bool(d["canonical"]) and "csr_rowptr" in d and d["format"] == gio.FORMAT
+
+
+def test_crafted_graph_file_executes_nothing(tmp_path):
+    """A pickle may name any importable callable; the loader maps everything outside its allow-list (tensor rebuild
+    helpers, plain containers) to an inert attribute bag, so a crafted graph file runs no code."""
+    marker = tmp_path / "pwned"
+
+    class Evil:
+        def __reduce__(self):
+            import os as _os
+            return (_os.system, ("touch %s" % marker,))
+
+    g = gio.make_graph(torch.rand(3, 2), 4, 4)
+    payload = {"edge_index": g.edge_index, "x_s": g.x_s, "x_t": g.x_t, "x_e": g.x_e, "x_u": g.x_u, "extra": Evil()}
+    p = str(tmp_path / "evil.pt")
+    torch.save(payload, p)
+    h = gio.load_graph(p)                       # loads the tensors ...
+    assert torch.equal(h.edge_index, g.edge_index)
+    assert not marker.exists()                  # ... and never called os.system
