@@ -217,15 +217,6 @@ int make_topo(const pfs_topology& t, Topo& o) {
     return PFS_OK;
 }
 
-// weights -> __constant__ memory on the launch stream (common.cuh: c_w)
-int upload_weights(const PackList& pl, int nfloats, float* staging, cudaStream_t st) {
-    if (nfloats > kConstFloats) return fail(PFS_ERR_UNSUPPORTED, "weights (%d floats) exceed the constant bank", nfloats);
-    k_pack_weights<<<8, 256, 0, st>>>(pl, staging);
-    PFS_LAUNCH_CHECK("k_pack_weights");
-    PFS_CUDA(cudaMemcpyToSymbolAsync(c_w, staging, sizeof(float) * (size_t)nfloats, 0, cudaMemcpyDeviceToDevice, st));
-    return PFS_OK;
-}
-
 // message-MLP weights of the SModel / TModel edge kernels (common.cuh: MsgEdgeConst) appended to a pack list
 template <int F>
 void add_msg_weights(PackList& pl, const float* w1, const float* w2, const float* b2) {
@@ -361,12 +352,6 @@ int node_linear_bwd(const float* d, long long N, const float* W, int ldw, int ko
     if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
     k_node_linear_bwd<K, J, false><<<(int)blocks, kThreads, 0, st>>>(d, N, W, ldw, koff, dx);
     PFS_LAUNCH_CHECK("k_node_linear_bwd");
-    return PFS_OK;
-}
-int reduce_partials(const float* partial, int ncta, int pstride, int poff, int n, int cols, float* out, int ldo,
-                    int coff, cudaStream_t st) {
-    k_reduce_partials<<<(n + 127) / 128, 128, 0, st>>>(partial, ncta, pstride, poff, n, cols, out, ldo, coff);
-    PFS_LAUNCH_CHECK("k_reduce_partials");
     return PFS_OK;
 }
 // builder for k_reduce_multi: segments of any number of partial buffers, one launch
