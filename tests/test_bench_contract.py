@@ -59,3 +59,26 @@ def test_cpu_arm_reference_and_port_compute_the_same_step():
         if k.endswith("bias") and ".norm." not in k:      # a bias in front of a train-mode BatchNorm: analytically zero gradient,
             scale = max(scale, ref_grads[k[:-4] + "weight"].abs().max().item())     # both hold round-off on the weight's scale
         assert (p.grad - ref_grads[k]).abs().max().item() <= 2e-4 * max(scale, 1e-3), k
+
+
+def _teardown_worker(rank, world, port):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    import bench
+    import torch
+    t = torch.ones(3)
+    dist.all_reduce(t)
+    assert float(t[0]) == world
+    bench.shutdown_process_group()           # returns (the watchdog is cancelled) and leaves no initialised group behind
+    assert not dist.is_initialized()
+
+
+def test_process_group_teardown_returns_on_every_rank():
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_teardown_worker, args=(2, port), nprocs=2, join=True)
