@@ -63,3 +63,52 @@ def test_single_process_bucket_is_a_noop():
     g = lin.weight.grad.clone()
     dp.GradBucket(lin.parameters()).all_reduce()
     assert torch.equal(lin.weight.grad, g)
+
+
+def _block_worker(rank, world, port, out):
+    """DP over graphs with the Block's real parameter set: every rank runs its share of the graphs (the CPU oracle does the
+    arithmetic on the module's own parameters, so `.grad` lands where the product path puts it), one flat-bucket
+    all-reduce; the result must equal the single-process sum over all graphs."""
+    from oracle import block_oracle as bo
+    from pfs_neural_net_b200 import gnn
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    F, S, T, G = 4, 9, 5, 6
+    torch.manual_seed(100 + rank)                        # different initial weights per rank ...
+    blk = gnn.Block(F)
+    dp.broadcast_parameters(blk)                         # ... until rank 0's are broadcast
+    ei = bo.complete_bipartite(S, T)
+    g = torch.Generator().manual_seed(5)
+    ins = [torch.randn(G, S, F, generator=g), torch.randn(G, T, F, generator=g), torch.randn(G, S * T, F, generator=g),
+           torch.randn(G, 1, F, generator=g)]
+    ups = [torch.randn(t.shape, generator=g) for t in ins]
+
+    def run(graphs):
+        for p in blk.parameters():
+            p.grad = None
+        state = dict(blk.named_parameters())
+        state.update(dict(blk.named_buffers()))
+        for i in graphs:
+            outs = bo.block(state, "", ei, ins[0][i], ins[1][i], ins[2][i], ins[3][i], training=True, buffers={})
+            torch.autograd.backward(list(outs), [u[i] for u in ups])
+        return {k: (None if p.grad is None else p.grad.clone()) for k, p in blk.named_parameters()}
+
+    full = run(range(G))                                 # every rank can compute the whole batch: the expected sum
+    run(dp.shard_graphs(G, rank, world))
+    bucket = dp.GradBucket(blk.parameters())
+    bucket.all_reduce()
+    ok = True
+    for k, p in blk.named_parameters():
+        scale = max(full[k].abs().max().item(), 1e-6)
+        ok &= (p.grad - full[k]).abs().max().item() <= 1e-4 * max(scale, full[k[:-4] + "weight"].abs().max().item()
+                                                                  if k.endswith("bias") and ".norm." not in k else scale)
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_block_gradients_over_two_ranks_equal_the_single_process_sum():
+    world = 2
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_block_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+        assert dict(out) == {0: True, 1: True}
